@@ -260,16 +260,15 @@ def lk_track(prev_pyr, next_pyr, prev_pts, guess_pts, win: int = 15, max_iter: i
             dif = F32(A11 - A22)
             rad = F32(F32(dif * dif) + F32(F32(F32(4.0) * A12) * A12))
             min_eig = F32(F32(F32(A22 + A11) - F32(np.sqrt(rad))) / F32(2 * win * win))
-            if min_eig < F32(min_eig_thr) or D < FLT_EPSILON:
+            if float(min_eig) < float(min_eig_thr) or D < FLT_EPSILON:   # float vs double threshold
                 if level == 0:
                     status[i] = 0
                 continue
             D = F32(F32(1.0) / D)
+            stored_x, stored_y = nx, ny                 # nextPts[i] as stored before the loop
             nx = F32(nx - half)
             ny = F32(ny - half)
             pdx = pdy = F32(0)
-            stored_x = F32(nx + half)
-            stored_y = F32(ny + half)
             for j in range(max_iter):
                 inx = int(np.floor(nx))
                 iny = int(np.floor(ny))
@@ -322,8 +321,9 @@ def undistort_radtan(pts, intr, dist, R=None):
     p = pts.astype(np.float64).reshape(-1, 2)
     fx, fy, cx, cy = (float(v) for v in intr)
     k1, k2, p1, p2 = (float(v) for v in dist[:4])
-    x0 = (p[:, 0] - cx) / fx
-    y0 = (p[:, 1] - cy) / fy
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    x0 = (p[:, 0] - cx) * ifx
+    y0 = (p[:, 1] - cy) * ify
     x, y = x0.copy(), y0.copy()
     for _ in range(5):
         r2 = x * x + y * y
@@ -336,8 +336,8 @@ def undistort_radtan(pts, intr, dist, R=None):
         R = np.asarray(R, dtype=np.float64)
         X = R[0, 0] * x + R[0, 1] * y + R[0, 2]
         Y = R[1, 0] * x + R[1, 1] * y + R[1, 2]
-        Wv = R[2, 0] * x + R[2, 1] * y + R[2, 2]
-        x, y = X / Wv, Y / Wv
+        Wv = 1.0 / (R[2, 0] * x + R[2, 1] * y + R[2, 2])
+        x, y = X * Wv, Y * Wv
     return np.stack([x, y], axis=1).astype(out_dtype)
 
 

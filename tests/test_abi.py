@@ -1,0 +1,91 @@
+"""CPU-side checks of the drop-in boundary: libavb.so loads, exports every symbol include/avb.h declares,
+struct layouts agree, and there is NO CPU fallback (context creation fails loudly without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, 'include', 'avb.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(avb_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, 'include', 'avb.h')).read()
+    for needle in ('pipeline.py:46-150', 'stereo_matcher.py:33-115', 'feature_tracker.py:102-108',
+                   'camera_model.py:24-47', 'pyramid_builder.py:22-48', 'feature_adder.py:64'):
+        assert needle in src
+
+
+def test_library_exports_every_declared_symbol():
+    from image_processing import _native
+    lib = _native.load()
+    names = _declared_functions()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(names) == set(_native.EXPORTS)
+    assert lib.avb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from image_processing import _native
+    assert C.sizeof(_native.AvbFrameHeader) == 48
+    # 14 int32 + 4 double + 4*4 double + 2*9 double
+    assert C.sizeof(_native.AvbConfig) == 14 * 4 + (4 + 16 + 18) * 8
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present; the no-device path cannot be exercised here')
+    from image_processing import _native
+    from oracle.configs import config_default
+    with pytest.raises(RuntimeError, match='no CUDA device|AVB|avb_create'):
+        _native.Context(config_default(), 752, 480)
+    from image_processing import ImageProcessor
+    from synth_euroc import SlidingTextureStream
+    ip = ImageProcessor(config_default())
+    with pytest.raises(RuntimeError):
+        ip.stereo_callback(SlidingTextureStream(n_frames=1).frame(0))
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'uav-airvision_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, f
+                assert 'import cv2' not in text, f'{f}: the product path must not lean on cv2'
+
+
+def test_imu_processor_matches_port():
+    """Host-side gyro integration (stays in Python) against the oracle port, incl. the window quirks (B13)."""
+    from image_processing import IMUProcessor
+    from oracle.configs import config_default
+    from oracle.pipeline_port import FrontEndPort
+    from synth_euroc import img_msg, imu_msg
+    cfg = config_default()
+    a = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    b = FrontEndPort.__new__(FrontEndPort)
+    T0, T1 = np.linalg.inv(cfg.T_imu_cam0), np.linalg.inv(cfg.T_imu_cam1)
+    b.R_cam0_imu, b.R_cam1_imu, b.imu_buffer = T0[:3, :3], T1[:3, :3], []
+    g = np.random.default_rng(0)
+    msgs = [imu_msg(10.0 + i * 0.005, g.normal(0, 0.3, 3), np.zeros(3)) for i in range(60)]
+    for m in msgs[:45]:
+        a.imu_callback(m)
+        b.imu_buffer.append(m)
+    for t_prev, t_curr in ((10.0, 10.05), (10.05, 10.1), (10.1, 10.15), (10.15, 10.6)):
+        a.cam0_prev_img_msg, a.cam0_curr_img_msg = img_msg(t_prev, None), img_msg(t_curr, None)
+        Ra0, Ra1 = a.integrate_imu_data()
+        Rb0, Rb1 = b._integrate_imu(t_prev, t_curr)
+        assert np.array_equal(Ra0, Rb0) and np.array_equal(Ra1, Rb1)
+        assert len(a.imu_buffer) == len(b.imu_buffer)
+    assert np.array_equal(Ra0, np.eye(3))          # last window has no end message: identity, no trim

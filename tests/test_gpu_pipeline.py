@@ -1,0 +1,154 @@
+"""GPU parity, end to end: ImageProcessor.stereo_callback (one CUDA-graph launch per frame) against
+(a) golden dumps of the UNMODIFIED reference and (b) the oracle port run live on the same stream."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.configs import FrontEndConfig, config_c3
+from oracle.driver import run_stream
+from oracle.pipeline_port import FrontEndPort
+from synth_euroc import SlidingTextureStream
+from tools.make_golden import CASES
+
+
+def _run_gpu(cfg, stream, use_graph=True):
+    from image_processing import ImageProcessor
+    ip = ImageProcessor(cfg, use_graph=use_graph)
+    frames = []
+
+    def on_frame(k, msg, fm):
+        cell, life, p0, p1 = ip.context.features(0)
+        hdr, ids, meas = ip.context.result(0)
+        frames.append(dict(ids=ids.copy(), cell=cell, life=life, p0=p0, p1=p1, pub=meas.copy(),
+                           has_new=int(hdr['has_new']), counters=dict(ip.num_features),
+                           n_fast=int(hdr['n_fast'])))
+
+    msgs = run_stream(ip, stream, on_frame=on_frame)
+    nid = ip.next_feature_id
+    ip.context.close()
+    return msgs, frames, nid
+
+
+def _compare(frames, ref_frames, tol=0.01):
+    """ids / cells / lifetimes identical, positions within tol px.  Returns the worst deviation."""
+    worst = 0.0
+    for k, (f, r) in enumerate(zip(frames, ref_frames)):
+        assert np.array_equal(f['ids'], r['ids']), f'frame {k}: feature ids differ'
+        assert np.array_equal(f['cell'], r['cell']), f'frame {k}: grid cells differ'
+        assert np.array_equal(f['life'], r['life']), f'frame {k}: lifetimes differ'
+        if len(f['ids']):
+            d = max(np.abs(f['p0'].astype(np.float64) - r['p0']).max(), np.abs(f['p1'].astype(np.float64) - r['p1']).max())
+            worst = max(worst, d)
+            assert d <= tol, f'frame {k}: tracked position off by {d} px'
+            assert np.abs(f['pub'] - r['pub']).max() <= 1e-4, f'frame {k}: published normalized coords'
+    return worst
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_pipeline_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    gr, gc, gmin, gmax, skw = CASES[name]
+    cfg = FrontEndConfig(grid_row=gr, grid_col=gc, grid_min=gmin, grid_max=gmax)
+    msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**skw))
+    n = int(g['n_frames'][0])
+    assert len(msgs) == n
+    ref = [dict(ids=g[f'f{k}_ids'], cell=g[f'f{k}_cell'], life=g[f'f{k}_life'], p0=g[f'f{k}_p0'],
+                p1=g[f'f{k}_p1'], pub=g[f'f{k}_pub']) for k in range(n)]
+    worst = _compare(frames, ref)
+    exact = all(np.array_equal(f['p0'].astype(np.float64), r['p0']) and np.array_equal(f['p1'].astype(np.float64), r['p1'])
+                for f, r in zip(frames, ref))
+    print(f'{name}: worst position deviation {worst:.3g} px over {n} frames; bit-exact positions: {exact}')
+    for k, (fm, f) in enumerate(zip(msgs, frames)):
+        assert fm.timestamp == g[f'f{k}_ts'][0]
+        assert [x.id for x in fm.features] == list(g[f'f{k}_pub_ids'])
+        assert f['has_new'] == int(g[f'f{k}_u0_is_f64'][0]) or len(fm.features) == 0
+        if k > 0:
+            c = f['counters']
+            assert [c.get('before_tracking', -1), c.get('after_tracking', -1), c.get('after_matching', -1),
+                    c.get('after_ransac', -1)] == list(g[f'f{k}_counters'])
+    assert nid == int(g['next_feature_id'][0])
+
+
+def _port_frames(cfg, stream):
+    fe = FrontEndPort(cfg, backend='cv2')
+    out = []
+
+    def on_frame(k, msg, fm):
+        pub = np.array([[f.u0, f.v0, f.u1, f.v1] for f in fm.features], np.float64).reshape(-1, 4)
+        out.append(dict(ids=fe.ids.copy(), cell=fe.cell.copy(), life=fe.life.copy(), p0=fe.p0.astype(np.float64),
+                        p1=fe.p1.astype(np.float64), pub=pub))
+
+    run_stream(fe, stream, on_frame=on_frame)
+    return out, fe.next_feature_id
+
+
+def test_pipeline_vs_port_c2_25_frames_with_and_without_graph():
+    cfg = FrontEndConfig(grid_row=6, grid_col=10)
+    kw = dict(n_frames=25, seed=7, sigma=2.2, drift=(1.6, 0.7), gyro=(0.01, -0.02, 0.03), noise=1.0)
+    ref, ref_nid = _port_frames(cfg, SlidingTextureStream(**kw))
+    for use_graph in (True, False):
+        msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**kw), use_graph=use_graph)
+        worst = _compare(frames, ref)
+        print(f'C2 25 frames graph={use_graph}: worst deviation {worst:.3g} px; features/frame {len(frames[-1]["ids"])}')
+        assert nid == ref_nid
+        assert len(frames[-1]['ids']) > 250
+
+
+def test_pipeline_vs_port_c3_stress():
+    cfg = config_c3()
+    kw = dict(width=1280, height=1024, n_frames=5, seed=11, sigma=1.8, drift=(1.2, 0.9))
+    ref, ref_nid = _port_frames(cfg, SlidingTextureStream(**kw))
+    msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**kw))
+    worst = _compare(frames, ref)
+    print(f'C3: worst deviation {worst:.3g} px; features/frame {[len(f["ids"]) for f in frames]}')
+    assert nid == ref_nid
+    assert len(frames[-1]['ids']) > 800
+
+
+def test_empty_and_textureless_stream():
+    """Flat images: no corners, nothing tracked, empty feature lists every frame (reference behaviour:
+    empty inputs short-circuit, stereo_matcher.py:44-45, feature_tracker.py:97-98)."""
+    from image_processing import ImageProcessor
+    from synth_euroc import img_msg, stereo_msg
+    cfg = FrontEndConfig()
+    ip = ImageProcessor(cfg)
+    flat = np.full((480, 752), 90, np.uint8)
+    for k in range(3):
+        ts = 5.0 + 0.05 * k
+        fm = ip.stereo_callback(stereo_msg(ts, flat, flat, img_msg(ts, flat), img_msg(ts, flat)))
+        assert fm.timestamp == ts and fm.features == []
+    assert ip.next_feature_id == 0
+    assert all(len(c) == 0 for c in ip.prev_features)
+    ip.context.close()
+
+
+def test_multi_stream_context_equals_single_streams():
+    """S streams processed by the same launches give exactly what S separate contexts give."""
+    from image_processing import _native
+    cfg = FrontEndConfig(grid_row=6, grid_col=10)
+    streams = [SlidingTextureStream(n_frames=6, seed=20 + s, sigma=2.0 + 0.3 * s, drift=(1.0 + 0.2 * s, 0.5)) for s in range(3)]
+    singles = []
+    for st in streams:
+        c = _native.Context(cfg, 752, 480, num_streams=1)
+        rows = []
+        for k in range(st.n):
+            f = st.frame(k)
+            c.process([f.cam0_image], [f.cam1_image])
+            hdr, ids, meas = c.result(0)
+            rows.append((ids.copy(), meas.copy(), c.features(0)))
+        singles.append(rows)
+        c.close()
+    c = _native.Context(cfg, 752, 480, num_streams=3)
+    for k in range(6):
+        fr = [st.frame(k) for st in streams]
+        c.process([f.cam0_image for f in fr], [f.cam1_image for f in fr])
+        for s in range(3):
+            hdr, ids, meas = c.result(s)
+            assert np.array_equal(ids, singles[s][k][0])
+            assert np.array_equal(meas, singles[s][k][1])
+            for a, b in zip(c.features(s), singles[s][k][2]):
+                assert np.array_equal(a, b)
+    c.close()

@@ -1,0 +1,674 @@
+// C-ABI of libavb (include/avb.h): context, memory, CUDA-graph frame path, per-stage entry points.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "avb_common.cuh"
+
+static thread_local std::string g_create_error;
+
+struct avb_ctx {
+    avb_config cfg;
+    Geom g;
+    DevState d;
+    PyrMaps maps;
+    cudaStream_t st = nullptr, st_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    uint8_t* h_in = nullptr;        // pinned: one input block (images + H)
+    uint8_t* h_out = nullptr;       // pinned: S result blocks
+    size_t out_stride = 0;
+    int parity = 1;                 // parity of the current frame; the first frame lands in parity 0
+    bool first_frame = true;
+    bool have_frame = false;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // steady-state frame, per parity, host-input variant
+    cudaGraphExec_t graph_dev[2] = {nullptr, nullptr}; // same, device-input variant (no H2D of images)
+    std::vector<void*> allocs;
+    // scratch for the per-stage entry points
+    float2 *s_a = nullptr, *s_b = nullptr, *s_c = nullptr;
+    uint8_t* s_st = nullptr;
+    double *s_da = nullptr, *s_db = nullptr, *s_R = nullptr;
+    int s_cap = 0;
+    std::string err;
+    float last_ms = 0.f;
+};
+
+static int fail(avb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(c, AVB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(avb_ctx* c, T** p, size_t count, bool zero = true) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, std::max<size_t>(count * sizeof(T), 256));
+    if (e != cudaSuccess) return e;
+    c->allocs.push_back(v);
+    if (zero) e = cudaMemset(v, 0, std::max<size_t>(count * sizeof(T), 256));
+    *p = static_cast<T*>(v);
+    return e;
+}
+
+extern "C" int avb_abi_version(void) { return AVB_ABI_VERSION; }
+
+extern "C" const char* avb_last_error(const avb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(avb_ctx* c, EncodeTiledFn enc, CUtensorMap* m, void* base, int w, int h, int nimg, size_t pitch,
+                    size_t img_stride, int bw, int bh) {
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nimg};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, AVB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%dx%d pitch %zu", (int)r, w, h, nimg, pitch);
+    return AVB_OK;
+}
+
+static int build_graphs(avb_ctx* c);
+
+extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
+    avb_ctx* c = nullptr;
+    if (!cfg || !out) return fail(c, AVB_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(c, AVB_E_NO_DEVICE, "no CUDA device: libavb has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(c, AVB_E_INVALID, "device %d out of range", cfg->device);
+    if (cfg->win_size != AVB_WIN) return fail(c, AVB_E_INVALID, "only patch_size 15 is compiled (got %d)", cfg->win_size);
+    if (cfg->width % 16 || cfg->width < 64 || cfg->height < 64 || cfg->width > 4096 || cfg->height > 4095)
+        return fail(c, AVB_E_INVALID, "width must be a multiple of 16, 64 <= size <= 4096 (got %dx%d)", cfg->width, cfg->height);
+    if (cfg->max_level < 0 || cfg->max_level >= AVB_MAX_LEVELS) return fail(c, AVB_E_INVALID, "pyramid_levels must be 0..%d", AVB_MAX_LEVELS - 1);
+    if ((cfg->width >> cfg->max_level) < 32 || (cfg->height >> cfg->max_level) < 32)
+        return fail(c, AVB_E_INVALID, "coarsest pyramid level would be smaller than 32 px");
+    if (cfg->grid_row < 1 || cfg->grid_col < 1 || cfg->grid_row * cfg->grid_col > AVB_MAX_CELLS)
+        return fail(c, AVB_E_INVALID, "grid must have 1..%d cells", AVB_MAX_CELLS);
+    if (cfg->grid_max_feature_num < 1 || cfg->grid_max_feature_num > AVB_MAX_CAP || cfg->grid_min_feature_num < 0 ||
+        cfg->grid_min_feature_num > cfg->grid_max_feature_num)
+        return fail(c, AVB_E_INVALID, "need 0 <= grid_min <= grid_max <= %d", AVB_MAX_CAP);
+    if (cfg->num_streams < 1 || cfg->num_streams > 4096) return fail(c, AVB_E_INVALID, "num_streams must be 1..4096");
+    if (cfg->fast_threshold < 1 || cfg->fast_threshold > 254) return fail(c, AVB_E_INVALID, "fast_threshold must be 1..254");
+    if (cfg->ransac) return fail(c, AVB_E_INVALID, "two-point RANSAC is not part of the reference path (all-ones stub); ransac=1 unsupported");
+    if ((size_t)cfg->width * cfg->height >= (1u << 24)) return fail(c, AVB_E_INVALID, "image too large for the 24-bit scan index");
+
+    c = new avb_ctx();
+    c->cfg = *cfg;
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) {
+        fail(nullptr, AVB_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+        delete c;
+        return AVB_E_CUDA;
+    }
+
+    Geom& g = c->g;
+    memset(&g, 0, sizeof g);
+    g.W = cfg->width;
+    g.H = cfg->height;
+    g.nlev = cfg->max_level + 1;
+    g.S = cfg->num_streams;
+    size_t off = 0;
+    for (int l = 0; l < g.nlev; ++l) {
+        g.lv[l].w = l ? (g.lv[l - 1].w + 1) / 2 : g.W;
+        g.lv[l].h = l ? (g.lv[l - 1].h + 1) / 2 : g.H;
+        g.lv[l].pitch = l ? ((g.lv[l].w + 15) & ~15) : g.W;
+        g.lv[l].off = l ? off : 0;
+        if (l) off += ((size_t)g.lv[l].pitch * g.lv[l].h + 255) & ~(size_t)255;
+    }
+    g.slot_bytes = std::max<size_t>(off, 256);
+    g.rows = cfg->grid_row;
+    g.cols = cfg->grid_col;
+    g.NC = g.rows * g.cols;
+    g.gh = (g.H + g.rows - 1) / g.rows;       // int(np.ceil(h / grid_row))  (B12)
+    g.gw = (g.W + g.cols - 1) / g.cols;
+    g.gmin = cfg->grid_min_feature_num;
+    g.gmax = cfg->grid_max_feature_num;
+    g.NMAX = g.NC * g.gmax;
+    // strict 3x3 NMS: no two keypoints are 8-neighbours -> at most ceil(gw/2)*ceil(gh/2) per cell
+    g.KPC = (((g.gw + 1) / 2) * ((g.gh + 1) / 2) + 3) & ~3;
+    g.fast_thr = cfg->fast_threshold;
+    g.max_iter = std::min(std::max(cfg->max_iteration, 0), 100);
+    g.min_eig = cfg->min_eig_threshold;
+    const double eps = std::min(std::max(cfg->track_precision, 0.0), 10.0);
+    g.eps2 = eps * eps;
+    g.cam0 = {cfg->cam0_intrinsics[0], cfg->cam0_intrinsics[1], cfg->cam0_intrinsics[2], cfg->cam0_intrinsics[3],
+              cfg->cam0_distortion[0], cfg->cam0_distortion[1], cfg->cam0_distortion[2], cfg->cam0_distortion[3]};
+    g.cam1 = {cfg->cam1_intrinsics[0], cfg->cam1_intrinsics[1], cfg->cam1_intrinsics[2], cfg->cam1_intrinsics[3],
+              cfg->cam1_distortion[0], cfg->cam1_distortion[1], cfg->cam1_distortion[2], cfg->cam1_distortion[3]};
+    memcpy(g.R01, cfg->R_cam0_to_cam1, sizeof g.R01);
+    memcpy(g.E, cfg->essential, sizeof g.E);
+    g.epi_thr = cfg->stereo_threshold * (4.0 / (2 * g.cam0.fx + 2 * g.cam0.fy));
+    if (g.NMAX > 8192) {
+        delete c;
+        return fail(nullptr, AVB_E_INVALID, "grid_num*grid_max = %d exceeds 8192", g.NMAX);
+    }
+
+#define CKC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e2_ = (call);                                                                   \
+        if (e2_ != cudaSuccess) {                                                                   \
+            fail(nullptr, AVB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e2_), __FILE__, __LINE__); \
+            avb_destroy(c);                                                                         \
+            return AVB_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+    DevState& d = c->d;
+    memset(&d, 0, sizeof d);
+    const size_t S = g.S, NM = g.NMAX, NC = g.NC;
+    const size_t inb = in_block_bytes(g);
+    CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->st_side, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CKC(cudaEventCreate(&c->ev_t0));
+    CKC(cudaEventCreate(&c->ev_t1));
+    CKC(dalloc(c, &d.in[0], inb));
+    CKC(dalloc(c, &d.in[1], inb));
+    CKC(dalloc(c, &d.pyr, S * SLOTS_PER_STREAM * g.slot_bytes));
+    CKC(dalloc(c, &d.kp_key, S * NC * g.KPC));
+    CKC(dalloc(c, &d.kp_count, S * NC));
+    CKC(dalloc(c, &d.kp_p1, S * NC * g.KPC));
+    CKC(dalloc(c, &d.kp_ok, S * NC * g.KPC));
+    for (int p = 0; p < 2; ++p) {
+        CKC(dalloc(c, &d.grid[p].ids, S * NM));
+        CKC(dalloc(c, &d.grid[p].life, S * NM));
+        CKC(dalloc(c, &d.grid[p].p0, S * NM));
+        CKC(dalloc(c, &d.grid[p].p1, S * NM));
+        CKC(dalloc(c, &d.grid[p].fresh, S * NM));
+        CKC(dalloc(c, &d.grid[p].count, S * NC));
+    }
+    CKC(dalloc(c, &d.t_p0, S * NM));
+    CKC(dalloc(c, &d.t_p1, S * NM));
+    CKC(dalloc(c, &d.t_cell, S * NM));
+    CKC(dalloc(c, &d.c_key, S * NM));
+    CKC(dalloc(c, &d.c_src, S * NM));
+    CKC(dalloc(c, &d.c_p1, S * NM));
+    CKC(dalloc(c, &d.c_ok, S * NM));
+    CKC(dalloc(c, &d.c_count, S * NC));
+    CKC(dalloc(c, &d.n_new, S * NC));
+    CKC(dalloc(c, &d.new_rank, S * NM));
+    CKC(dalloc(c, &d.next_id, S));
+    CKC(dalloc(c, &d.counters, S * 8));
+    CKC(dalloc(c, &d.frame_index, S));
+    c->out_stride = out_stride_bytes(g.NMAX);
+    CKC(dalloc(c, &d.out, S * c->out_stride));
+    CKC(cudaHostAlloc((void**)&c->h_in, inb, cudaHostAllocDefault));
+    CKC(cudaHostAlloc((void**)&c->h_out, S * c->out_stride, cudaHostAllocDefault));
+    memset(c->h_in, 0, inb);
+    memset(c->h_out, 0, S * c->out_stride);
+    {   // identity H until the caller provides rotations
+        double* H = reinterpret_cast<double*>(c->h_in + in_images_bytes(g));
+        for (size_t s = 0; s < S; ++s) H[s * 9 + 0] = H[s * 9 + 4] = H[s * 9 + 8] = 1.0;
+    }
+
+    // dynamic shared memory of the bookkeeping kernels
+    const size_t sel_smem = ((size_t)g.KPC + g.NMAX) * 4;
+    if (sel_smem > 200 * 1024) {
+        avb_destroy(c);
+        return fail(nullptr, AVB_E_INVALID, "grid cell too large for the selection kernel (%zu B shared)", sel_smem);
+    }
+    if (avb_set_smem_limits(sel_smem, (size_t)g.NMAX * 8) != 0) {
+        avb_destroy(c);
+        return fail(nullptr, AVB_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+    }
+
+    // TMA descriptors
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        avb_destroy(c);
+        return fail(nullptr, AVB_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    }
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+    const size_t img_bytes = (size_t)g.W * g.H;
+    for (int p = 0; p < 2; ++p) {
+        int r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 144, 68);
+        if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 80, 24);
+        if (r != AVB_OK) {
+            g_create_error = c->err;
+            avb_destroy(c);
+            return r;
+        }
+    }
+    for (int l = 1; l < g.nlev - 1; ++l) {
+        int r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
+                         g.slot_bytes, 144, 68);
+        if (r != AVB_OK) {
+            g_create_error = c->err;
+            avb_destroy(c);
+            return r;
+        }
+    }
+    CKC(cudaStreamSynchronize(c->st));
+    CKC(cudaDeviceSynchronize());
+    if (cfg->use_graph) {
+        int r = build_graphs(c);
+        if (r != AVB_OK) {
+            g_create_error = c->err;
+            avb_destroy(c);
+            return r;
+        }
+    }
+    *out = c;
+    return AVB_OK;
+}
+
+extern "C" void avb_destroy(avb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (int p = 0; p < 2; ++p) {
+        if (c->graph[p]) cudaGraphExecDestroy(c->graph[p]);
+        if (c->graph_dev[p]) cudaGraphExecDestroy(c->graph_dev[p]);
+    }
+    for (void* p : c->allocs) cudaFree(p);
+    for (void* p : {(void*)c->s_a, (void*)c->s_b, (void*)c->s_c, (void*)c->s_st, (void*)c->s_da, (void*)c->s_db, (void*)c->s_R})
+        if (p) cudaFree(p);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_side) cudaStreamDestroy(c->st_side);
+    delete c;
+}
+
+extern "C" int avb_capacity(const avb_ctx* c) { return c ? c->g.NMAX : 0; }
+extern "C" int avb_num_cells(const avb_ctx* c) { return c ? c->g.NC : 0; }
+extern "C" uint8_t* avb_input_staging(avb_ctx* c) { return c ? c->h_in : nullptr; }
+extern "C" void* avb_cuda_stream(avb_ctx* c) { return c ? (void*)c->st : nullptr; }
+
+extern "C" int avb_reset(avb_ctx* c) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->st));
+    const Geom& g = c->g;
+    for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(c->d.grid[p].count, 0, (size_t)g.S * g.NC * sizeof(int), c->st));
+    CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)g.S * sizeof(long long), c->st));
+    CK(cudaMemsetAsync(c->d.frame_index, 0, (size_t)g.S * sizeof(int), c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->parity = 1;
+    c->first_frame = true;
+    c->have_frame = false;
+    return AVB_OK;
+}
+
+// ---- the frame ------------------------------------------------------------------------------------
+
+// Enqueues the kernel chain of one frame on c->st (FAST runs on a forked branch).  Inputs of parity p must
+// already be (or be ordered before this on c->st) in d.in[p].
+static void enqueue_chain(avb_ctx* c, int p, bool first) {
+    const Geom& g = c->g;
+    const DevState& d = c->d;
+    cudaEventRecord(c->ev_fork, c->st);
+    cudaStreamWaitEvent(c->st_side, c->ev_fork, 0);
+    launch_clear_frame(g, d, c->st_side);
+    launch_fast(g, d, c->maps, p, c->st_side);
+    cudaEventRecord(c->ev_join, c->st_side);
+    launch_pyramid(g, d, c->maps, p, c->st);
+    if (first) {
+        cudaStreamWaitEvent(c->st, c->ev_join, 0);
+        launch_stereo_buckets(g, d, p, c->st);
+        launch_select(g, d, p, 1, c->st);
+    } else {
+        launch_track(g, d, p, c->st);
+        cudaStreamWaitEvent(c->st, c->ev_join, 0);
+        launch_select(g, d, p, 0, c->st);
+        launch_stereo_candidates(g, d, p, c->st);
+    }
+    launch_grid_update(g, d, p, first ? 1 : 0, c->st);
+    launch_publish(g, d, p, c->st);
+}
+
+extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
+    if (!c) return 0;
+    // clear, fast, (nlev-1) pyramid levels, track, select, stereo_candidates, grid_update, publish
+    return 2 + (c->g.nlev - 1) + 5;
+}
+
+static int build_graphs(avb_ctx* c) {
+    const Geom& g = c->g;
+    const size_t inb = in_block_bytes(g);
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int p = 0; p < 2; ++p) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+            if (variant == 0)   // device variant: the block was placed by a D2D copy ordered before the launch
+                cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st);
+            enqueue_chain(c, p, false);
+            cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
+            CK(cudaStreamEndCapture(c->st, &graph));
+            cudaGraphExec_t exec = nullptr;
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            (variant == 0 ? c->graph : c->graph_dev)[p] = exec;
+        }
+    }
+    return AVB_OK;
+}
+
+extern "C" size_t avb_input_block_bytes(const avb_ctx* c) { return c ? in_block_bytes(c->g) : 0; }
+extern "C" size_t avb_input_rotation_offset(const avb_ctx* c) { return c ? in_images_bytes(c->g) : 0; }
+
+extern "C" int avb_fill_rotations(const avb_ctx* c, uint8_t* block, const double* R_p_c0) {
+    // H = K R_p_c K^-1 (feature_tracker.py:166-171) in double: (K @ R) @ inv(K), inv(K) in closed form
+    if (!c || !block) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    double* H = reinterpret_cast<double*>(block + in_images_bytes(g));
+    const double fx = g.cam0.fx, fy = g.cam0.fy, cx = g.cam0.cx, cy = g.cam0.cy;
+    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    const double Ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
+    for (int s = 0; s < g.S; ++s) {
+        double* h = H + (size_t)s * 9;
+        if (!R_p_c0) {
+            for (int i = 0; i < 9; ++i) h[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            continue;
+        }
+        const double* R = R_p_c0 + (size_t)s * 9;
+        double KR[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) KR[i * 3 + j] = K[i * 3] * R[j] + K[i * 3 + 1] * R[3 + j] + K[i * 3 + 2] * R[6 + j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) h[i * 3 + j] = KR[i * 3] * Ki[j] + KR[i * 3 + 1] * Ki[3 + j] + KR[i * 3 + 2] * Ki[6 + j];
+    }
+    return AVB_OK;
+}
+
+static int run_frame(avb_ctx* c, int variant /*0 host images in h_in, 1 device images already copied*/, bool wait) {
+    const Geom& g = c->g;
+    const int p = c->parity ^ 1;
+    const size_t inb = in_block_bytes(g);
+    CK(cudaEventRecord(c->ev_t0, c->st));
+    if (!c->first_frame && c->cfg.use_graph) {
+        CK(cudaGraphLaunch((variant == 0 ? c->graph : c->graph_dev)[p], c->st));
+    } else {
+        if (variant == 0) CK(cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st));
+        enqueue_chain(c, p, c->first_frame);
+        CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev_t1, c->st));
+    c->parity = p;
+    c->first_frame = false;
+    c->have_frame = true;
+    if (wait) {
+        CK(cudaStreamSynchronize(c->st));
+        cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1);
+    }
+    return AVB_OK;
+}
+
+extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
+                                 const double* R_p_c0) {
+    if (!c) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->cfg.device));
+    if (img0 && img1) {
+        if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
+        const size_t ib = (size_t)g.W * g.H;
+        for (int s = 0; s < g.S; ++s) {
+            for (int cam = 0; cam < 2; ++cam) {
+                const uint8_t* src = cam ? img1[s] : img0[s];
+                if (!src) return fail(c, AVB_E_INVALID, "null image pointer (stream %d cam %d)", s, cam);
+                uint8_t* dst = c->h_in + ((size_t)s * 2 + cam) * ib;
+                if (stride == g.W)
+                    memcpy(dst, src, ib);
+                else
+                    for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
+            }
+        }
+    }
+    avb_fill_rotations(c, c->h_in, R_p_c0);
+    return run_frame(c, 0, true);
+}
+
+extern "C" int avb_enqueue_frame_device(avb_ctx* c, const uint8_t* d_block) {
+    if (!c || !d_block) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    const int p = c->parity ^ 1;
+    CK(cudaMemcpyAsync(c->d.in[p], d_block, in_block_bytes(c->g), cudaMemcpyDeviceToDevice, c->st));
+    return run_frame(c, 1, false);
+}
+
+extern "C" int avb_sync(avb_ctx* c) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaStreamSynchronize(c->st));
+    cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1);
+    return AVB_OK;
+}
+
+extern "C" int avb_process_frame_device(avb_ctx* c, const uint8_t* d_block) {
+    int r = avb_enqueue_frame_device(c, d_block);
+    if (r != AVB_OK) return r;
+    return avb_sync(c);
+}
+
+extern "C" int avb_last_frame_ms(avb_ctx* c, float* ms) {
+    if (!c || !ms) return AVB_E_INVALID;
+    *ms = c->last_ms;
+    return AVB_OK;
+}
+
+extern "C" int avb_get_result(avb_ctx* c, int s, const avb_frame_header** hdr, const int64_t** ids, const double** meas) {
+    if (!c || s < 0 || s >= c->g.S) return AVB_E_INVALID;
+    if (!c->have_frame) return fail(c, AVB_E_STATE, "no frame processed yet");
+    uint8_t* b = c->h_out + (size_t)s * c->out_stride;
+    if (hdr) *hdr = reinterpret_cast<const avb_frame_header*>(b);
+    if (ids) *ids = reinterpret_cast<const int64_t*>(out_ids(b));
+    if (meas) *meas = out_meas(b, c->g.NMAX);
+    return AVB_OK;
+}
+
+extern "C" int avb_get_features(avb_ctx* c, int s, int32_t* cell, int32_t* lifetime, float* cam0_xy, float* cam1_xy) {
+    if (!c || s < 0 || s >= c->g.S) return AVB_E_INVALID;
+    if (!c->have_frame) return fail(c, AVB_E_STATE, "no frame processed yet");
+    uint8_t* b = c->h_out + (size_t)s * c->out_stride;
+    const size_t n = (size_t) reinterpret_cast<const avb_frame_header*>(b)->n_features;
+    const int nm = c->g.NMAX;
+    if (cell) memcpy(cell, out_cell(b, nm), n * 4);
+    if (lifetime) memcpy(lifetime, out_life(b, nm), n * 4);
+    if (cam0_xy) memcpy(cam0_xy, out_p0(b, nm), n * 8);
+    if (cam1_xy) memcpy(cam1_xy, out_p1(b, nm), n * 8);
+    return AVB_OK;
+}
+
+// ---- per-stage entry points --------------------------------------------------------------------------
+
+static int api_slot(const avb_ctx* c, int slot) {       // 0 cur cam0, 1 cur cam1, 2 prev cam0, 3 prev cam1
+    const int cam = slot & 1, par = (slot & 2) ? (c->parity ^ 1) : c->parity;
+    return SLOT(cam, par);
+}
+
+extern "C" int avb_advance(avb_ctx* c) {
+    if (!c) return AVB_E_INVALID;
+    c->parity ^= 1;
+    return AVB_OK;
+}
+
+extern "C" int avb_upload_stereo(avb_ctx* c, int s, const uint8_t* img0, const uint8_t* img1, int stride) {
+    if (!c || s < 0 || s >= c->g.S || !img0 || !img1) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
+    CK(cudaSetDevice(c->cfg.device));
+    const size_t ib = (size_t)g.W * g.H;
+    for (int cam = 0; cam < 2; ++cam) {
+        uint8_t* dst = c->d.in[c->parity] + ((size_t)s * 2 + cam) * ib;
+        CK(cudaMemcpy2DAsync(dst, g.W, cam ? img1 : img0, stride, g.W, g.H, cudaMemcpyHostToDevice, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
+}
+
+extern "C" int avb_build_pyramids(avb_ctx* c) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    launch_pyramid(c->g, c->d, c->maps, c->parity, c->st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
+}
+
+extern "C" int avb_download_level(avb_ctx* c, int s, int slot, int level, uint8_t* out, int* w, int* h) {
+    if (!c || s < 0 || s >= c->g.S || slot < 0 || slot > 3 || level < 0 || level >= c->g.nlev) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->cfg.device));
+    const int sl = api_slot(c, slot);
+    const uint8_t* src = level ? pyr_slot(c->d, g, s, sl) + g.lv[level].off : level0_ptr(c->d, g, s, sl);
+    if (w) *w = g.lv[level].w;
+    if (h) *h = g.lv[level].h;
+    if (out) {
+        CK(cudaMemcpy2DAsync(out, g.lv[level].w, src, g.lv[level].pitch, g.lv[level].w, g.lv[level].h, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
+    return AVB_OK;
+}
+
+extern "C" int avb_fast_detect(avb_ctx* c, int s, const uint8_t* mask, int32_t* xs, int32_t* ys, int32_t* responses, int* n) {
+    if (!c || s < 0 || s >= c->g.S || !n) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->cfg.device));
+    launch_clear_frame(g, c->d, c->st);
+    launch_fast(g, c->d, c->maps, c->parity, c->st);
+    CK(cudaGetLastError());
+    std::vector<int> counts(g.NC);
+    std::vector<unsigned> keys((size_t)g.NC * g.KPC);
+    CK(cudaMemcpyAsync(counts.data(), c->d.kp_count + (size_t)s * g.NC, g.NC * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(keys.data(), c->d.kp_key + (size_t)s * g.NC * g.KPC, keys.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    std::vector<unsigned long long> all;   // (scan index << 8) | response
+    for (int cell = 0; cell < g.NC; ++cell) {
+        if (counts[cell] > g.KPC) return fail(c, AVB_E_CAPACITY, "FAST bucket overflow in cell %d (%d > %d)", cell, counts[cell], g.KPC);
+        for (int j = 0; j < counts[cell]; ++j) {
+            int r, x, y;
+            kp_decode(keys[(size_t)cell * g.KPC + j], g.W, r, x, y);
+            if (mask && !mask[(size_t)y * g.W + x]) continue;
+            all.push_back(((unsigned long long)(y * g.W + x) << 8) | (unsigned)r);
+        }
+    }
+    std::sort(all.begin(), all.end());
+    const int cap = *n;
+    *n = (int)all.size();
+    if ((int)all.size() > cap) return fail(c, AVB_E_CAPACITY, "%zu keypoints > capacity %d", all.size(), cap);
+    for (size_t i = 0; i < all.size(); ++i) {
+        const unsigned lin = (unsigned)(all[i] >> 8);
+        if (xs) xs[i] = lin % g.W;
+        if (ys) ys[i] = lin / g.W;
+        if (responses) responses[i] = (int)(all[i] & 0xff);
+    }
+    return AVB_OK;
+}
+
+static int ensure_scratch(avb_ctx* c, int n) {
+    if (n <= c->s_cap) return AVB_OK;
+    const int cap = std::max(n, 4096);
+    for (void* p : {(void*)c->s_a, (void*)c->s_b, (void*)c->s_c, (void*)c->s_st, (void*)c->s_da, (void*)c->s_db})
+        if (p) cudaFree(p);
+    c->s_a = c->s_b = c->s_c = nullptr;
+    c->s_st = nullptr;
+    c->s_da = c->s_db = nullptr;
+    c->s_cap = 0;
+    CK(cudaMalloc(&c->s_a, cap * sizeof(float2)));
+    CK(cudaMalloc(&c->s_b, cap * sizeof(float2)));
+    CK(cudaMalloc(&c->s_c, cap * sizeof(float2)));
+    CK(cudaMalloc(&c->s_st, cap));
+    CK(cudaMalloc(&c->s_da, cap * 2 * sizeof(double)));
+    CK(cudaMalloc(&c->s_db, cap * 2 * sizeof(double)));
+    if (!c->s_R) CK(cudaMalloc(&c->s_R, 9 * sizeof(double)));
+    c->s_cap = cap;
+    return AVB_OK;
+}
+
+extern "C" int avb_klt_track(avb_ctx* c, int s, int slot_from, int slot_to, const float* prev_xy, const float* guess_xy, int n,
+                             float* out_xy, uint8_t* status) {
+    if (!c || s < 0 || s >= c->g.S || slot_from < 0 || slot_from > 3 || slot_to < 0 || slot_to > 3 || n < 0) return AVB_E_INVALID;
+    if (n == 0) return AVB_OK;
+    if (!prev_xy || !guess_xy || !out_xy || !status) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    int r = ensure_scratch(c, n);
+    if (r != AVB_OK) return r;
+    CK(cudaMemcpyAsync(c->s_a, prev_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->s_b, guess_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    launch_klt_points(c->g, c->d, s, api_slot(c, slot_from), api_slot(c, slot_to), c->s_a, c->s_b, n, c->s_c, c->s_st, c->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_xy, c->s_c, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(status, c->s_st, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
+}
+
+extern "C" int avb_stereo_match(avb_ctx* c, int s, const float* cam0_xy, int n, float* cam1_xy, uint8_t* inlier) {
+    if (!c || s < 0 || s >= c->g.S || n < 0) return AVB_E_INVALID;
+    if (n == 0) return AVB_OK;
+    if (!cam0_xy || !cam1_xy || !inlier) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    int r = ensure_scratch(c, n);
+    if (r != AVB_OK) return r;
+    CK(cudaMemcpyAsync(c->s_a, cam0_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    launch_stereo_points(c->g, c->d, s, c->parity, c->s_a, n, c->s_c, c->s_st, c->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cam1_xy, c->s_c, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(inlier, c->s_st, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
+}
+
+static int undist_common(avb_ctx* c, const double* intr, const double* dist, const double* xy, int n, const double* R,
+                         int f32_io, int distort, double* out) {
+    if (!c || !intr || !dist || n < 0) return AVB_E_INVALID;
+    if (n == 0) return AVB_OK;
+    if (!xy || !out) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    int r = ensure_scratch(c, n);
+    if (r != AVB_OK) return r;
+    const CamModel cam = {intr[0], intr[1], intr[2], intr[3], dist[0], dist[1], dist[2], dist[3]};
+    CK(cudaMemcpyAsync(c->s_da, xy, (size_t)n * 16, cudaMemcpyHostToDevice, c->st));
+    if (R) CK(cudaMemcpyAsync(c->s_R, R, 9 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    launch_undistort(cam, c->s_da, n, c->s_R, R ? 1 : 0, f32_io, distort, c->s_db, c->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->s_db, (size_t)n * 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
+}
+
+extern "C" int avb_undistort_points(avb_ctx* c, const double* intr, const double* dist, const double* xy, int n,
+                                    const double* R, int f32_io, double* out_xy) {
+    return undist_common(c, intr, dist, xy, n, R, f32_io, 0, out_xy);
+}
+extern "C" int avb_distort_points(avb_ctx* c, const double* intr, const double* dist, const double* xy, int n, int f32_io,
+                                  double* out_xy) {
+    return undist_common(c, intr, dist, xy, n, nullptr, f32_io, 1, out_xy);
+}
+
+extern "C" int avb_time_pyramid(avb_ctx* c, int iters, float* ms_avg) {
+    if (!c || iters < 1 || !ms_avg) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaEventRecord(c->ev_t0, c->st));
+    for (int i = 0; i < iters; ++i) launch_pyramid(c->g, c->d, c->maps, c->parity, c->st);
+    CK(cudaEventRecord(c->ev_t1, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+    *ms_avg = ms / iters;
+    return AVB_OK;
+}

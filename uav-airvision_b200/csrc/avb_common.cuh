@@ -1,0 +1,180 @@
+// Shared device-side layout for libavb (sm_100a only).  See DESIGN.md "Data layout in HBM".
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/avb.h"
+
+#define AVB_WIN 15                 // LK window (cfg.patch_size); the lane mapping is built around 15x15
+#define AVB_HALF 7
+#define AVB_MAX_CAP 32             // grid_max_feature_num upper bound (one warp ballots a cell's candidates)
+#define AVB_MAX_CELLS 1024
+
+// Image slots of a stream: slot = cam * 2 + parity (parity = frame index & 1).  Level 0 of a slot is the
+// uploaded image itself inside the input block of that parity; levels >= 1 live in the pyramid arena.
+#define SLOTS_PER_STREAM 4
+#define SLOT(cam, parity) ((cam) * 2 + (parity))
+
+struct LevelGeom {
+    int w, h, pitch;
+    unsigned long long off;        // byte offset inside one pyramid slot (levels >= 1)
+};
+
+// One image pyramid as the LK code sees it.
+struct PyrView {
+    const uint8_t* lv[AVB_MAX_LEVELS];
+};
+
+struct CamModel {
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2;
+};
+
+// Geometry + constants, identical for all streams of a context (kernel parameter, by value).
+struct Geom {
+    int W, H, nlev;
+    LevelGeom lv[AVB_MAX_LEVELS];
+    unsigned long long slot_bytes; // bytes of one pyramid slot (all levels), multiple of 256
+    int S;
+    int rows, cols, NC;            // grid
+    int gh, gw;                    // cell size in px (ceil)
+    int gmin, gmax;                // per-cell min/max feature counts; gmax = slot capacity of a cell
+    int NMAX;                      // NC * gmax
+    int KPC;                       // FAST bucket capacity of one cell
+    int fast_thr;
+    int max_iter;
+    double min_eig;
+    double eps2;                   // (track_precision)^2 in double, like criteria.epsilon
+    CamModel cam0, cam1;
+    double R01[9];                 // R_cam0_to_cam1
+    double E[9];                   // essential
+    double epi_thr;                // stereo_threshold * 4/(2fx+2fy)
+};
+
+// Feature table in grid order: cell c owns slots [c*gmax, c*gmax + count[c]).
+struct GridTable {
+    long long* ids;                // [S][NMAX]
+    int* life;                     // [S][NMAX]
+    float2* p0;                    // [S][NMAX]  cam0 pixel
+    float2* p1;                    // [S][NMAX]  cam1 pixel
+    uint8_t* fresh;                // [S][NMAX]  1 = created this frame
+    int* count;                    // [S][NC]
+};
+
+struct FrameOut {                  // per-stream block in pinned host + mirror on device
+    avb_frame_header hdr;
+    // followed by: int64 ids[NMAX]; double meas[NMAX*4]; int32 cell[NMAX]; int32 life[NMAX];
+    //              float p0[NMAX*2]; float p1[NMAX*2]
+};
+
+__host__ __device__ inline size_t out_stride_bytes(int nmax) {
+    size_t b = sizeof(avb_frame_header) + (size_t)nmax * (8 + 32 + 4 + 4 + 8 + 8);
+    return (b + 255) & ~(size_t)255;
+}
+__host__ __device__ inline long long* out_ids(uint8_t* base) { return (long long*)(base + sizeof(avb_frame_header)); }
+__host__ __device__ inline double* out_meas(uint8_t* base, int nmax) { return (double*)(base + sizeof(avb_frame_header) + (size_t)nmax * 8); }
+__host__ __device__ inline int* out_cell(uint8_t* base, int nmax) { return (int*)(base + sizeof(avb_frame_header) + (size_t)nmax * 40); }
+__host__ __device__ inline int* out_life(uint8_t* base, int nmax) { return (int*)(base + sizeof(avb_frame_header) + (size_t)nmax * 44); }
+__host__ __device__ inline float* out_p0(uint8_t* base, int nmax) { return (float*)(base + sizeof(avb_frame_header) + (size_t)nmax * 48); }
+__host__ __device__ inline float* out_p1(uint8_t* base, int nmax) { return (float*)(base + sizeof(avb_frame_header) + (size_t)nmax * 56); }
+
+// All device buffers of a context (kernel parameter, by value).
+struct DevState {
+    uint8_t* in[2];                // input block per parity: [S][2 cams][H*W] images, then [S][9] doubles (H = K R K^-1)
+    uint8_t* pyr;                  // [S][4 slots][slot_bytes], levels 1..L
+    // FAST buckets
+    unsigned* kp_key;              // [S][NC][KPC]  (response << 24) | (0xFFFFFF - (y*W + x))
+    int* kp_count;                 // [S][NC]
+    float2* kp_p1;                 // [S][NC][KPC]  frame-0 stereo result
+    uint8_t* kp_ok;                // [S][NC][KPC]
+    // feature tables (ping/pong)
+    GridTable grid[2];
+    // tracking scratch, indexed like the previous grid table
+    float2* t_p0;                  // [S][NMAX] tracked cam0 position in the current frame
+    float2* t_p1;                  // [S][NMAX]
+    int* t_cell;                   // [S][NMAX] new cell, -1 = lost
+    // new-feature candidates, [cell][gmax], in descending key order
+    unsigned* c_key;               // [S][NMAX]
+    int* c_src;                    // [S][NMAX] index into the cell's FAST bucket
+    float2* c_p1;                  // [S][NMAX]
+    uint8_t* c_ok;                 // [S][NMAX]
+    int* c_count;                  // [S][NC]
+    int* n_new;                    // [S][NC]  new features given ids this frame (before pruning)
+    uint8_t* new_rank;             // [S][NMAX] rank of a fresh feature among its cell's new ones
+    long long* next_id;            // [S]
+    int* counters;                 // [S][8]: before_tracking, after_tracking, after_matching, n_fast, n_cand
+    uint8_t* out;                  // [S][out_stride] device mirror of the result block
+    int* frame_index;              // [S]
+};
+
+__host__ __device__ inline uint8_t* pyr_slot(const DevState& d, const Geom& g, int s, int slot) {
+    return d.pyr + ((size_t)s * SLOTS_PER_STREAM + slot) * g.slot_bytes;
+}
+__host__ __device__ inline uint8_t* level0_ptr(const DevState& d, const Geom& g, int s, int slot) {
+    return d.in[slot & 1] + ((size_t)s * 2 + (slot >> 1)) * ((size_t)g.W * g.H);
+}
+__host__ __device__ inline size_t in_images_bytes(const Geom& g) {
+    return (((size_t)g.S * 2 * g.W * g.H) + 255) & ~(size_t)255;
+}
+__host__ __device__ inline size_t in_block_bytes(const Geom& g) {
+    return in_images_bytes(g) + (((size_t)g.S * 9 * sizeof(double)) + 255 & ~(size_t)255);
+}
+__host__ __device__ inline const double* frame_H(const DevState& d, const Geom& g, int s, int parity) {
+    return reinterpret_cast<const double*>(d.in[parity] + in_images_bytes(g)) + (size_t)s * 9;
+}
+
+__device__ __forceinline__ PyrView pyr_view(const DevState& d, const Geom& g, int s, int slot) {
+    PyrView v;
+    uint8_t* b = pyr_slot(d, g, s, slot);
+    v.lv[0] = level0_ptr(d, g, s, slot);
+#pragma unroll
+    for (int l = 1; l < AVB_MAX_LEVELS; ++l) v.lv[l] = b + (l < g.nlev ? g.lv[l].off : 0);
+    return v;
+}
+
+__device__ __forceinline__ int refl101(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * n - 2 - i : i;
+}
+
+// FAST keypoint key: larger key = earlier in the reference's ranking
+// (response desc, then row-major scan order; stable sorted(..., reverse=True), Appendix B9).
+__host__ __device__ inline unsigned kp_make_key(int resp, int x, int y, int W) {
+    return ((unsigned)resp << 24) | (0xFFFFFFu - (unsigned)(y * W + x));
+}
+__host__ __device__ inline void kp_decode(unsigned key, int W, int& resp, int& x, int& y) {
+    resp = (int)(key >> 24);
+    unsigned lin = 0xFFFFFFu - (key & 0xFFFFFFu);
+    y = (int)(lin / (unsigned)W);
+    x = (int)(lin % (unsigned)W);
+}
+
+// ---- launchers implemented in the stage files -------------------------------------------
+// TMA views (x, y, image).  Level 0: one map per parity over the input block, image = s*2 + cam.
+// Levels >= 1: one map per level over the arena, image = s*4 + slot.  `fast0` has the FAST box shape.
+struct PyrMaps {
+    CUtensorMap l0[2];
+    CUtensorMap lv[AVB_MAX_LEVELS];
+    CUtensorMap fast0[2];
+};
+
+void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
+void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
+void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
+void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_grid_update(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
+void launch_publish(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st);
+int  avb_set_smem_limits(size_t select_bytes, size_t grid_bytes);   // opt in to > 48 KB dynamic shared memory
+// flat point lists (per-stage entry points)
+void launch_klt_points(const Geom& g, const DevState& d, int s, int slot_from, int slot_to,
+                       const float2* prev, const float2* guess, int n, float2* out, uint8_t* status,
+                       cudaStream_t st);
+void launch_stereo_points(const Geom& g, const DevState& d, int s, int parity, const float2* p0, int n,
+                          float2* p1, uint8_t* ok, cudaStream_t st);
+void launch_undistort(const CamModel& cam, const double* xy, int n, const double* R, int has_R, int f32_io,
+                      int distort, double* out, cudaStream_t st);

@@ -1,0 +1,318 @@
+"""ctypes binding of libavb.so (include/avb.h).  No CPU fallback: if the library or a CUDA device is
+missing, loading / context creation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libavb.so')
+
+EXPORTS = (
+    'avb_abi_version', 'avb_last_error', 'avb_create', 'avb_destroy', 'avb_capacity', 'avb_num_cells',
+    'avb_reset', 'avb_input_staging', 'avb_input_block_bytes', 'avb_input_rotation_offset',
+    'avb_fill_rotations', 'avb_process_frame', 'avb_process_frame_device', 'avb_enqueue_frame_device',
+    'avb_sync', 'avb_get_result', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
+    'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
+    'avb_undistort_points', 'avb_distort_points', 'avb_last_frame_ms', 'avb_kernels_per_frame',
+    'avb_cuda_stream', 'avb_time_pyramid',
+)
+
+
+class AvbConfig(C.Structure):
+    _fields_ = [
+        ('width', C.c_int32), ('height', C.c_int32), ('max_level', C.c_int32), ('win_size', C.c_int32),
+        ('max_iteration', C.c_int32), ('fast_threshold', C.c_int32), ('grid_row', C.c_int32),
+        ('grid_col', C.c_int32), ('grid_min_feature_num', C.c_int32), ('grid_max_feature_num', C.c_int32),
+        ('num_streams', C.c_int32), ('device', C.c_int32), ('use_graph', C.c_int32), ('ransac', C.c_int32),
+        ('track_precision', C.c_double), ('min_eig_threshold', C.c_double), ('stereo_threshold', C.c_double),
+        ('ransac_threshold', C.c_double),
+        ('cam0_intrinsics', C.c_double * 4), ('cam0_distortion', C.c_double * 4),
+        ('cam1_intrinsics', C.c_double * 4), ('cam1_distortion', C.c_double * 4),
+        ('R_cam0_to_cam1', C.c_double * 9), ('essential', C.c_double * 9),
+    ]
+
+
+class AvbFrameHeader(C.Structure):
+    _fields_ = [
+        ('n_features', C.c_int64), ('next_feature_id', C.c_int64),
+        ('before_tracking', C.c_int32), ('after_tracking', C.c_int32), ('after_matching', C.c_int32),
+        ('after_ransac', C.c_int32), ('has_new', C.c_int32), ('n_fast', C.c_int32),
+        ('n_candidates', C.c_int32), ('frame_index', C.c_int32),
+    ]
+
+
+HEADER_DTYPE = np.dtype([
+    ('n_features', '<i8'), ('next_feature_id', '<i8'), ('before_tracking', '<i4'), ('after_tracking', '<i4'),
+    ('after_matching', '<i4'), ('after_ransac', '<i4'), ('has_new', '<i4'), ('n_fast', '<i4'),
+    ('n_candidates', '<i4'), ('frame_index', '<i4')])
+assert HEADER_DTYPE.itemsize == C.sizeof(AvbFrameHeader) == 48
+
+_lib = None
+
+
+def load():
+    """Loads libavb.so (once).  Raises OSError with a build hint when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f'{LIB_PATH} not found: build it with `python uav-airvision_b200/build.py` '
+                      '(nvcc, sm_100a). There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, u8p, f32p, f64p, i32p = C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.avb_abi_version.restype = C.c_int
+    lib.avb_last_error.restype = C.c_char_p
+    lib.avb_last_error.argtypes = [vp]
+    lib.avb_create.argtypes = [C.POINTER(AvbConfig), C.POINTER(vp)]
+    lib.avb_destroy.argtypes = [vp]
+    lib.avb_destroy.restype = None
+    for name in ('avb_capacity', 'avb_num_cells', 'avb_reset', 'avb_sync', 'avb_advance', 'avb_build_pyramids',
+                 'avb_kernels_per_frame'):
+        getattr(lib, name).argtypes = [vp]
+    lib.avb_input_staging.argtypes = [vp]
+    lib.avb_input_staging.restype = C.c_void_p
+    lib.avb_input_block_bytes.argtypes = [vp]
+    lib.avb_input_block_bytes.restype = C.c_size_t
+    lib.avb_input_rotation_offset.argtypes = [vp]
+    lib.avb_input_rotation_offset.restype = C.c_size_t
+    lib.avb_fill_rotations.argtypes = [vp, u8p, f64p]
+    lib.avb_process_frame.argtypes = [vp, vp, vp, ip, f64p]
+    lib.avb_process_frame_device.argtypes = [vp, vp]
+    lib.avb_enqueue_frame_device.argtypes = [vp, vp]
+    lib.avb_get_result.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.avb_get_features.argtypes = [vp, ip, i32p, i32p, f32p, f32p]
+    lib.avb_upload_stereo.argtypes = [vp, ip, u8p, u8p, ip]
+    lib.avb_download_level.argtypes = [vp, ip, ip, ip, u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.avb_fast_detect.argtypes = [vp, ip, u8p, i32p, i32p, i32p, C.POINTER(C.c_int)]
+    lib.avb_klt_track.argtypes = [vp, ip, ip, ip, f32p, f32p, ip, f32p, u8p]
+    lib.avb_stereo_match.argtypes = [vp, ip, f32p, ip, f32p, u8p]
+    lib.avb_undistort_points.argtypes = [vp, f64p, f64p, f64p, ip, f64p, ip, f64p]
+    lib.avb_distort_points.argtypes = [vp, f64p, f64p, f64p, ip, ip, f64p]
+    lib.avb_last_frame_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.avb_cuda_stream.argtypes = [vp]
+    lib.avb_cuda_stream.restype = C.c_void_p
+    lib.avb_time_pyramid.argtypes = [vp, ip, C.POINTER(C.c_float)]
+    if lib.avb_abi_version() != 1:
+        raise OSError('libavb.so ABI version mismatch: rebuild')
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def stereo_geometry(cfg):
+    """R_cam0_to_cam1 and the essential matrix exactly as StereoMatcher forms them
+    (reference stereo_matcher.py:49, 90-91; imu_processor.py:11-17)."""
+    T0 = np.linalg.inv(cfg.T_imu_cam0)
+    T1 = np.linalg.inv(cfg.T_imu_cam1)
+    R0, t0, R1, t1 = T0[:3, :3], T0[:3, 3], T1[:3, :3], T1[:3, 3]
+    R01 = R1.T @ R0
+    t01 = R1.T @ (t0 - t1)
+    x, y, z = t01
+    E = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]]) @ R01
+    return R01, E
+
+
+class Context:
+    """One libavb context = S lock-stepped stereo streams on one CUDA device."""
+
+    def __init__(self, cfg, width, height, num_streams=1, device=0, use_graph=True):
+        lib = load()
+        for k in ('cam0_distortion_model', 'cam1_distortion_model'):
+            if getattr(cfg, k, 'radtan') != 'radtan':
+                raise RuntimeError('libavb implements the radtan model only (EuRoC, config.py:99,116)')
+        ac = AvbConfig()
+        ac.width, ac.height = int(width), int(height)
+        ac.max_level = int(cfg.lk_params['maxLevel'])
+        ws = cfg.lk_params['winSize']
+        if ws[0] != ws[1]:
+            raise RuntimeError('square LK window required')
+        ac.win_size = int(ws[0])
+        crit = cfg.lk_params['criteria']
+        ac.max_iteration, ac.track_precision = int(crit[1]), float(crit[2])
+        ac.min_eig_threshold = float(cfg.lk_params.get('minEigThreshold', 1e-4))
+        ac.fast_threshold = int(cfg.fast_threshold)
+        ac.grid_row, ac.grid_col = int(cfg.grid_row), int(cfg.grid_col)
+        ac.grid_min_feature_num, ac.grid_max_feature_num = int(cfg.grid_min_feature_num), int(cfg.grid_max_feature_num)
+        ac.num_streams, ac.device, ac.use_graph, ac.ransac = int(num_streams), int(device), int(bool(use_graph)), 0
+        ac.stereo_threshold = float(cfg.stereo_threshold)
+        ac.ransac_threshold = float(getattr(cfg, 'ransac_threshold', 3))
+        ac.cam0_intrinsics[:] = [float(v) for v in cfg.cam0_intrinsics]
+        ac.cam0_distortion[:] = [float(v) for v in cfg.cam0_distortion_coeffs[:4]]
+        ac.cam1_intrinsics[:] = [float(v) for v in cfg.cam1_intrinsics]
+        ac.cam1_distortion[:] = [float(v) for v in cfg.cam1_distortion_coeffs[:4]]
+        R01, E = stereo_geometry(cfg)
+        ac.R_cam0_to_cam1[:] = [float(v) for v in R01.reshape(-1)]
+        ac.essential[:] = [float(v) for v in E.reshape(-1)]
+        self._lib = lib
+        self._h = C.c_void_p()
+        rc = lib.avb_create(C.byref(ac), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f'avb_create failed ({rc}): {lib.avb_last_error(None).decode()}')
+        self.width, self.height, self.S = ac.width, ac.height, ac.num_streams
+        self.capacity = lib.avb_capacity(self._h)
+        self.num_cells = lib.avb_num_cells(self._h)
+        self.max_level = ac.max_level
+        self.block_bytes = lib.avb_input_block_bytes(self._h)
+        self.rot_offset = lib.avb_input_rotation_offset(self._h)
+        base = lib.avb_input_staging(self._h)
+        img_bytes = self.S * 2 * self.width * self.height
+        self._staging_block = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(self.block_bytes,))
+        self.staging = self._staging_block[:img_bytes].reshape(self.S, 2, self.height, self.width)
+        self._ident = np.tile(np.eye(3).reshape(-1), self.S)
+        self._views = {}
+
+    # -- lifecycle -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.avb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f'libavb error {rc}: {self._lib.avb_last_error(self._h).decode()}')
+
+    def reset(self):
+        self._ck(self._lib.avb_reset(self._h))
+
+    # -- hot path ----------------------------------------------------------------------------------------
+    def process_staged(self, R_p_c0=None):
+        """One frame from the pinned staging block (caller filled self.staging[s, cam])."""
+        R = self._ident if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_process_frame(self._h, None, None, self.width, _ptr(R)))
+
+    def process(self, imgs0, imgs1, R_p_c0=None):
+        """One frame: imgs0[s], imgs1[s] are (H, W) uint8 arrays (copied into pinned staging)."""
+        for s in range(self.S):
+            self.staging[s, 0] = imgs0[s]
+            self.staging[s, 1] = imgs1[s]
+        self.process_staged(R_p_c0)
+
+    def fill_rotations(self, block, R_p_c0=None):
+        R = None if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_fill_rotations(self._h, _ptr(block), _ptr(R)))
+
+    def process_device(self, d_block_ptr: int):
+        self._ck(self._lib.avb_process_frame_device(self._h, C.c_void_p(d_block_ptr)))
+
+    def enqueue_device(self, d_block_ptr: int):
+        self._ck(self._lib.avb_enqueue_frame_device(self._h, C.c_void_p(d_block_ptr)))
+
+    def sync(self):
+        self._ck(self._lib.avb_sync(self._h))
+
+    def result(self, s=0):
+        """(header record, ids int64[n], meas float64[n,4]) -- views into pinned memory, valid until the
+        next frame."""
+        v = self._views.get(s)
+        if v is None:
+            hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self._ck(self._lib.avb_get_result(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
+            hdr = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(48,)).view(HEADER_DTYPE)
+            ids = np.ctypeslib.as_array(C.cast(ip_, C.POINTER(C.c_int64)), shape=(self.capacity,))
+            meas = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_double)), shape=(self.capacity, 4))
+            v = (hdr, ids, meas)
+            self._views[s] = v
+        hdr, ids, meas = v
+        n = int(hdr['n_features'][0])
+        return hdr[0], ids[:n], meas[:n]
+
+    def features(self, s=0):
+        """Grid-ordered state of stream s: (cell, lifetime, cam0_xy, cam1_xy)."""
+        n = int(self.result(s)[0]['n_features'])
+        cell = np.empty(n, np.int32)
+        life = np.empty(n, np.int32)
+        p0 = np.empty((n, 2), np.float32)
+        p1 = np.empty((n, 2), np.float32)
+        self._ck(self._lib.avb_get_features(self._h, s, _ptr(cell), _ptr(life), _ptr(p0), _ptr(p1)))
+        return cell, life, p0, p1
+
+    def last_frame_ms(self):
+        ms = C.c_float()
+        self._ck(self._lib.avb_last_frame_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def kernels_per_frame(self):
+        return self._lib.avb_kernels_per_frame(self._h)
+
+    def cuda_stream(self):
+        return self._lib.avb_cuda_stream(self._h)
+
+    def time_pyramid(self, iters=20):
+        ms = C.c_float()
+        self._ck(self._lib.avb_time_pyramid(self._h, iters, C.byref(ms)))
+        return ms.value
+
+    # -- per-stage entry points -----------------------------------------------------------------------------
+    def upload(self, img0, img1, s=0):
+        img0 = np.ascontiguousarray(img0, dtype=np.uint8)
+        img1 = np.ascontiguousarray(img1, dtype=np.uint8)
+        if img0.shape != (self.height, self.width) or img1.shape != (self.height, self.width):
+            raise RuntimeError(f'image shape {img0.shape} does not match the context ({self.height}, {self.width})')
+        self._ck(self._lib.avb_upload_stereo(self._h, s, _ptr(img0), _ptr(img1), self.width))
+
+    def advance(self):
+        self._ck(self._lib.avb_advance(self._h))
+
+    def build_pyramids(self):
+        self._ck(self._lib.avb_build_pyramids(self._h))
+
+    def download_level(self, slot, level, s=0):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self._lib.avb_download_level(self._h, s, slot, level, None, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        self._ck(self._lib.avb_download_level(self._h, s, slot, level, _ptr(out), C.byref(w), C.byref(h)))
+        return out
+
+    def fast_detect(self, mask=None, s=0):
+        cap = (self.width * self.height) // 4 + 16
+        xs, ys, rs = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32)
+        n = C.c_int(cap)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self._lib.avb_fast_detect(self._h, s, _ptr(m), _ptr(xs), _ptr(ys), _ptr(rs), C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
+
+    def klt_track(self, slot_from, slot_to, prev_xy, guess_xy, s=0):
+        prev = np.ascontiguousarray(prev_xy, dtype=np.float32).reshape(-1, 2)
+        guess = np.ascontiguousarray(guess_xy, dtype=np.float32).reshape(-1, 2)
+        n = len(prev)
+        out = np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.uint8)
+        self._ck(self._lib.avb_klt_track(self._h, s, slot_from, slot_to, _ptr(prev), _ptr(guess), n, _ptr(out), _ptr(st)))
+        return out, st
+
+    def stereo_match(self, cam0_xy, s=0):
+        p0 = np.ascontiguousarray(cam0_xy, dtype=np.float32).reshape(-1, 2)
+        n = len(p0)
+        p1 = np.zeros((n, 2), np.float32)
+        ok = np.zeros(n, np.uint8)
+        self._ck(self._lib.avb_stereo_match(self._h, s, _ptr(p0), n, _ptr(p1), _ptr(ok)))
+        return p1, ok.astype(bool)
+
+    def undistort_ex(self, intrinsics, distortion, xy, R=None, f32_io=False):
+        p = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros_like(p)
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        D = np.ascontiguousarray(np.asarray(distortion, dtype=np.float64)[:4])
+        Rm = None if R is None else np.ascontiguousarray(R, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_undistort_points(self._h, _ptr(K), _ptr(D), _ptr(p), len(p), _ptr(Rm), int(f32_io), _ptr(out)))
+        return out
+
+    def distort_ex(self, intrinsics, distortion, xy, f32_io=False):
+        p = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros_like(p)
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        D = np.ascontiguousarray(np.asarray(distortion, dtype=np.float64)[:4])
+        self._ck(self._lib.avb_distort_points(self._h, _ptr(K), _ptr(D), _ptr(p), len(p), int(f32_io), _ptr(out)))
+        return out

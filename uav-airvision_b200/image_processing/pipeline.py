@@ -1,0 +1,124 @@
+"""ImageProcessingPipeline: the reference's per-frame orchestrator (image_processing/pipeline.py:14-150)
+with the whole stage sequence -- pyramid build, temporal KLT, stereo KLT + filters, FAST + grid ranking,
+new-feature stereo match, prune, publish -- executed as ONE CUDA-graph launch inside libavb
+(avb_process_frame).  Stereo message in, feature_msg(timestamp, [FeatureMeasurement]) out."""
+from __future__ import annotations
+
+from collections import defaultdict, namedtuple
+
+import numpy as np
+
+from . import _native
+from .camera_model import CameraModel
+from .feature_measurment import FeatureMeasurement
+from .feature_meta_data import FeatureMetaData
+from .imu_processor import IMUProcessor
+
+feature_msg = namedtuple('feature_msg', ['timestamp', 'features'])
+
+
+class ImageProcessingPipeline:
+    def __init__(self, config, device=0, use_graph=True):
+        self.config = config
+        self.prev_cam0_msg = None
+        self.imu_processor = IMUProcessor(config.T_imu_cam0, config.T_imu_cam1)
+        self.detector = None                      # FAST lives in libavb (k_fast); kept for attribute parity
+        self.camera_model = CameraModel(config.cam0_intrinsics, config.cam0_distortion_model,
+                                        config.cam0_distortion_coeffs)
+        self.next_feature_id = 0
+        self.num_features = defaultdict(int)
+        self.first_frame = True
+        self.prev_pyr0 = None
+        self._device, self._use_graph = device, use_graph
+        self._ctx = None
+        self._grid_cache = None
+        self._new = FeatureMeasurement.__new__
+
+    # -- plumbing ------------------------------------------------------------------------------------------
+    @property
+    def context(self):
+        return self._ctx
+
+    def _ensure_context(self, img):
+        if self._ctx is None:
+            h, w = img.shape[:2]
+            self._ctx = _native.Context(self.config, w, h, num_streams=1, device=self._device,
+                                        use_graph=self._use_graph)
+            _native_register(self._ctx)
+        return self._ctx
+
+    def imu_callback(self, imu_msg):
+        self.imu_processor.imu_callback(imu_msg)
+
+    # -- the hot path -----------------------------------------------------------------------------------------
+    def stereo_callback(self, stereo_msg):
+        cam0_msg, cam1_msg = stereo_msg.cam0_msg, stereo_msg.cam1_msg
+        ctx = self._ensure_context(cam0_msg.image)
+        imu = self.imu_processor
+        imu.cam0_prev_img_msg = self.prev_cam0_msg
+        imu.cam0_curr_img_msg = cam0_msg
+        R = None
+        if not self.first_frame:
+            R, _ = imu.integrate_imu_data()
+        st = ctx.staging
+        st[0, 0] = cam0_msg.image
+        st[0, 1] = cam1_msg.image
+        ctx.process_staged(R)
+        hdr, ids, meas = ctx.result(0)
+        self.next_feature_id = int(hdr['next_feature_id'])
+        if not self.first_frame:
+            nf = self.num_features
+            nf['before_tracking'] = int(hdr['before_tracking'])
+            if nf['before_tracking']:
+                nf['after_tracking'] = int(hdr['after_tracking'])
+                nf['after_matching'] = int(hdr['after_matching'])
+                nf['after_ransac'] = int(hdr['after_ransac'])
+        self.first_frame = False
+        self.prev_cam0_msg = cam0_msg
+        self.prev_pyr0 = cam0_msg.image
+        self._grid_cache = None
+        FM = FeatureMeasurement
+        feats = [FM(i, a, b, c, d) for i, (a, b, c, d) in zip(ids.tolist(), meas.tolist())]
+        return feature_msg(cam0_msg.timestamp, feats)
+
+    # -- state read-back (pipeline.prev_features / curr_features of the reference) ---------------------------
+    @property
+    def prev_features(self):
+        """Grid of FeatureMetaData lists as the reference holds it after the roll (pipeline.py:145-148)."""
+        if self._grid_cache is None:
+            grid = [[] for _ in range(self.config.grid_num)]
+            if self._ctx is not None and not self.first_frame:
+                _, ids, _ = self._ctx.result(0)
+                cell, life, p0, p1 = self._ctx.features(0)
+                for i in range(len(ids)):
+                    f = FeatureMetaData()
+                    f.id, f.lifetime = int(ids[i]), int(life[i])
+                    f.cam0_point, f.cam1_point = p0[i].copy(), p1[i].copy()
+                    grid[int(cell[i])].append(f)
+            self._grid_cache = grid
+        return self._grid_cache
+
+    @property
+    def curr_features(self):
+        return [[] for _ in range(self.config.grid_num)]
+
+
+_current_ctx = None
+
+
+def _native_register(ctx):
+    global _current_ctx
+    _current_ctx = ctx
+
+
+def current_context():
+    """Most recently created libavb context (the stage classes use it when none is passed)."""
+    if _current_ctx is None:
+        raise RuntimeError('no libavb context yet: create an ImageProcessingPipeline / call create_context first')
+    return _current_ctx
+
+
+def create_context(config, width, height, num_streams=1, device=0, use_graph=True):
+    ctx = _native.Context(config, width, height, num_streams=num_streams, device=device, use_graph=use_graph)
+    _native_register(ctx)
+    return ctx
