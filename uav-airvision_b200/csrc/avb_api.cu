@@ -240,8 +240,8 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
     const size_t img_bytes = (size_t)g.W * g.H;
     for (int p = 0; p < 2; ++p) {
-        int r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 144, 68);
-        if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 80, 24);
+        int r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 160, 68);
+        if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 24);
         if (r != AVB_OK) {
             g_create_error = c->err;
             avb_destroy(c);
@@ -250,7 +250,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     }
     for (int l = 1; l < g.nlev - 1; ++l) {
         int r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
-                         g.slot_bytes, 144, 68);
+                         g.slot_bytes, 160, 68);
         if (r != AVB_OK) {
             g_create_error = c->err;
             avb_destroy(c);

@@ -12,7 +12,8 @@
 
 #define FT_W 64
 #define FT_H 16
-#define FB_W 80                     // TMA box: FT_W + 8 rounded to 16 bytes
+#define FB_W 96                     // TMA box: 16 left halo (TMA start column must be a 16-byte multiple) + FT_W + 16
+#define FB_X 16
 #define FB_H 24                     // FT_H + 8
 #define SC_PITCH 68
 
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ CUtensorMa
     __syncthreads();
     if (tid == 0) {
         f_mbar_expect_tx(&bar, FB_W * FB_H);
-        f_tma_load_3d(&tile[0][0], &map0, &bar, X0 - 4, Y0 - 4, s * 2);   // image = s*2 + cam0
+        f_tma_load_3d(&tile[0][0], &map0, &bar, X0 - FB_X, Y0 - 4, s * 2);   // image = s*2 + cam0
     }
     f_mbar_wait(&bar, 0);
 
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ CUtensorMa
         const int py = i / (FT_W + 2) - 1, px = i % (FT_W + 2) - 1;
         const int X = X0 + px, Y = Y0 + py;
         int r = 0;
-        if (X >= 3 && X <= g.W - 4 && Y >= 3 && Y <= g.H - 4) r = fast_response(&tile[py + 4][px + 4], g.fast_thr);
+        if (X >= 3 && X <= g.W - 4 && Y >= 3 && Y <= g.H - 4) r = fast_response(&tile[py + 4][px + FB_X], g.fast_thr);
         sc[py + 1][px + 1] = (uint8_t)r;
     }
     __syncthreads();

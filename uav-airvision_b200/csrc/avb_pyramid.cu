@@ -5,14 +5,17 @@
 //
 // Each CTA produces a 64x32 tile of the destination level.  The (2*64+4) x (2*32+4) source
 // footprint is staged into shared memory by ONE TMA tensor copy (cp.async.bulk.tensor.3d, box
-// 144 x 68 x 1 over the (x, y, image) view of the pyramid arena; out-of-image elements arrive as
-// zeros and are never read because taps are reflected first).  Horizontal 5-tap pass -> u16
+// 160 x 68 x 1 over the (x, y, image) view of the pyramid arena; out-of-image elements arrive as
+// zeros and are never read because taps are reflected first).  The TMA start column must be a
+// multiple of 16 bytes (measured on B200: any other inner coordinate raises "illegal instruction"),
+// so the box starts 16 columns left of the tile instead of 2.  Horizontal 5-tap pass -> u16
 // shared buffer -> vertical pass; every thread emits 16 output pixels with one 128-bit store.
 #include "avb_common.cuh"
 
 #define PT_W 64
 #define PT_H 32
-#define PB_W 144                    // box width  (>= 2*PT_W + 4, multiple of 16 bytes)
+#define PB_W 160                    // box width: 16 left halo (alignment) + 2*PT_W + 16, multiple of 16 bytes
+#define PB_X 16                     // columns between the box start and the tile's first source column
 #define PB_H 68                     // box height (2*PT_H + 4)
 #define HB_PITCH 72                 // u16 pitch of the horizontal-pass buffer (bank spread)
 
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ CUtens
     const int slot = SLOT(cam, parity);
     const int img = (level == 1) ? (s * 2 + cam) : (s * SLOTS_PER_STREAM + slot);
     const LevelGeom ls = g.lv[level - 1], ld = g.lv[level];
-    const int x0 = 2 * PT_W * blockIdx.x - 2, y0 = 2 * PT_H * blockIdx.y - 2;
+    const int x0 = 2 * PT_W * blockIdx.x - PB_X, y0 = 2 * PT_H * blockIdx.y - 2;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
