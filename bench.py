@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s and tracked features/s of the B200 image front end.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+
+A "step" is one stereo frame of one stream through the whole front end (pyramid build, temporal KLT, stereo
+KLT + filters, FAST + grid ranking, new-feature stereo match, prune, publish).  At N GPUs every rank owns one
+independent synthetic EuRoC-format stream (no collective on the data path: "scaling": "weak"); rank 0 prints ONE
+JSON line.
+
+  value     frames/s with the whole frame sequence already resident in HBM (K dependent frames enqueued on the
+            context's stream, CUDA events on that stream, max over ranks)
+  e2e       the same frames through the public API, ImageProcessor.stereo_callback(stereo_msg) with HOST numpy
+            images: host->pinned copy, H2D, the CUDA-graph frame, D2H of the result block and construction of the
+            FeatureMeasurement list are all inside the timed region
+  roofline  the frame's kernel chain against the HBM copy peak of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the reference front end's CPU path (oracle/pipeline_port.py calling cv2 exactly where the reference
+            does; the reference itself is Python and cannot travel to the GPU box) on the same frames
+
+Inputs are synthetic (seeded sliding-texture stereo + IMU, synth_euroc.py).  The timed sequence (W+K+1 distinct
+frames of 0.72 MB) is larger than L2 once K >= 180, and every frame is read exactly once.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'uav-airvision_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+sys.dont_write_bytecode = True
+
+METRIC = 'stereo_frames_per_s'
+UNIT = 'frames/s'
+
+
+def workload(name):
+    from oracle.configs import config_c2, config_c3      # plain attribute bags (no oracle arithmetic)
+    if name == 'c2':
+        return config_c2(), dict(width=752, height=480, seed=7, sigma=2.2, drift=(1.6, 0.7),
+                                 gyro=(0.01, -0.02, 0.03), noise=1.0), \
+            'C2: single synthetic EuRoC-format stereo stream 752x480, grid 6x10 x max 5 = 300 features, ' \
+            '4-level pyramid, KLT 15x15'
+    if name == 'c3':
+        return config_c3(), dict(width=1280, height=1024, seed=11, sigma=1.8, drift=(1.2, 0.9)), \
+            'C3: 1280x1024 stereo, grid 10x10 x max 20 = 2000 features, 5-level pyramid (intrinsics scaled with ' \
+            'the image; RANSAC off = reference parity)'
+    raise SystemExit(f'unknown workload {name}')
+
+
+def algorithmic_bytes_per_frame(w, h, max_level, n_feat):
+    """read both u8 inputs once + write pyramid levels 1..L once + 64 B per feature."""
+    px, tot = w * h, 0
+    lw, lh = w, h
+    for _ in range(max_level):
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+        tot += lw * lh
+    return 2 * (px + tot) + 64 * n_feat
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed regions run (B200_PROFILING.md, clocks line)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def summary(self, windows):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        rows = [r for t, r in self.rows if any(a - 0.05 <= t <= b + 0.05 for a, b in windows)] or \
+               [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_sequence(skw, n_frames):
+    from synth_euroc import SlidingTextureStream
+    return SlidingTextureStream(n_frames=n_frames, **skw)
+
+
+def rotations_for(cfg, stream):
+    """cam0_R_p_c per frame exactly as the pipeline's IMUProcessor produces it with the synchronous driver."""
+    from image_processing import IMUProcessor
+    imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    out, prev = [], None
+    for kind, msg in stream.events():
+        if kind == 'imu':
+            imu.imu_callback(msg)
+            continue
+        imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = prev, msg.cam0_msg
+        out.append(np.eye(3) if prev is None else imu.integrate_imu_data()[0])
+        prev = msg.cam0_msg
+    return out
+
+
+def cpu_front_end(cfg, stream, n_frames, budget_s=30.0):
+    """Reference CPU path (port, cv2 backend) on the first frames of the same stream.  Returns per-frame seconds
+    (frame 0 first), features per frame."""
+    import cv2
+    from oracle.pipeline_port import FrontEndPort
+    fe = FrontEndPort(cfg, backend='cv2')
+    times, feats = [], []
+    t_start = time.perf_counter()
+    k = 0
+    for kind, msg in stream.events():
+        if kind == 'imu':
+            fe.imu_callback(msg)
+            continue
+        t0 = time.perf_counter()
+        fm = fe.stereo_callback(msg)
+        times.append(time.perf_counter() - t0)
+        feats.append(len(fm.features))
+        k += 1
+        if k >= n_frames or (time.perf_counter() - t_start) > budget_s:
+            break
+    return times, feats, cv2.getNumThreads(), cv2.__version__
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU front end alone, rank 0 only."""
+    if rank != 0:
+        return
+    cfg, skw, wname = workload(args.workload)
+    n = args.warmup + args.steps + 1
+    stream = make_sequence(skw, n)
+    frames = [stream.frame(k) for k in range(n)]          # pre-decoded in RAM
+    stream.frames = lambda: iter(frames)
+    times, feats, threads, cvv = cpu_front_end(cfg, stream, n, budget_s=150.0)
+    done = len(times)
+    w = min(args.warmup + 1, max(done - 1, 1))            # frame 0 + warm-up frames are not timed
+    timed = times[w:]
+    total = float(np.sum(timed))
+    k = len(timed)
+    val = k / total if total > 0 else 0.0
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': k, 'warmup': w, 'ms_per_step': 1e3 * total / max(k, 1), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (cv2)', 'data': 'synthetic',
+        'config': {'workload': wname, 'streams': 1, 'frames_timed': k,
+                   'note': 'reference front end restated in oracle/pipeline_port.py, cv2 %s called exactly where '
+                           'the reference calls it; the Python reference itself cannot travel to the GPU box' % cvv},
+        'tracked_features_per_s': float(np.sum(feats[w:]) / total) if total > 0 else 0.0,
+        'frame0_ms': 1e3 * times[0],
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': f'{k} consecutive frames of the workload stream after frame 0 + {w - 1} warm-up '
+                                   f'frames; host cores {os.cpu_count()}, cv2 threads {threads}'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3'])
+    ap.add_argument('--streams', type=int, default=64, help='streams per GPU of the extra multi-stream leg (0 = skip)')
+    ap.add_argument('--ms-steps', type=int, default=20)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: libavb has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from image_processing import ImageProcessor, _native
+    cfg, skw, wname = workload(args.workload)
+    skw = dict(skw, seed=skw['seed'] + rank)              # every rank owns its own stream
+    W, K = args.warmup, args.steps
+    n_prof = 12
+    n_extra = (2 * (args.streams - 1) + 4 + 1 + args.ms_steps + 2) if args.streams > 0 else 0
+    n = max(W + K + 1 + n_prof, n_extra)
+    stream = make_sequence(skw, n)
+    frames = [stream.frame(k) for k in range(n)]
+    stream.frames = lambda: iter(frames)
+    Rs = rotations_for(cfg, stream)
+    width, height = stream.w, stream.h
+
+    # ---- device-resident leg ("value") --------------------------------------------------------------------
+    ctx = _native.Context(cfg, width, height, num_streams=1, device=local, use_graph=True)
+    bb = ctx.block_bytes
+    host_blocks = torch.empty((n, bb), dtype=torch.uint8).pin_memory()
+    hb = host_blocks.numpy()
+    img_bytes = width * height
+    for k, f in enumerate(frames):
+        hb[k, :img_bytes] = f.cam0_image.reshape(-1)
+        hb[k, img_bytes:2 * img_bytes] = f.cam1_image.reshape(-1)
+        ctx.fill_rotations(hb[k], Rs[k])
+    dev_blocks = host_blocks.cuda(non_blocking=False)
+    ptr = dev_blocks.data_ptr()
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    windows = []
+
+    for k in range(W + 1):                                # frame 0 (first-frame chain) + W warm-up frames
+        ctx.process_device(ptr + k * bb)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_a = time.perf_counter()
+    e0.record(ext)
+    for k in range(W + 1, W + 1 + K):
+        ctx.enqueue_device(ptr + k * bb)
+    e1.record(ext)
+    ctx.sync()
+    barrier()
+    windows.append((t_a, time.perf_counter()))
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    hdr, ids, _ = ctx.result(0)
+    last_n_dev = int(hdr['n_features'])
+    kernels_per_frame = ctx.kernels_per_frame()
+
+    # per-stage device times of the steady-state chain, serialised (explains `value`; not a bench number)
+    stage_ms = {}
+    for k in range(W + 1 + K, W + 1 + K + n_prof):
+        st = ctx.profile_frame_device(ptr + k * bb)
+        for name, v in st.items():
+            stage_ms.setdefault(name, []).append(v)
+    stage_ms = {k_: float(np.median(v)) for k_, v in stage_ms.items()}
+    ctx.close()
+
+    # ---- end-to-end leg through the public API ----------------------------------------------------------------
+    ip = ImageProcessor(cfg, device=local, use_graph=True)
+    feats_per_frame = []
+    events = list(stream.events())
+    idx = 0
+    frame_no = 0
+
+    def pump(until_frames):
+        nonlocal idx, frame_no
+        while idx < len(events) and frame_no < until_frames:
+            kind, msg = events[idx]
+            idx += 1
+            if kind == 'imu':
+                ip.imu_callback(msg)
+            else:
+                fm = ip.stereo_callback(msg)
+                feats_per_frame.append(len(fm.features))
+                frame_no += 1
+
+    pump(W + 1)
+    barrier()
+    t0 = time.perf_counter()
+    pump(W + 1 + K)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    barrier()
+    windows.append((t0, t1))
+    e2e_s = max_over_ranks(t1 - t0)
+    d2h_bytes = int(_native.C.sizeof(_native.AvbFrameHeader)) + ip.context.capacity * 64
+    d2h_bytes = (d2h_bytes + 255) & ~255
+    timed_feats = sum(feats_per_frame[W + 1:W + 1 + K])
+    assert feats_per_frame[W + K] == last_n_dev, 'device-resident and end-to-end legs disagree on the last frame'
+    ip.context.close()
+    total_feats = sum_over_ranks(timed_feats)
+
+    # ---- multi-stream leg: S time-offset runs of the same sequence per GPU (run.bat sweep shape) ---------------
+    multi = None
+    if args.streams > 0:
+        S, KM, WM = args.streams, args.ms_steps, 4
+        mctx = _native.Context(cfg, width, height, num_streams=S, device=local, use_graph=True)
+        mbb = mctx.block_bytes
+        rot_off = mctx.rot_offset
+        nblk = WM + 1 + KM + 2                            # + 2 frames for the serialised stage timing
+        mblocks = torch.zeros((nblk, mbb), dtype=torch.uint8, device='cuda')
+        imgs = dev_blocks[:, :2 * img_bytes]
+        Hs = dev_blocks[:, ctx.rot_offset:ctx.rot_offset + 72]
+        for k in range(nblk):
+            src = torch.arange(S, device='cuda') * 2 + k      # stream s starts 2*s frames into the sequence
+            mblocks[k, :S * 2 * img_bytes] = imgs[src].reshape(-1)
+            mblocks[k, rot_off:rot_off + S * 72] = Hs[src].reshape(-1)
+        mptr = mblocks.data_ptr()
+        mext = torch.cuda.ExternalStream(mctx.cuda_stream(), device=local)
+        for k in range(WM + 1):
+            mctx.process_device(mptr + k * mbb)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_a = time.perf_counter()
+        m0.record(mext)
+        for k in range(WM + 1, WM + 1 + KM):
+            mctx.enqueue_device(mptr + k * mbb)
+        m1.record(mext)
+        mctx.sync()
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        m_ms = max_over_ranks(m0.elapsed_time(m1))
+        nf = sum(int(mctx.result(s)[0]['n_features']) for s in range(S))
+        mctx.profile_frame_device(mptr + (nblk - 2) * mbb)
+        st = mctx.profile_frame_device(mptr + (nblk - 1) * mbb)
+        mctx.close()
+        bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nf / S)
+        m_fps = world * S * KM / (m_ms * 1e-3)
+        multi = {'streams_per_gpu': S, 'steps': KM, 'value': m_fps, 'unit': UNIT, 'ms_per_step': m_ms / KM,
+                 'features_per_frame': nf / S, 'hbm_gbs': bpf * S * KM / (m_ms * 1e-3) / 1e9,
+                 'stage_ms': {k_: round(v, 4) for k_, v in st.items()},
+                 'note': 'S time-offset runs of the sequence (stream s starts 2*s frames in), lock-stepped in one '
+                         'context: every kernel launch covers all S streams; inputs resident in HBM'}
+        del mblocks
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        times, cfeats, threads, cvv = cpu_front_end(cfg, stream, min(n, W + 1 + K), budget_s=25.0)
+        done = len(times)
+        w_ = min(W + 1, max(done - 1, 1))
+        tot = float(np.sum(times[w_:]))
+        cpu = {'value': (done - w_) / tot if tot > 0 else 0.0, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'{done - w_} consecutive frames of the same stream (after frame 0 + {w_ - 1} warm-up frames), '
+                         f'oracle/pipeline_port.py with cv2 {cvv} where the reference calls cv2; host cores '
+                         f'{os.cpu_count()}, cv2 threads {threads}',
+               'ms_per_frame_median': 1e3 * float(np.median(times[w_:])), 'frame0_ms': 1e3 * times[0],
+               'tracked_features_per_s': float(np.sum(cfeats[w_:]) / tot) if tot > 0 else 0.0}
+
+    clocks = sampler.summary(windows) if sampler is not None else None
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        else:
+            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        fps = world * K / (dev_ms * 1e-3)
+        nfeat = timed_feats / K
+        bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nfeat)
+        chain_ms = dev_ms / K
+        achieved = bpf / (chain_ms * 1e-3) / 1e9
+        kernel_stages = {k_: v for k_, v in stage_ms.items() if k_ not in ('input_copy', 'result_copy')}
+        dominant = max(kernel_stages, key=kernel_stages.get)
+        line = {
+            'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': chain_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u8/int32 fixed-point + f32 (LK), f64 (undistort)', 'data': 'synthetic',
+            'config': {'workload': wname, 'streams_per_gpu': 1, 'features_per_frame': nfeat,
+                       'l2_policy': f'{W + K + 1} distinct frames x {2 * img_bytes} B = '
+                                    f'{(W + K + 1) * 2 * img_bytes / 1e6:.0f} MB device-resident sequence, each read once '
+                                    f'(larger than the 126 MB L2 when steps >= 180)',
+                       'frame_graph': 'one CUDA-graph launch per frame'},
+            'tracked_features_per_s': total_feats / (dev_ms * 1e-3),
+            'e2e': {'value': world * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(bb),
+                    'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': 1e3 * e2e_s / K,
+                    'tracked_features_per_s': total_feats / e2e_s,
+                    'api': 'ImageProcessor.stereo_callback(stereo_msg) -> feature_msg, host numpy images in, '
+                           'FeatureMeasurement list out'},
+            'gpu_launches': int(K * kernels_per_frame),
+            'roofline': {'bound': 'hbm', 'kernel': f'frame chain ({kernels_per_frame} kernels, one CUDA graph); '
+                                                   f'dominant stage by time: {dominant}',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': bpf,
+                         'stage_ms_serialised': {k_: round(v, 4) for k_, v in stage_ms.items()},
+                         'note': 'single stream = latency-bound dependent chain; see multi_stream for the '
+                                 'batched figure and DESIGN.md section 5'},
+            'multi_stream': multi,
+            'cpu_baseline': cpu,
+            'clocks': clocks,
+        }
+        if multi is not None:
+            multi['roofline_frac'] = multi['hbm_gbs'] / peak
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -340,6 +340,48 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
     launch_publish(g, d, p, c->st);
 }
 
+// Serialised, instrumented variant of the steady-state chain: one event after every stage on c->st.
+// Stage order: 0 input copy | 1 clear+FAST | 2 pyramid | 3 track | 4 select | 5 stereo(new) | 6 grid update |
+// 7 publish | 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
+extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, float* stage_ms /*[9]*/) {
+    if (!c || !d_block || !stage_ms) return AVB_E_INVALID;
+    if (c->first_frame) return fail(c, AVB_E_STATE, "profile the steady state: process frame 0 first");
+    CK(cudaSetDevice(c->cfg.device));
+    const Geom& g = c->g;
+    const DevState& d = c->d;
+    const int p = c->parity ^ 1;
+    cudaEvent_t ev[10];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaEventRecord(ev[0], c->st));
+    CK(cudaMemcpyAsync(c->d.in[p], d_block, in_block_bytes(g), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaEventRecord(ev[1], c->st));
+    launch_clear_frame(g, d, c->st);
+    launch_fast(g, d, c->maps, p, c->st);
+    CK(cudaEventRecord(ev[2], c->st));
+    launch_pyramid(g, d, c->maps, p, c->st);
+    CK(cudaEventRecord(ev[3], c->st));
+    launch_track(g, d, p, c->st);
+    CK(cudaEventRecord(ev[4], c->st));
+    launch_select(g, d, p, 0, c->st);
+    CK(cudaEventRecord(ev[5], c->st));
+    launch_stereo_candidates(g, d, p, c->st);
+    CK(cudaEventRecord(ev[6], c->st));
+    launch_grid_update(g, d, p, 0, c->st);
+    CK(cudaEventRecord(ev[7], c->st));
+    launch_publish(g, d, p, c->st);
+    CK(cudaEventRecord(ev[8], c->st));
+    CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaEventRecord(ev[9], c->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+    cudaEventElapsedTime(&c->last_ms, ev[0], ev[9]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    c->parity = p;
+    return AVB_OK;
+}
+
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
     // clear, fast, (nlev-1) pyramid levels, track, select, stereo_candidates, grid_update, publish

@@ -17,7 +17,7 @@ EXPORTS = (
     'avb_sync', 'avb_get_result', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
     'avb_undistort_points', 'avb_distort_points', 'avb_last_frame_ms', 'avb_kernels_per_frame',
-    'avb_cuda_stream', 'avb_time_pyramid',
+    'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device',
 )
 
 
@@ -95,6 +95,7 @@ def load():
     lib.avb_cuda_stream.argtypes = [vp]
     lib.avb_cuda_stream.restype = C.c_void_p
     lib.avb_time_pyramid.argtypes = [vp, ip, C.POINTER(C.c_float)]
+    lib.avb_profile_frame_device.argtypes = [vp, vp, C.POINTER(C.c_float)]
     if lib.avb_abi_version() != 1:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
@@ -248,6 +249,14 @@ class Context:
 
     def cuda_stream(self):
         return self._lib.avb_cuda_stream(self._h)
+
+    STAGES = ('input_copy', 'clear+fast', 'pyramid', 'track', 'select', 'stereo_new', 'grid_update', 'publish',
+              'result_copy')
+
+    def profile_frame_device(self, d_block_ptr: int):
+        ms = (C.c_float * 9)()
+        self._ck(self._lib.avb_profile_frame_device(self._h, C.c_void_p(d_block_ptr), ms))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
 
     def time_pyramid(self, iters=20):
         ms = C.c_float()
