@@ -92,6 +92,7 @@ int  avb_create(const avb_config* cfg, avb_ctx** out);
 void avb_destroy(avb_ctx* ctx);
 int  avb_capacity(const avb_ctx* ctx);                /* max features per stream = grid_num*grid_max */
 int  avb_num_cells(const avb_ctx* ctx);
+int  avb_get_geometry(const avb_ctx* ctx, int* width, int* height, int* num_streams);
 int  avb_reset(avb_ctx* ctx);                         /* back to first_frame = True for all streams */
 
 /* One frame's input for all streams is a single "input block": S*2 images of width*height bytes in

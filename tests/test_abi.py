@@ -67,7 +67,8 @@ def test_product_package_does_not_import_oracle():
 
 
 def test_imu_processor_matches_port():
-    """Host-side gyro integration (stays in Python) against the oracle port, incl. the window quirks (B13)."""
+    """Host-side gyro integration (C helper behind the Python class) against the oracle port, incl. the window
+    quirks (B13).  Equal to a few ulp: the C code sums R^T w in a fixed order, numpy's matmul in its own."""
     from image_processing import IMUProcessor
     from oracle.configs import config_default
     from oracle.pipeline_port import FrontEndPort
@@ -86,6 +87,42 @@ def test_imu_processor_matches_port():
         a.cam0_prev_img_msg, a.cam0_curr_img_msg = img_msg(t_prev, None), img_msg(t_curr, None)
         Ra0, Ra1 = a.integrate_imu_data()
         Rb0, Rb1 = b._integrate_imu(t_prev, t_curr)
-        assert np.array_equal(Ra0, Rb0) and np.array_equal(Ra1, Rb1)
+        assert np.abs(Ra0 - Rb0).max() < 1e-15 and np.abs(Ra1 - Rb1).max() < 1e-15
         assert len(a.imu_buffer) == len(b.imu_buffer)
     assert np.array_equal(Ra0, np.eye(3))          # last window has no end message: identity, no trim
+
+
+def test_host_extension_imu_integration_matches_python_rule():
+    """_avbhost.integrate_imu (C) == the window rule of the reference's IMUProcessor.integrate_imu_data
+    (imu_processor.py:28-67): first t >= t_prev-0.01 .. first t >= t_curr-0.004, identity + no trim when open."""
+    from image_processing.imu_processor import IMUProcessor, rodrigues
+    from oracle.configs import config_default
+    from synth_euroc import img_msg, imu_msg
+    cfg = config_default()
+    imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    rng = np.random.default_rng(3)
+    t0 = 50.0
+    # no IMU yet -> identity, buffer untouched
+    imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = img_msg(t0 - 0.05, None), img_msg(t0, None)
+    R0, R1 = imu.integrate_imu_data()
+    assert np.array_equal(R0, np.eye(3)) and np.array_equal(R1, np.eye(3)) and imu.imu_buffer == []
+    for k in range(40):
+        for j in range(10):
+            imu.imu_callback(imu_msg(t0 + k * 0.05 + j * 0.005, rng.normal(size=3) * 0.4, np.zeros(3)))
+        tp, tc = t0 + k * 0.05 - 0.05, t0 + k * 0.05
+        imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = img_msg(tp, None), img_msg(tc, None)
+        buf = list(imu.imu_buffer)
+        R0, R1 = imu.integrate_imu_data()
+        b = next((i for i, m in enumerate(buf) if m.timestamp >= tp - 0.01), None)
+        e = next((i for i, m in enumerate(buf) if m.timestamp >= tc - 0.004), None)
+        if b is None or e is None:
+            assert np.array_equal(R0, np.eye(3)) and len(imu.imu_buffer) == len(buf)
+            continue
+        w = np.zeros(3)
+        for m in buf[b:e]:
+            w += m.angular_velocity
+        if e - b > 0:
+            w /= (e - b)
+        assert np.abs(R0 - rodrigues((imu.R_cam0_imu.T @ w) * (tc - tp)).T).max() < 1e-15
+        assert np.abs(R1 - rodrigues((imu.R_cam1_imu.T @ w) * (tc - tp)).T).max() < 1e-15
+        assert imu.imu_buffer == buf[e:]

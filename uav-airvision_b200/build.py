@@ -1,4 +1,7 @@
-"""Builds libavb.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""Builds the native code in-tree (cross-compiles without a GPU):
+
+  lib/libavb.so                         nvcc, sm_100a: CUDA kernels + the C-ABI of include/avb.h
+  image_processing/_avbhost.*.so        gcc: CPython extension, the per-frame host driver (csrc/avb_host.c)
 
     python uav-airvision_b200/build.py [--force] [--verbose]
 """
@@ -7,10 +10,12 @@ from __future__ import annotations
 import os
 import subprocess
 import sys
+import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libavb.so')
+HOST_EXT = os.path.join(HERE, 'image_processing', '_avbhost' + sysconfig.get_config_var('EXT_SUFFIX'))
 SOURCES = ['avb_api.cu', 'avb_pyramid.cu', 'avb_fast.cu', 'avb_points.cu', 'avb_grid.cu']
 HEADERS = ['avb_common.cuh', 'avb_lk.cuh', os.path.join('..', '..', 'include', 'avb.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -18,26 +23,38 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--shared', '-lcudart']
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _stale(target, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ['-o', LIB]
+def needs_build() -> bool:
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return _stale(LIB, deps) or _stale(HOST_EXT, [os.path.join(CSRC, 'avb_host.c'), LIB, os.path.abspath(__file__)])
+
+
+def _run(cmd, verbose, what):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed building libavb.so')
+        raise RuntimeError(f'{what} failed')
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    if force or _stale(LIB, deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+        _run([nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) +
+             [os.path.join(CSRC, f) for f in SOURCES] + ['-o', LIB], verbose, 'nvcc (libavb.so)')
+    if force or _stale(HOST_EXT, [os.path.join(CSRC, 'avb_host.c'), LIB, os.path.abspath(__file__)]):
+        inc = sysconfig.get_paths()['include']
+        _run([os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-ffp-contract=off', '-Wall', '-I', inc,
+              os.path.join(CSRC, 'avb_host.c'), '-o', HOST_EXT, '-L', os.path.dirname(LIB), '-lavb', '-lm',
+              '-Wl,-rpath,$ORIGIN/../lib'], verbose, 'gcc (_avbhost)')
     return LIB
 
 

@@ -295,6 +295,13 @@ extern "C" void avb_destroy(avb_ctx* c) {
 
 extern "C" int avb_capacity(const avb_ctx* c) { return c ? c->g.NMAX : 0; }
 extern "C" int avb_num_cells(const avb_ctx* c) { return c ? c->g.NC : 0; }
+extern "C" int avb_get_geometry(const avb_ctx* c, int* w, int* h, int* S) {
+    if (!c) return AVB_E_INVALID;
+    if (w) *w = c->g.W;
+    if (h) *h = c->g.H;
+    if (S) *S = c->g.S;
+    return AVB_OK;
+}
 extern "C" uint8_t* avb_input_staging(avb_ctx* c) { return c ? c->h_in : nullptr; }
 extern "C" void* avb_cuda_stream(avb_ctx* c) { return c ? (void*)c->st : nullptr; }
 

@@ -1,0 +1,384 @@
+/*
+ * _avbhost -- CPython extension: the per-frame host side of ImageProcessingPipeline.stereo_callback in C.
+ *
+ * The CUDA frame takes ~0.15 ms; building 300 FeatureMeasurement objects and integrating the gyro window in
+ * interpreted Python took longer than that.  This module keeps the reference's Python surface (message objects in,
+ * list of FeatureMeasurement out; reference image_processing/pipeline.py:46-150, feature_publisher.py:109-121,
+ * imu_processor.py:28-67) and does the per-frame work natively:
+ *
+ *   process_frame(ctx, img0, img1, R|None, FeatureMeasurement) -> (features, header tuple)
+ *       copies the two host images into libavb's pinned staging block (GIL released), runs avb_process_frame
+ *       (H2D + CUDA-graph frame + D2H), and materialises the FeatureMeasurement list straight from the pinned
+ *       result block
+ *   integrate_imu(buffer, t_prev, t_curr, R_cam0_imu, R_cam1_imu, out0, out1) -> end index | -1
+ *       IMUProcessor.integrate_imu_data: mean gyro over the window rule of imu_processor.py:37-66, Rodrigues,
+ *       transposed; the caller trims the buffer
+ *
+ * Built by uav-airvision_b200/build.py with gcc against libavb.so (C-ABI in include/avb.h).  No numpy C-API:
+ * arrays travel through the buffer protocol.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <descrobject.h>
+#include <structmember.h>
+
+#include <math.h>
+#include <string.h>
+
+#include "../../include/avb.h"
+
+/* ---- FeatureMeasurement construction ------------------------------------------------------------------ */
+
+typedef struct {
+    PyTypeObject* type;            /* borrowed; identity check only */
+    Py_ssize_t off[5];             /* slot offsets of id, u0, v0, u1, v1; -1 = generic setattr path */
+} fm_layout;
+
+static fm_layout g_layout = {NULL, {-1, -1, -1, -1, -1}};
+static PyObject* g_names[5];
+
+static int resolve_layout(PyTypeObject* tp) {
+    static const char* names[5] = {"id", "u0", "v0", "u1", "v1"};
+    if (g_layout.type == tp) return 0;
+    g_layout.type = tp;
+    int slots = 1;
+    for (int i = 0; i < 5; ++i) {
+        g_layout.off[i] = -1;
+        PyObject* d = PyObject_GetAttrString((PyObject*)tp, names[i]);      /* slot member descriptor */
+        if (d && Py_TYPE(d) == &PyMemberDescr_Type) {
+            PyMemberDef* m = ((PyMemberDescrObject*)d)->d_member;
+            if (m && m->type == T_OBJECT_EX) g_layout.off[i] = m->offset;
+        }
+        if (!d) PyErr_Clear();
+        Py_XDECREF(d);
+        if (g_layout.off[i] < 0) slots = 0;
+    }
+    if (!slots)
+        for (int i = 0; i < 5; ++i) g_layout.off[i] = -1;
+    return 0;
+}
+
+static PyObject* make_feature(PyTypeObject* tp, long long id, const double* m) {
+    PyObject* vals[5];
+    vals[0] = PyLong_FromLongLong(id);
+    vals[1] = PyFloat_FromDouble(m[0]);
+    vals[2] = PyFloat_FromDouble(m[1]);
+    vals[3] = PyFloat_FromDouble(m[2]);
+    vals[4] = PyFloat_FromDouble(m[3]);
+    PyObject* o = NULL;
+    int ok = vals[0] && vals[1] && vals[2] && vals[3] && vals[4];
+    if (ok) {
+        if (g_layout.off[0] >= 0) {                 /* __slots__ class: fill the slots directly, no __init__ */
+            o = tp->tp_alloc(tp, 0);
+            if (o) {
+                for (int i = 0; i < 5; ++i) {
+                    *(PyObject**)((char*)o + g_layout.off[i]) = vals[i];
+                    vals[i] = NULL;
+                }
+            }
+        } else {                                    /* any other class with id/u0/v0/u1/v1 attributes */
+            o = PyObject_CallNoArgs((PyObject*)tp);
+            if (o) {
+                for (int i = 0; i < 5; ++i) {
+                    if (PyObject_SetAttr(o, g_names[i], vals[i]) < 0) {
+                        Py_CLEAR(o);
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    for (int i = 0; i < 5; ++i) Py_XDECREF(vals[i]);
+    return o;
+}
+
+static PyObject* build_list(PyTypeObject* tp, const avb_frame_header* h, const int64_t* ids, const double* meas) {
+    const Py_ssize_t n = (Py_ssize_t)h->n_features;
+    PyObject* list = PyList_New(n);
+    if (!list) return NULL;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject* o = make_feature(tp, (long long)ids[i], meas + 4 * i);
+        if (!o) {
+            Py_DECREF(list);
+            return NULL;
+        }
+        PyList_SET_ITEM(list, i, o);
+    }
+    return list;
+}
+
+static PyObject* header_tuple(const avb_frame_header* h) {
+    return Py_BuildValue("(LLiiiiiiii)", (long long)h->n_features, (long long)h->next_feature_id, h->before_tracking,
+                         h->after_tracking, h->after_matching, h->after_ransac, h->has_new, h->n_fast, h->n_candidates,
+                         h->frame_index);
+}
+
+static int copy_image(uint8_t* dst, Py_buffer* b, int W, int H) {
+    if (b->ndim != 2 || b->itemsize != 1 || b->shape[0] != H || b->shape[1] != W || b->strides[1] != 1) return -1;
+    const uint8_t* src = (const uint8_t*)b->buf;
+    if (b->strides[0] == W) {
+        memcpy(dst, src, (size_t)W * H);
+    } else {
+        for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * W, src + (size_t)y * b->strides[0], W);
+    }
+    return 0;
+}
+
+/* process_frame(ctx:int, stream_count:int(=1), img0, img1, R|None, fm_type) */
+static PyObject* py_process_frame(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    PyObject *img0, *img1, *Robj, *tpobj;
+    if (!PyArg_ParseTuple(args, "KOOOO", &handle, &img0, &img1, &Robj, &tpobj)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx || !PyType_Check(tpobj)) {
+        PyErr_SetString(PyExc_TypeError, "process_frame(ctx, img0, img1, R|None, FeatureMeasurement)");
+        return NULL;
+    }
+    int W = 0, H = 0, S = 0;
+    avb_get_geometry(ctx, &W, &H, &S);
+    if (S != 1) {
+        PyErr_SetString(PyExc_RuntimeError, "process_frame drives single-stream contexts");
+        return NULL;
+    }
+    Py_buffer b0, b1, bR;
+    int haveR = 0;
+    if (PyObject_GetBuffer(img0, &b0, PyBUF_STRIDES) < 0) return NULL;
+    if (PyObject_GetBuffer(img1, &b1, PyBUF_STRIDES) < 0) {
+        PyBuffer_Release(&b0);
+        return NULL;
+    }
+    double R[9];
+    if (Robj != Py_None) {
+        if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) {
+            PyBuffer_Release(&b0);
+            PyBuffer_Release(&b1);
+            return NULL;
+        }
+        if (bR.len != 72 || bR.itemsize != 8) {
+            PyBuffer_Release(&b0);
+            PyBuffer_Release(&b1);
+            PyBuffer_Release(&bR);
+            PyErr_SetString(PyExc_ValueError, "R must be a C-contiguous 3x3 float64 array");
+            return NULL;
+        }
+        memcpy(R, bR.buf, 72);
+        PyBuffer_Release(&bR);
+        haveR = 1;
+    }
+    uint8_t* st = avb_input_staging(ctx);
+    int bad = 0, rc = 0;
+    Py_BEGIN_ALLOW_THREADS
+    bad = copy_image(st, &b0, W, H) || copy_image(st + (size_t)W * H, &b1, W, H);
+    if (!bad) rc = avb_process_frame(ctx, NULL, NULL, W, haveR ? R : NULL);
+    Py_END_ALLOW_THREADS
+    PyBuffer_Release(&b0);
+    PyBuffer_Release(&b1);
+    if (bad) {
+        PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride", H, W);
+        return NULL;
+    }
+    if (rc != AVB_OK) {
+        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+        return NULL;
+    }
+    const avb_frame_header* h;
+    const int64_t* ids;
+    const double* meas;
+    rc = avb_get_result(ctx, 0, &h, &ids, &meas);
+    if (rc != AVB_OK) {
+        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+        return NULL;
+    }
+    resolve_layout((PyTypeObject*)tpobj);
+    PyObject* list = build_list((PyTypeObject*)tpobj, h, ids, meas);
+    if (!list) return NULL;
+    PyObject* hd = header_tuple(h);
+    if (!hd) {
+        Py_DECREF(list);
+        return NULL;
+    }
+    PyObject* out = PyTuple_Pack(2, list, hd);
+    Py_DECREF(list);
+    Py_DECREF(hd);
+    return out;
+}
+
+/* features_from_result(ctx:int, s:int, fm_type) -> (features, header tuple): list construction only, for contexts
+ * driven through avb_process_frame* elsewhere (multi-stream drivers). */
+static PyObject* py_features_from_result(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    int s;
+    PyObject* tpobj;
+    if (!PyArg_ParseTuple(args, "KiO", &handle, &s, &tpobj)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx || !PyType_Check(tpobj)) {
+        PyErr_SetString(PyExc_TypeError, "features_from_result(ctx, stream, FeatureMeasurement)");
+        return NULL;
+    }
+    const avb_frame_header* h;
+    const int64_t* ids;
+    const double* meas;
+    int rc = avb_get_result(ctx, s, &h, &ids, &meas);
+    if (rc != AVB_OK) {
+        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+        return NULL;
+    }
+    resolve_layout((PyTypeObject*)tpobj);
+    PyObject* list = build_list((PyTypeObject*)tpobj, h, ids, meas);
+    if (!list) return NULL;
+    PyObject* hd = header_tuple(h);
+    if (!hd) {
+        Py_DECREF(list);
+        return NULL;
+    }
+    PyObject* out = PyTuple_Pack(2, list, hd);
+    Py_DECREF(list);
+    Py_DECREF(hd);
+    return out;
+}
+
+/* ---- gyro integration ---------------------------------------------------------------------------------- */
+
+static PyObject *s_timestamp, *s_angular_velocity;
+
+static int msg_time(PyObject* msg, double* t) {
+    PyObject* v = PyObject_GetAttr(msg, s_timestamp);
+    if (!v) return -1;
+    *t = PyFloat_AsDouble(v);
+    Py_DECREF(v);
+    return (*t == -1.0 && PyErr_Occurred()) ? -1 : 0;
+}
+
+static int msg_gyro(PyObject* msg, double* w) {
+    PyObject* v = PyObject_GetAttr(msg, s_angular_velocity);
+    if (!v) return -1;
+    Py_buffer b;
+    int rc = -1;
+    if (PyObject_GetBuffer(v, &b, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) == 0) {
+        if (b.len == 24 && b.itemsize == 8 && b.format && (b.format[0] == 'd' || (b.format[0] && b.format[1] == 'd'))) {
+            memcpy(w, b.buf, 24);
+            rc = 0;
+        }
+        PyBuffer_Release(&b);
+    } else {
+        PyErr_Clear();
+    }
+    if (rc != 0) {                                   /* any 3-sequence of numbers */
+        PyObject* seq = PySequence_Fast(v, "angular_velocity must be a 3-vector");
+        if (seq && PySequence_Fast_GET_SIZE(seq) == 3) {
+            rc = 0;
+            for (int i = 0; i < 3; ++i) {
+                w[i] = PyFloat_AsDouble(PySequence_Fast_GET_ITEM(seq, i));
+                if (w[i] == -1.0 && PyErr_Occurred()) rc = -1;
+            }
+        } else if (seq) {
+            PyErr_SetString(PyExc_ValueError, "angular_velocity must be a 3-vector");
+        }
+        Py_XDECREF(seq);
+    }
+    Py_DECREF(v);
+    return rc;
+}
+
+/* cv2.Rodrigues(v)[0] transposed, written row-major into out[9] */
+static void rodrigues_T(const double* v, double* out) {
+    const double theta = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double R[9];
+    if (theta < 2.220446049250313e-16) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        const double r[3] = {v[0] / theta, v[1] / theta, v[2] / theta};
+        const double c = cos(theta), s = sin(theta), c1 = 1.0 - c;
+        const double rx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i * 3 + j] = (c * (i == j ? 1.0 : 0.0) + c1 * (r[i] * r[j])) + s * rx[i * 3 + j];
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out[i * 3 + j] = R[j * 3 + i];
+}
+
+static int get_mat9(PyObject* o, double* m, int writable, Py_buffer* keep) {
+    if (PyObject_GetBuffer(o, keep, (writable ? PyBUF_WRITABLE : 0) | PyBUF_C_CONTIGUOUS) < 0) return -1;
+    if (keep->len != 72 || keep->itemsize != 8) {
+        PyBuffer_Release(keep);
+        PyErr_SetString(PyExc_ValueError, "expected a C-contiguous 3x3 float64 array");
+        return -1;
+    }
+    if (m) memcpy(m, keep->buf, 72);
+    return 0;
+}
+
+/* integrate_imu(buffer:list, t_prev, t_curr, R_cam0_imu, R_cam1_imu, out0, out1) -> end | -1 */
+static PyObject* py_integrate_imu(PyObject* self, PyObject* args) {
+    PyObject *buf, *R0o, *R1o, *o0, *o1;
+    double t_prev, t_curr;
+    if (!PyArg_ParseTuple(args, "O!ddOOOO", &PyList_Type, &buf, &t_prev, &t_curr, &R0o, &R1o, &o0, &o1)) return NULL;
+    double R0[9], R1[9];
+    Py_buffer b;
+    if (get_mat9(R0o, R0, 0, &b) < 0) return NULL;
+    PyBuffer_Release(&b);
+    if (get_mat9(R1o, R1, 0, &b) < 0) return NULL;
+    PyBuffer_Release(&b);
+    const Py_ssize_t n = PyList_GET_SIZE(buf);
+    Py_ssize_t begin = -1, end = -1;
+    const double lo = t_prev - 0.01, hi = t_curr - 0.004;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        double t;
+        if (msg_time(PyList_GET_ITEM(buf, i), &t) < 0) return NULL;
+        if (begin < 0 && t >= lo) begin = i;
+        if (end < 0 && t >= hi) end = i;
+        if (begin >= 0 && end >= 0) break;
+    }
+    double out0[9], out1[9];
+    long ret = -1;
+    if (begin < 0 || end < 0) {
+        for (int i = 0; i < 9; ++i) out0[i] = out1[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        double w[3] = {0, 0, 0};
+        for (Py_ssize_t i = begin; i < end; ++i) {
+            double g[3];
+            if (msg_gyro(PyList_GET_ITEM(buf, i), g) < 0) return NULL;
+            w[0] += g[0];
+            w[1] += g[1];
+            w[2] += g[2];
+        }
+        if (end - begin > 0) {
+            const double cnt = (double)(end - begin);
+            w[0] /= cnt;
+            w[1] /= cnt;
+            w[2] /= cnt;
+        }
+        const double dt = t_curr - t_prev;
+        double v0[3], v1[3];
+        for (int j = 0; j < 3; ++j) {               /* (R^T w) * dt */
+            v0[j] = ((R0[0 * 3 + j] * w[0] + R0[1 * 3 + j] * w[1]) + R0[2 * 3 + j] * w[2]) * dt;
+            v1[j] = ((R1[0 * 3 + j] * w[0] + R1[1 * 3 + j] * w[1]) + R1[2 * 3 + j] * w[2]) * dt;
+        }
+        rodrigues_T(v0, out0);
+        rodrigues_T(v1, out1);
+        ret = (long)end;
+    }
+    if (get_mat9(o0, NULL, 1, &b) < 0) return NULL;
+    memcpy(b.buf, out0, 72);
+    PyBuffer_Release(&b);
+    if (get_mat9(o1, NULL, 1, &b) < 0) return NULL;
+    memcpy(b.buf, out1, 72);
+    PyBuffer_Release(&b);
+    return PyLong_FromLong(ret);
+}
+
+static PyMethodDef methods[] = {
+    {"process_frame", py_process_frame, METH_VARARGS, "One stereo frame: host images in, (FeatureMeasurement list, header) out."},
+    {"features_from_result", py_features_from_result, METH_VARARGS, "FeatureMeasurement list of stream s from the last frame."},
+    {"integrate_imu", py_integrate_imu, METH_VARARGS, "Gyro window integration (imu_processor.py:28-67)."},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_avbhost", "libavb host-side frame driver", -1, methods};
+
+PyMODINIT_FUNC PyInit__avbhost(void) {
+    static const char* names[5] = {"id", "u0", "v0", "u1", "v1"};
+    for (int i = 0; i < 5; ++i) g_names[i] = PyUnicode_InternFromString(names[i]);
+    s_timestamp = PyUnicode_InternFromString("timestamp");
+    s_angular_velocity = PyUnicode_InternFromString("angular_velocity");
+    return PyModule_Create(&moddef);
+}

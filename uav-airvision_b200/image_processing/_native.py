@@ -17,7 +17,7 @@ EXPORTS = (
     'avb_sync', 'avb_get_result', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
     'avb_undistort_points', 'avb_distort_points', 'avb_last_frame_ms', 'avb_kernels_per_frame',
-    'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device',
+    'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device', 'avb_get_geometry',
 )
 
 

@@ -10,6 +10,8 @@ import threading
 
 import numpy as np
 
+from . import _avbhost
+
 
 def rodrigues(v):
     """Rotation matrix of an axis-angle 3-vector (what cv2.Rodrigues(v)[0] returns)."""
@@ -31,6 +33,8 @@ class IMUProcessor:
         self.T_cam1_imu = np.linalg.inv(T_imu_cam1)
         self.R_cam1_imu = self.T_cam1_imu[:3, :3]
         self.t_cam1_imu = self.T_cam1_imu[:3, 3]
+        self._R0 = np.ascontiguousarray(self.R_cam0_imu, dtype=np.float64)
+        self._R1 = np.ascontiguousarray(self.R_cam1_imu, dtype=np.float64)
         self.imu_buffer = []
         self.cam0_prev_img_msg = None
         self.cam0_curr_img_msg = None
@@ -45,20 +49,12 @@ class IMUProcessor:
     def integrate_imu_data(self):
         t_prev = self.cam0_prev_img_msg.timestamp
         t_curr = self.cam0_curr_img_msg.timestamp
+        cam0_R_p_c, cam1_R_p_c = np.empty((3, 3)), np.empty((3, 3))
         with self._lock:
             buf = self.imu_buffer
-            begin = next((i for i, m in enumerate(buf) if m.timestamp >= t_prev - 0.01), None)
-            end = next((i for i, m in enumerate(buf) if m.timestamp >= t_curr - 0.004), None)
-            if begin is None or end is None:
-                return np.identity(3), np.identity(3)
-            window = buf[begin:end]
-            self.imu_buffer = buf[end:]
-        mean_w = np.zeros(3)
-        for m in window:
-            mean_w += m.angular_velocity
-        if end - begin > 0:
-            mean_w /= (end - begin)
-        dt = t_curr - t_prev
-        cam0_R_p_c = rodrigues((self.R_cam0_imu.T @ mean_w) * dt).T
-        cam1_R_p_c = rodrigues((self.R_cam1_imu.T @ mean_w) * dt).T
+            # window scan, mean rate, Rodrigues and the transposes run in C (csrc/avb_host.c: integrate_imu)
+            end = _avbhost.integrate_imu(buf, float(t_prev), float(t_curr), self._R0, self._R1,
+                                         cam0_R_p_c, cam1_R_p_c)
+            if end >= 0:
+                self.imu_buffer = buf[end:]
         return cam0_R_p_c, cam1_R_p_c

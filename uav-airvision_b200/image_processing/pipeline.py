@@ -8,7 +8,7 @@ from collections import defaultdict, namedtuple
 
 import numpy as np
 
-from . import _native
+from . import _avbhost, _native
 from .camera_model import CameraModel
 from .feature_measurment import FeatureMeasurement
 from .feature_meta_data import FeatureMetaData
@@ -53,32 +53,25 @@ class ImageProcessingPipeline:
     # -- the hot path -----------------------------------------------------------------------------------------
     def stereo_callback(self, stereo_msg):
         cam0_msg, cam1_msg = stereo_msg.cam0_msg, stereo_msg.cam1_msg
-        ctx = self._ensure_context(cam0_msg.image)
+        ctx = self._ctx or self._ensure_context(cam0_msg.image)
         imu = self.imu_processor
         imu.cam0_prev_img_msg = self.prev_cam0_msg
         imu.cam0_curr_img_msg = cam0_msg
         R = None
         if not self.first_frame:
             R, _ = imu.integrate_imu_data()
-        st = ctx.staging
-        st[0, 0] = cam0_msg.image
-        st[0, 1] = cam1_msg.image
-        ctx.process_staged(R)
-        hdr, ids, meas = ctx.result(0)
-        self.next_feature_id = int(hdr['next_feature_id'])
+        # host images -> pinned staging -> H2D -> CUDA-graph frame -> D2H -> FeatureMeasurement list, all in C
+        feats, hdr = _avbhost.process_frame(ctx._h.value, cam0_msg.image, cam1_msg.image, R, FeatureMeasurement)
+        self.next_feature_id = hdr[1]
         if not self.first_frame:
             nf = self.num_features
-            nf['before_tracking'] = int(hdr['before_tracking'])
-            if nf['before_tracking']:
-                nf['after_tracking'] = int(hdr['after_tracking'])
-                nf['after_matching'] = int(hdr['after_matching'])
-                nf['after_ransac'] = int(hdr['after_ransac'])
+            nf['before_tracking'] = hdr[2]
+            if hdr[2]:
+                nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = hdr[3], hdr[4], hdr[5]
         self.first_frame = False
         self.prev_cam0_msg = cam0_msg
         self.prev_pyr0 = cam0_msg.image
         self._grid_cache = None
-        FM = FeatureMeasurement
-        feats = [FM(i, a, b, c, d) for i, (a, b, c, d) in zip(ids.tolist(), meas.tolist())]
         return feature_msg(cam0_msg.timestamp, feats)
 
     # -- state read-back (pipeline.prev_features / curr_features of the reference) ---------------------------
