@@ -171,7 +171,8 @@ int  avb_kernels_per_frame(const avb_ctx* ctx);
 void* avb_cuda_stream(avb_ctx* ctx);
 /* Instrumented steady-state frame from a device-resident input block: kernels run serialised with a CUDA
  * event after every stage.  stage_ms[9] = input copy, clear+FAST, pyramid (all levels), track, select,
- * stereo match of new candidates, grid update, publish, result copy.  Advances the stream like a frame. */
+ * stereo match of new candidates, finish (grid update + publish), 0 (reserved), result copy.  Advances the stream
+ * like a frame. */
 int  avb_profile_frame_device(avb_ctx* ctx, const uint8_t* d_block, float* stage_ms);
 /* Per-kernel timing: run the last frame's pyramid kernel `iters` times back to back on the
  * context stream and return the average device ms (bench.py roofline for the HBM-bound stage). */

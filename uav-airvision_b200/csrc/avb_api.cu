@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -143,6 +144,10 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     // strict 3x3 NMS: no two keypoints are 8-neighbours -> at most ceil(gw/2)*ceil(gh/2) per cell
     g.KPC = (((g.gw + 1) / 2) * ((g.gh + 1) / 2) + 3) & ~3;
     g.fast_thr = cfg->fast_threshold;
+    // LK lane mapping: few features in flight (one or a handful of streams) -> 4 warps per feature to shorten the
+    // dependent chain; many -> 1 warp per feature for throughput.  AVB_WPF=1|4 overrides (experiments).
+    g.wpf = ((long long)g.S * g.NMAX <= 4736) ? 4 : 1;      // 4736 = 148 SMs x 32 resident teams
+    if (const char* e = getenv("AVB_WPF")) g.wpf = (atoi(e) == 4) ? 4 : 1;
     g.max_iter = std::min(std::max(cfg->max_iteration, 0), 100);
     g.min_eig = cfg->min_eig_threshold;
     const double eps = std::min(std::max(cfg->track_precision, 0.0), 10.0);
@@ -219,12 +224,12 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     }
 
     // dynamic shared memory of the bookkeeping kernels
-    const size_t sel_smem = ((size_t)g.KPC + g.NMAX) * 4;
+    const size_t sel_smem = (size_t)g.KPC * 4;
     if (sel_smem > 200 * 1024) {
         avb_destroy(c);
         return fail(nullptr, AVB_E_INVALID, "grid cell too large for the selection kernel (%zu B shared)", sel_smem);
     }
-    if (avb_set_smem_limits(sel_smem, (size_t)g.NMAX * 8) != 0) {
+    if (avb_set_smem_limits(sel_smem, (size_t)g.NMAX * 12) != 0) {
         avb_destroy(c);
         return fail(nullptr, AVB_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
     }
@@ -239,18 +244,22 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     }
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
     const size_t img_bytes = (size_t)g.W * g.H;
-    for (int p = 0; p < 2; ++p) {
-        int r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 160, 68);
-        if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 24);
-        if (r != AVB_OK) {
-            g_create_error = c->err;
-            avb_destroy(c);
-            return r;
+    {
+        const int built = g.nlev - 1, pair_at = built >= 2 ? built - 1 : 0;
+        int r = AVB_OK;
+        for (int p = 0; p < 2 && r == AVB_OK; ++p) {
+            r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 160, 36);
+            if (r == AVB_OK) r = make_map(c, enc, &c->maps.pair0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 44);
+            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 24);
         }
-    }
-    for (int l = 1; l < g.nlev - 1; ++l) {
-        int r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
-                         g.slot_bytes, 160, 68);
+        for (int l = 1; l < g.nlev - 1 && r == AVB_OK; ++l)
+            r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
+                         g.slot_bytes, 160, 36);
+        if (pair_at >= 2 && r == AVB_OK) {
+            const int l = pair_at - 1;
+            r = make_map(c, enc, &c->maps.pair, d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
+                         g.slot_bytes, 96, 44);
+        }
         if (r != AVB_OK) {
             g_create_error = c->err;
             avb_destroy(c);
@@ -343,13 +352,12 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
         launch_select(g, d, p, 0, c->st);
         launch_stereo_candidates(g, d, p, c->st);
     }
-    launch_grid_update(g, d, p, first ? 1 : 0, c->st);
-    launch_publish(g, d, p, c->st);
+    launch_finish(g, d, p, first ? 1 : 0, c->st);
 }
 
 // Serialised, instrumented variant of the steady-state chain: one event after every stage on c->st.
-// Stage order: 0 input copy | 1 clear+FAST | 2 pyramid | 3 track | 4 select | 5 stereo(new) | 6 grid update |
-// 7 publish | 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
+// Stage order: 0 input copy | 1 clear+FAST | 2 pyramid | 3 track | 4 select | 5 stereo(new) | 6 finish (grid update +
+// publish) | 7 (unused, 0) | 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
 extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, float* stage_ms /*[9]*/) {
     if (!c || !d_block || !stage_ms) return AVB_E_INVALID;
     if (c->first_frame) return fail(c, AVB_E_STATE, "profile the steady state: process frame 0 first");
@@ -374,9 +382,8 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     CK(cudaEventRecord(ev[5], c->st));
     launch_stereo_candidates(g, d, p, c->st);
     CK(cudaEventRecord(ev[6], c->st));
-    launch_grid_update(g, d, p, 0, c->st);
+    launch_finish(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[7], c->st));
-    launch_publish(g, d, p, c->st);
     CK(cudaEventRecord(ev[8], c->st));
     CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev[9], c->st));
@@ -391,8 +398,8 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
 
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
-    // clear, fast, (nlev-1) pyramid levels, track, select, stereo_candidates, grid_update, publish
-    return 2 + (c->g.nlev - 1) + 5;
+    // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
+    return 2 + avb_pyramid_launches(c->g) + 4;
 }
 
 static int build_graphs(avb_ctx* c) {

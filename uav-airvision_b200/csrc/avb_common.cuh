@@ -22,9 +22,11 @@ struct LevelGeom {
     unsigned long long off;        // byte offset inside one pyramid slot (levels >= 1)
 };
 
-// One image pyramid as the LK code sees it.
+// One image pyramid as the LK code sees it: level 0 is the uploaded image, levels >= 1 sit at
+// arena + Geom::lv[level].off.
 struct PyrView {
-    const uint8_t* lv[AVB_MAX_LEVELS];
+    const uint8_t* l0;
+    const uint8_t* arena;
 };
 
 struct CamModel {
@@ -43,6 +45,7 @@ struct Geom {
     int gmin, gmax;                // per-cell min/max feature counts; gmax = slot capacity of a cell
     int NMAX;                      // NC * gmax
     int KPC;                       // FAST bucket capacity of one cell
+    int wpf;                       // warps per feature in the LK kernels: 4 = latency mapping, 1 = throughput mapping
     int fast_thr;
     int max_iter;
     double min_eig;
@@ -127,11 +130,12 @@ __host__ __device__ inline const double* frame_H(const DevState& d, const Geom& 
 
 __device__ __forceinline__ PyrView pyr_view(const DevState& d, const Geom& g, int s, int slot) {
     PyrView v;
-    uint8_t* b = pyr_slot(d, g, s, slot);
-    v.lv[0] = level0_ptr(d, g, s, slot);
-#pragma unroll
-    for (int l = 1; l < AVB_MAX_LEVELS; ++l) v.lv[l] = b + (l < g.nlev ? g.lv[l].off : 0);
+    v.l0 = level0_ptr(d, g, s, slot);
+    v.arena = pyr_slot(d, g, s, slot);
     return v;
+}
+__device__ __forceinline__ const uint8_t* pyr_level(const PyrView& v, const Geom& g, int level) {
+    return level ? v.arena + g.lv[level].off : v.l0;
 }
 
 __device__ __forceinline__ int refl101(int i, int n) {
@@ -155,19 +159,21 @@ __host__ __device__ inline void kp_decode(unsigned key, int W, int& resp, int& x
 // TMA views (x, y, image).  Level 0: one map per parity over the input block, image = s*2 + cam.
 // Levels >= 1: one map per level over the arena, image = s*4 + slot.  `fast0` has the FAST box shape.
 struct PyrMaps {
-    CUtensorMap l0[2];
-    CUtensorMap lv[AVB_MAX_LEVELS];
+    CUtensorMap l0[2];              // source level 0, box of k_pyr_down
+    CUtensorMap lv[AVB_MAX_LEVELS]; // source level l >= 1, box of k_pyr_down
+    CUtensorMap pair0[2];           // source level 0, box of k_pyr_pair (used when the pair kernel builds levels 1+2)
+    CUtensorMap pair;               // source level nlev-3 >= 1, box of k_pyr_pair
     CUtensorMap fast0[2];
 };
 
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
+int  avb_pyramid_launches(const Geom& g);
 void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);
-void launch_grid_update(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
-void launch_publish(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st);
 int  avb_set_smem_limits(size_t select_bytes, size_t grid_bytes);   // opt in to > 48 KB dynamic shared memory
 // flat point lists (per-stage entry points)

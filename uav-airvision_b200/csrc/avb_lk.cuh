@@ -1,4 +1,4 @@
-// K3/K4 device code: one warp tracks one point through all pyramid levels.
+// K3/K4 device code: a team of WPF warps tracks one point through all pyramid levels.
 //
 // Pyramidal Lucas-Kanade exactly as cv2.calcOpticalFlowPyrLK computes it with
 // OPTFLOW_USE_INITIAL_FLOW, winSize 15x15 (reference call sites: feature_tracker.py:102-108,
@@ -12,33 +12,63 @@
 //   * three loop exits (|delta|^2 <= eps^2 in double, oscillation, window out of bounds), status
 //     decided at level 0 only, final window re-test (the "err" block).
 //
-// Lane mapping: lane = 2*row + half.  Row r in 0..15 of the 16x16 bilinear footprint, half 0 owns window
-// columns 0..7, half 1 columns 8..14.  Every lane fetches its 9 bytes of row r from L1/L2; row r+1 arrives
-// by shuffle from lane+2, so an iteration costs 9 byte loads + 3 shuffles + 4 REDUX per lane.
+// Two lane mappings of the 16x16 bilinear footprint (15x15 window + the row/column below/right):
+//   WPF = 1  (throughput: many streams per launch)   lane = 2*row + half; half 0 owns window columns 0..7,
+//            half 1 columns 8..14; one warp per feature, no shared memory, no block barrier.
+//   WPF = 4  (latency: one stream)   4 warps per feature; a warp owns 4 window rows + the supply row below them,
+//            lane = 6*rr + cg, cg < 5 owns columns 3cg..3cg+2; a thread touches 3 pixels per iteration instead
+//            of 8, the four warps meet in one block barrier per reduction.
+// In both, row r+1 arrives by shuffle from lane + LPR, so every pixel of image B is fetched once per iteration.
 #pragma once
 
 #include "avb_common.cuh"
 
 #define LK_W_BITS 14
 
-struct LKStatic {                   // lane-constant decomposition
-    int lane, r, c0, npx;
+template <int WPF>
+struct LKMap;
+template <>
+struct LKMap<1> {
+    static constexpr int LPR = 2, NPX = 8;
+};
+template <>
+struct LKMap<4> {
+    static constexpr int LPR = 6, NPX = 3;
 };
 
+struct LKStatic {                   // lane-constant decomposition
+    int row, c0, npx;               // window row (0..15; 15 only supplies), first column, active pixels (0 = none)
+};
+
+template <int WPF>
 __device__ __forceinline__ LKStatic lk_static() {
     LKStatic s;
-    s.lane = threadIdx.x & 31;
-    s.r = s.lane >> 1;
-    s.c0 = (s.lane & 1) * 8;
-    s.npx = (s.r < AVB_WIN) ? ((s.lane & 1) ? 7 : 8) : 0;
+    const int lane = threadIdx.x & 31;
+    if (WPF == 1) {
+        s.row = lane >> 1;
+        s.c0 = (lane & 1) * 8;
+        s.npx = (s.row < AVB_WIN) ? ((lane & 1) ? 7 : 8) : 0;
+    } else {
+        const int w = (threadIdx.x >> 5) & 3, rr = lane / 6, cg = lane - rr * 6;
+        s.row = 4 * w + rr;
+        s.c0 = cg * 3;
+        s.npx = (lane < 30 && cg < 5 && rr < 4 && s.row < AVB_WIN) ? 3 : 0;
+    }
     return s;
 }
 
-// exact warp sum of per-lane int32 partials (|v| < 2^31) as int64
-__device__ __forceinline__ long long warp_sum_exact(int v) {
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xffff));
-    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-    return (long long)hi * 65536ll + (long long)lo;
+struct LKShared;
+
+// Exact warp sums of N per-lane int32 partials (|v| < 2^31) as int64: split 16/16 warp REDUX.
+template <int WPF, int N>
+__device__ __forceinline__ void team_sum_exact(const int (&v)[N], long long (&out)[N], LKShared*, int&) {
+    static_assert(WPF == 1, "the 4-warp mapping reduces inline");
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v[i] & 0xffff));
+        const int hi = __reduce_add_sync(0xffffffffu, v[i] >> 16);
+        out[i] = (long long)hi * 65536ll + (long long)lo;
+    }
 }
 
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -69,15 +99,99 @@ struct LKParams {
     int max_iter;
     double min_eig;                 // compared in double, as cv2 does (float minEig vs double threshold)
     double eps2;
+    float eps2_lo, eps2_hi;         // float band around eps2 outside which the float estimate decides (lk_converged)
 };
 
+
+// Template of one window: I, Ix, Iy of this lane's (up to) NPX pixels and the lane's partial structure-tensor sums.
+// (ipx, ipy) = floor(prevPt - halfWin) at this level; weights from its fractional part.
+template <int NPX, int LPR>
+__device__ __forceinline__ void lk_template(const uint8_t* __restrict__ img, int cols, int rows, int pitch, int ipx, int ipy,
+                                            int w00, int w01, int w10, int w11, const LKStatic& L, short (&tI)[NPX],
+                                            short (&tIx)[NPX], short (&tIy)[NPX], int& sA11, int& sA12, int& sA22) {
+    const int y = ipy + L.row, x = ipx + L.c0;          // absolute position of this lane's first sample
+    int up[NPX + 3], mid[NPX + 3], dn[NPX + 3];          // rows y-1, y, y+1; columns x-1 .. x+NPX+1
+    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y - 1, up);
+    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y, mid);
+    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y + 1, dn);
+    // Scharr derivative at (y, x+k), k = 0..NPX; zero outside the level
+    unsigned dcur[NPX + 1], dnxt[NPX + 1];
+    const bool yin = (y >= 0) && (y < rows);
+#pragma unroll
+    for (int k = 0; k <= NPX; ++k) {
+        int dx = 3 * (up[k + 2] - up[k]) + 10 * (mid[k + 2] - mid[k]) + 3 * (dn[k + 2] - dn[k]);
+        int dy = 3 * (dn[k] - up[k]) + 10 * (dn[k + 1] - up[k + 1]) + 3 * (dn[k + 2] - up[k + 2]);
+        const bool in = yin && (x + k >= 0) && (x + k < cols);
+        dx = in ? dx : 0;
+        dy = in ? dy : 0;
+        dcur[k] = ((unsigned)dx & 0xffffu) | ((unsigned)dy << 16);
+    }
+#pragma unroll
+    for (int k = 0; k <= NPX; ++k) dnxt[k] = __shfl_down_sync(0xffffffffu, dcur[k], LPR);
+    sA11 = sA12 = sA22 = 0;
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+        const int iv = (mid[k + 1] * w00 + mid[k + 2] * w01 + dn[k + 1] * w10 + dn[k + 2] * w11 + (1 << (LK_W_BITS - 6))) >>
+                       (LK_W_BITS - 5);
+        const int dx00 = (short)(dcur[k] & 0xffff), dy00 = (int)dcur[k] >> 16;
+        const int dx01 = (short)(dcur[k + 1] & 0xffff), dy01 = (int)dcur[k + 1] >> 16;
+        const int dx10 = (short)(dnxt[k] & 0xffff), dy10 = (int)dnxt[k] >> 16;
+        const int dx11 = (short)(dnxt[k + 1] & 0xffff), dy11 = (int)dnxt[k + 1] >> 16;
+        int ixv = (dx00 * w00 + dx01 * w01 + dx10 * w10 + dx11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+        int iyv = (dy00 * w00 + dy01 * w01 + dy10 * w10 + dy11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+        const bool act = k < L.npx;
+        ixv = act ? ixv : 0;
+        iyv = act ? iyv : 0;
+        tI[k] = (short)iv;
+        tIx[k] = (short)ixv;
+        tIy[k] = (short)iyv;
+        sA11 += ixv * ixv;
+        sA12 += ixv * iyv;
+        sA22 += iyv * iyv;
+    }
+}
+
+// Structure tensor -> (A11, A12, A22, 1/D); false when cv2 rejects the level (minEig / determinant test).
+__device__ __forceinline__ bool lk_tensor(long long q11, long long q12, long long q22, double min_eig_thr, float& A11,
+                                          float& A12, float& A22, float& Dinv) {
+    A11 = __fmul_rn(__ll2float_rn(q11), 9.5367431640625e-07f);
+    A12 = __fmul_rn(__ll2float_rn(q12), 9.5367431640625e-07f);
+    A22 = __fmul_rn(__ll2float_rn(q22), 9.5367431640625e-07f);
+    const float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dif = __fsub_rn(A11, A22);
+    const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * AVB_WIN * AVB_WIN));
+    if ((double)min_eig < min_eig_thr || D < 1.1920929e-07f) return false;
+    Dinv = __fdiv_rn(1.f, D);
+    return true;
+}
+
+// cv2's two loop exits, bit for bit, without the double-precision round trip on the common path:
+//   converged   <=> (double)dx*dx + (double)dy*dy <= eps^2          (criteria.epsilon squared, in double)
+//   oscillating <=> j > 0 and |dx + prev dx| < 0.01 and |dy + prev dy| < 0.01   (float sums compared with the double 0.01)
+// The float32 estimate of |delta|^2 is within 2e-7 relative of the exact value; only inside a 1e-5 band around
+// eps^2 is the exact double expression evaluated.  (double)f < 0.01 <=> f <= 0.01f because 0.01f is the float just
+// below 0.01.
+__device__ __forceinline__ bool lk_converged(float dx, float dy, double eps2, float eps2_lo, float eps2_hi) {
+    const float f = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (f < eps2_lo) return true;
+    if (f > eps2_hi) return false;
+    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2;
+}
+__device__ __forceinline__ bool lk_oscillating(float dx, float dy, float pdx, float pdy) {
+    return fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f;
+}
+
+// ---- WPF = 1: one warp per point, template in registers ------------------------------------------------
 // Tracks (px0, py0) from pyramid A to pyramid B starting at guess (gx, gy).  All arguments and results are
 // warp-uniform.  Returns status (cv2's status byte); (ox, oy) = nextPts[i].
 __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B, const Geom& g, float px0, float py0,
                                               float gx, float gy, const LKParams& prm, float& ox, float& oy) {
-    const LKStatic L = lk_static();
+    constexpr int LPR = LKMap<1>::LPR, NPX = LKMap<1>::NPX;
+    const LKStatic L = lk_static<1>();
     bool status = true;
     float nx = 0.f, ny = 0.f;       // nextPts[i]
+    int flip = 0;
 
     for (int level = prm.nlev - 1; level >= 0; --level) {
         const float sc = __int_as_float((127 - level) << 23);       // 2^-level, exact
@@ -100,68 +214,22 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
-        // ---- template: I, Ix, Iy for this lane's (up to) 8 window pixels -------------------------
-        short tI[8], tIx[8], tIy[8];
-        int sA11 = 0, sA12 = 0, sA22 = 0;
-        {
-            const uint8_t* img = A.lv[level];
-            const int y = ipy + L.r, x = ipx + L.c0;            // absolute position of this lane's first sample
-            int up[11], mid[11], dn[11];                         // rows y-1, y, y+1; columns x-1 .. x+9
-            load_row<11>(img, cols, rows, pitch, x - 1, y - 1, up);
-            load_row<11>(img, cols, rows, pitch, x - 1, y, mid);
-            load_row<11>(img, cols, rows, pitch, x - 1, y + 1, dn);
-            // Scharr derivative at (y, x+k), k = 0..8; zero outside the level
-            unsigned dcur[9];
-            const bool yin = (y >= 0) && (y < rows);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                int dx = 3 * (up[k + 2] - up[k]) + 10 * (mid[k + 2] - mid[k]) + 3 * (dn[k + 2] - dn[k]);
-                int dy = 3 * (dn[k] - up[k]) + 10 * (dn[k + 1] - up[k + 1]) + 3 * (dn[k + 2] - up[k + 2]);
-                const bool in = yin && (x + k >= 0) && (x + k < cols);
-                dx = in ? dx : 0;
-                dy = in ? dy : 0;
-                dcur[k] = ((unsigned)dx & 0xffffu) | ((unsigned)dy << 16);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned dnxt0 = __shfl_down_sync(0xffffffffu, dcur[k], 2);
-                const unsigned dnxt1 = __shfl_down_sync(0xffffffffu, dcur[k + 1], 2);
-                const int iv = (mid[k + 1] * w00 + mid[k + 2] * w01 + dn[k + 1] * w10 + dn[k + 2] * w11 + (1 << (LK_W_BITS - 6))) >>
-                               (LK_W_BITS - 5);
-                const int dx00 = (short)(dcur[k] & 0xffff), dy00 = (int)dcur[k] >> 16;
-                const int dx01 = (short)(dcur[k + 1] & 0xffff), dy01 = (int)dcur[k + 1] >> 16;
-                const int dx10 = (short)(dnxt0 & 0xffff), dy10 = (int)dnxt0 >> 16;
-                const int dx11 = (short)(dnxt1 & 0xffff), dy11 = (int)dnxt1 >> 16;
-                int ixv = (dx00 * w00 + dx01 * w01 + dx10 * w10 + dx11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
-                int iyv = (dy00 * w00 + dy01 * w01 + dy10 * w10 + dy11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
-                const bool act = k < L.npx;
-                ixv = act ? ixv : 0;
-                iyv = act ? iyv : 0;
-                tI[k] = (short)iv;
-                tIx[k] = (short)ixv;
-                tIy[k] = (short)iyv;
-                sA11 += ixv * ixv;
-                sA12 += ixv * iyv;
-                sA22 += iyv * iyv;
-            }
-        }
-        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), 9.5367431640625e-07f);
-        const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), 9.5367431640625e-07f);
-        const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), 9.5367431640625e-07f);
-        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-        const float dif = __fsub_rn(A11, A22);
-        const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
-        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * AVB_WIN * AVB_WIN));
-        if ((double)min_eig < prm.min_eig || D < 1.1920929e-07f) {
+        short tI[NPX], tIx[NPX], tIy[NPX];
+        int sA[3];
+        lk_template<NPX, LPR>(pyr_level(A, g, level), cols, rows, pitch, ipx, ipy, w00, w01, w10, w11, L, tI, tIx, tIy, sA[0],
+                              sA[1], sA[2]);
+        long long qA[3];
+        team_sum_exact<1, 3>(sA, qA, nullptr, flip);
+        float A11, A12, A22, D;
+        if (!lk_tensor(qA[0], qA[1], qA[2], prm.min_eig, A11, A12, A22, D)) {
             if (level == 0) status = false;
             continue;
         }
-        D = __fdiv_rn(1.f, D);
 
         // ---- iterations on image B ------------------------------------------------------------------
         float cx = __fsub_rn(nx, (float)AVB_HALF), cy = __fsub_rn(ny, (float)AVB_HALF);
         float pdx = 0.f, pdy = 0.f;
-        const uint8_t* imgB = B.lv[level];
+        const uint8_t* imgB = pyr_level(B, g, level);
         for (int j = 0; j < prm.max_iter; ++j) {
             const int inx = __float2int_rd(cx), iny = __float2int_rd(cy);
             if (inx < -AVB_WIN || inx >= cols || iny < -AVB_WIN || iny >= rows) {
@@ -169,36 +237,38 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
                 break;
             }
             lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
-            int cur[9];
-            load_row<9>(imgB, cols, rows, pitch, inx + L.c0, iny + L.r, cur);
-            const unsigned p0 = (unsigned)cur[0] | ((unsigned)cur[1] << 8) | ((unsigned)cur[2] << 16) | ((unsigned)cur[3] << 24);
-            const unsigned p1 = (unsigned)cur[4] | ((unsigned)cur[5] << 8) | ((unsigned)cur[6] << 16) | ((unsigned)cur[7] << 24);
-            const unsigned q0 = __shfl_down_sync(0xffffffffu, p0, 2);
-            const unsigned q1 = __shfl_down_sync(0xffffffffu, p1, 2);
-            const int q2 = __shfl_down_sync(0xffffffffu, cur[8], 2);
-            int nxt[9];
-            nxt[0] = q0 & 0xff; nxt[1] = (q0 >> 8) & 0xff; nxt[2] = (q0 >> 16) & 0xff; nxt[3] = q0 >> 24;
-            nxt[4] = q1 & 0xff; nxt[5] = (q1 >> 8) & 0xff; nxt[6] = (q1 >> 16) & 0xff; nxt[7] = q1 >> 24;
-            nxt[8] = q2;
-            int sb1 = 0, sb2 = 0;
+            int cur[NPX + 1], nxt[NPX + 1];
+            load_row<NPX + 1>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row, cur);
+            {
+                const unsigned p0 = (unsigned)cur[0] | ((unsigned)cur[1] << 8) | ((unsigned)cur[2] << 16) | ((unsigned)cur[3] << 24);
+                const unsigned p1 = (unsigned)cur[4] | ((unsigned)cur[5] << 8) | ((unsigned)cur[6] << 16) | ((unsigned)cur[7] << 24);
+                const unsigned q0 = __shfl_down_sync(0xffffffffu, p0, LPR);
+                const unsigned q1 = __shfl_down_sync(0xffffffffu, p1, LPR);
+                nxt[NPX] = __shfl_down_sync(0xffffffffu, cur[NPX], LPR);
+                nxt[0] = q0 & 0xff; nxt[1] = (q0 >> 8) & 0xff; nxt[2] = (q0 >> 16) & 0xff; nxt[3] = q0 >> 24;
+                nxt[4] = q1 & 0xff; nxt[5] = (q1 >> 8) & 0xff; nxt[6] = (q1 >> 16) & 0xff; nxt[7] = q1 >> 24;
+            }
+            int sb[2] = {0, 0};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < NPX; ++k) {
                 const int jv = (cur[k] * w00 + cur[k + 1] * w01 + nxt[k] * w10 + nxt[k + 1] * w11 + (1 << (LK_W_BITS - 6))) >>
                                (LK_W_BITS - 5);
                 const int diff = jv - (int)tI[k];
-                sb1 += diff * (int)tIx[k];              // tIx/tIy are zero for inactive slots
-                sb2 += diff * (int)tIy[k];
+                sb[0] += diff * (int)tIx[k];            // tIx/tIy are zero for inactive slots
+                sb[1] += diff * (int)tIy[k];
             }
-            const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), 9.5367431640625e-07f);
-            const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), 9.5367431640625e-07f);
+            long long qb[2];
+            team_sum_exact<1, 2>(sb, qb, nullptr, flip);
+            const float b1 = __fmul_rn(__ll2float_rn(qb[0]), 9.5367431640625e-07f);
+            const float b2 = __fmul_rn(__ll2float_rn(qb[1]), 9.5367431640625e-07f);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             cx = __fadd_rn(cx, dx);
             cy = __fadd_rn(cy, dy);
             nx = __fadd_rn(cx, (float)AVB_HALF);
             ny = __fadd_rn(cy, (float)AVB_HALF);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= prm.eps2) break;
-            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+            if (lk_converged(dx, dy, prm.eps2, prm.eps2_lo, prm.eps2_hi)) break;
+            if (j > 0 && lk_oscillating(dx, dy, pdx, pdy)) {
                 nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f));
                 ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
                 break;
@@ -214,6 +284,180 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
     ox = nx;
     oy = ny;
     return status;
+}
+
+// ---- WPF = 4: four warps per point (latency mapping) ----------------------------------------------------
+// The template of a level depends only on prevPt, never on the iterations, so the four warps first build the
+// templates of ALL levels concurrently (warp w -> levels w, w+4; 16x2 lane mapping, results to shared memory), then
+// walk the levels together with the 5x6 lane mapping: 3 pixels per thread, both bilinear rows fetched directly
+// (no shuffle on the critical path), one REDUX per sum (60 pixels x 8160 x 4080 < 2^31) and one block barrier per
+// iteration.
+struct LKShared {
+    short I[AVB_MAX_LEVELS][AVB_WIN][16];      // [level][row][col]; col 15 is padding
+    short Ix[AVB_MAX_LEVELS][AVB_WIN][16];
+    short Iy[AVB_MAX_LEVELS][AVB_WIN][16];
+    float A11[AVB_MAX_LEVELS], A12[AVB_MAX_LEVELS], A22[AVB_MAX_LEVELS], Dinv[AVB_MAX_LEVELS];
+    int flag[AVB_MAX_LEVELS];                   // 0 usable, 1 window outside the level, 2 minEig / det reject
+    alignas(16) int red[2][2][4];               // [flip][sum][warp]
+};
+
+__device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B, const Geom& g, float px0, float py0,
+                                              float gx, float gy, const LKParams& prm, LKShared* sh, int& flip, float& ox,
+                                              float& oy) {
+    const int warp = (threadIdx.x >> 5) & 3;
+    __syncthreads();                            // the previous pass is done with the shared templates
+    {
+        constexpr int LPR = LKMap<1>::LPR, NPX = LKMap<1>::NPX;
+        const LKStatic L = lk_static<1>();
+        for (int level = warp; level < prm.nlev; level += 4) {
+            const float sc = __int_as_float((127 - level) << 23);
+            const int cols = g.lv[level].w, rows = g.lv[level].h, pitch = g.lv[level].pitch;
+            const float px = __fsub_rn(__fmul_rn(px0, sc), (float)AVB_HALF), py = __fsub_rn(__fmul_rn(py0, sc), (float)AVB_HALF);
+            const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+            if (ipx < -AVB_WIN || ipx >= cols || ipy < -AVB_WIN || ipy >= rows) {
+                if ((threadIdx.x & 31) == 0) sh->flag[level] = 1;
+                continue;
+            }
+            int w00, w01, w10, w11;
+            lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+            short tI[NPX], tIx[NPX], tIy[NPX];
+            int sA[3];
+            lk_template<NPX, LPR>(pyr_level(A, g, level), cols, rows, pitch, ipx, ipy, w00, w01, w10, w11, L, tI, tIx, tIy,
+                                  sA[0], sA[1], sA[2]);
+            if (L.row < AVB_WIN) {
+#pragma unroll
+                for (int k = 0; k < NPX; ++k) {
+                    if (k < L.npx) {
+                        sh->I[level][L.row][L.c0 + k] = tI[k];
+                        sh->Ix[level][L.row][L.c0 + k] = tIx[k];
+                        sh->Iy[level][L.row][L.c0 + k] = tIy[k];
+                    }
+                }
+            }
+            long long qA[3];
+            int f0 = 0;
+            team_sum_exact<1, 3>(sA, qA, nullptr, f0);
+            float A11, A12, A22, D = 0.f;
+            const bool ok = lk_tensor(qA[0], qA[1], qA[2], prm.min_eig, A11, A12, A22, D);
+            if ((threadIdx.x & 31) == 0) {
+                sh->A11[level] = A11;
+                sh->A12[level] = A12;
+                sh->A22[level] = A22;
+                sh->Dinv[level] = D;
+                sh->flag[level] = ok ? 0 : 2;
+            }
+        }
+    }
+    __syncthreads();
+
+    const LKStatic L = lk_static<4>();
+    bool status = true;
+    float nx = 0.f, ny = 0.f;
+    for (int level = prm.nlev - 1; level >= 0; --level) {
+        const float sc = __int_as_float((127 - level) << 23);
+        if (level == prm.nlev - 1) {
+            nx = __fmul_rn(gx, sc);
+            ny = __fmul_rn(gy, sc);
+        } else {
+            nx = __fmul_rn(nx, 2.f);
+            ny = __fmul_rn(ny, 2.f);
+        }
+        if (sh->flag[level]) {
+            if (level == 0) status = false;
+            continue;
+        }
+        const int cols = g.lv[level].w, rows = g.lv[level].h, pitch = g.lv[level].pitch;
+        const float A11 = sh->A11[level], A12 = sh->A12[level], A22 = sh->A22[level], D = sh->Dinv[level];
+        int tI[3] = {0, 0, 0}, tIx[3] = {0, 0, 0}, tIy[3] = {0, 0, 0};
+        if (L.npx) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                tI[k] = sh->I[level][L.row][L.c0 + k];
+                tIx[k] = sh->Ix[level][L.row][L.c0 + k];
+                tIy[k] = sh->Iy[level][L.row][L.c0 + k];
+            }
+        }
+        float cx = __fsub_rn(nx, (float)AVB_HALF), cy = __fsub_rn(ny, (float)AVB_HALF);
+        float pdx = 0.f, pdy = 0.f;
+        const uint8_t* imgB = pyr_level(B, g, level);
+        for (int j = 0; j < prm.max_iter; ++j) {
+            const int inx = __float2int_rd(cx), iny = __float2int_rd(cy);
+            if (inx < -AVB_WIN || inx >= cols || iny < -AVB_WIN || iny >= rows) {
+                if (level == 0) status = false;
+                break;
+            }
+            int sb1 = 0, sb2 = 0;
+            if (L.npx) {
+                int cur[4], nxt[4];
+                if (inx >= 0 && inx + 16 < cols && iny >= 0 && iny + 16 < rows) {   // team-uniform: window inside the level
+                    const uint8_t* p = imgB + (iny + L.row) * pitch + (inx + L.c0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        cur[k] = __ldg(p + k);
+                        nxt[k] = __ldg(p + pitch + k);
+                    }
+                } else {
+                    load_row<4>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row, cur);
+                    load_row<4>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row + 1, nxt);
+                }
+                int w00, w01, w10, w11;
+                lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int jv = (cur[k] * w00 + cur[k + 1] * w01 + nxt[k] * w10 + nxt[k + 1] * w11 + (1 << (LK_W_BITS - 6))) >>
+                                   (LK_W_BITS - 5);
+                    const int diff = jv - tI[k];
+                    sb1 += diff * tIx[k];
+                    sb2 += diff * tIy[k];
+                }
+            }
+            sb1 = __reduce_add_sync(0xffffffffu, sb1);
+            sb2 = __reduce_add_sync(0xffffffffu, sb2);
+            if ((threadIdx.x & 31) == 0) {
+                sh->red[flip][0][warp] = sb1;
+                sh->red[flip][1][warp] = sb2;
+            }
+            __syncthreads();
+            const int4 r1 = *reinterpret_cast<const int4*>(sh->red[flip][0]);
+            const int4 r2 = *reinterpret_cast<const int4*>(sh->red[flip][1]);
+            flip ^= 1;
+            const long long q1 = ((long long)r1.x + (long long)r1.y) + ((long long)r1.z + (long long)r1.w);
+            const long long q2 = ((long long)r2.x + (long long)r2.y) + ((long long)r2.z + (long long)r2.w);
+            const float b1 = __fmul_rn(__ll2float_rn(q1), 9.5367431640625e-07f);
+            const float b2 = __fmul_rn(__ll2float_rn(q2), 9.5367431640625e-07f);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            cx = __fadd_rn(cx, dx);
+            cy = __fadd_rn(cy, dy);
+            nx = __fadd_rn(cx, (float)AVB_HALF);
+            ny = __fadd_rn(cy, (float)AVB_HALF);
+            if (lk_converged(dx, dy, prm.eps2, prm.eps2_lo, prm.eps2_hi)) break;
+            if (j > 0 && lk_oscillating(dx, dy, pdx, pdy)) {
+                nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f));
+                ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx;
+            pdy = dy;
+        }
+    }
+    if (status) {
+        const int fx = __float2int_rd(__fsub_rn(nx, (float)AVB_HALF)), fy = __float2int_rd(__fsub_rn(ny, (float)AVB_HALF));
+        if (fx < -AVB_WIN || fx >= g.lv[0].w || fy < -AVB_WIN || fy >= g.lv[0].h) status = false;
+    }
+    ox = nx;
+    oy = ny;
+    return status;
+}
+
+template <int WPF>
+__device__ __forceinline__ bool lk_track_team(const PyrView& A, const PyrView& B, const Geom& g, float px0, float py0,
+                                              float gx, float gy, const LKParams& prm, LKShared* sh, int& flip, float& ox,
+                                              float& oy) {
+    if constexpr (WPF == 1)
+        return lk_track_warp(A, B, g, px0, py0, gx, gy, prm, ox, oy);
+    else
+        return lk_track_coop(A, B, g, px0, py0, gx, gy, prm, sh, flip, ox, oy);
 }
 
 // ---- radtan undistort / distort in double (cv2.undistortPoints / projectPoints, Appendix A.5) ----------
@@ -251,33 +495,95 @@ __device__ __forceinline__ void distort_pt(const CamModel& c, double x, double y
     ov = yd * c.fy + c.cy;
 }
 
-// StereoMatcher.stereo_match for one cam0 point (stereo_matcher.py:33-115), warp-uniform.
-// The cam0 model is used for both cameras (Appendix B3); backward-LK status is ignored (B5);
-// the epipolar error keeps only the x-term of the element-wise product (B4).
-__device__ __forceinline__ bool stereo_match_warp(const PyrView& P0, const PyrView& P1, const Geom& g, const LKParams& prm,
-                                                  float x0, float y0, float& x1, float& y1) {
-    double ux, uy, pu, pv;
-    undistort_pt(g.cam0, (double)x0, (double)y0, g.R01, ux, uy);
-    distort_pt(g.cam0, (double)(float)ux, (double)(float)uy, pu, pv);
-    const float gx = (float)pu, gy = (float)pv;                 // proj1 (float32)
-    float fx, fy, bx, by;
-    const bool st_f = lk_track_warp(P0, P1, g, x0, y0, gx, gy, prm, fx, fy);
-    x1 = fx;
-    y1 = fy;
-    if (!st_f) return false;
-    lk_track_warp(P1, P0, g, fx, fy, x0, y0, prm, bx, by);
-    const float ex = __fsub_rn(x0, bx), ey = __fsub_rn(y0, by);
-    const float err = __fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
-    const float disp = fabsf(__fsub_rn(gy, fy));
-    bool ok = (err < 3.f) && (disp < 20.f);
-    ok = ok && !(fx < 0.f || fx >= (float)g.W || fy < 0.f || fy >= (float)g.H);
-    if (!ok) return false;
-    double a0, b0, a1, b1;
-    undistort_pt(g.cam0, (double)x0, (double)y0, nullptr, a0, b0);
-    undistort_pt(g.cam0, (double)fx, (double)fy, nullptr, a1, b1);
-    const double u0x = (double)(float)a0, u0y = (double)(float)b0, u1x = (double)(float)a1;
-    const double l0 = g.E[0] * u0x + g.E[1] * u0y + g.E[2];
-    const double l1 = g.E[3] * u0x + g.E[4] * u0y + g.E[5];
-    const double epi = fabs(u1x * l0) / sqrt(l0 * l0 + l1 * l1);
-    return !(epi > g.epi_thr);
+// One feature through [temporal LK ->] stereo forward LK -> stereo backward LK -> filters, with ONE inlined copy
+// of the LK body (the three passes run through the same code; three copies made the kernel 99 KB and the
+// instruction fetch its top stall).  Team-uniform.
+//   temporal pass  FeatureTracker.track_features steps 3-6 (feature_tracker.py:85-123): LK prev cam0 -> cur cam0
+//                  from the gyro-predicted guess, then the image-bounds cull (> W-1 rule, B6)
+//   stereo passes  StereoMatcher.stereo_match (stereo_matcher.py:33-115): the cam0 model is used for both cameras
+//                  (B3); backward-LK status is ignored (B5); the epipolar error keeps only the x-term (B4)
+struct ChainResult {
+    bool tracked;                   // temporal LK ok and inside the image (always true without the temporal pass)
+    bool matched;                   // stereo inlier
+    float cx, cy;                   // cam0 position in the current frame
+    float x1, y1;                   // cam1 position
+};
+
+template <int WPF>
+__device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevState& d, int s, int parity, bool temporal,
+                                                     float x, float y, float gx, float gy, LKShared* sh) {
+    int flip = 0;
+    LKParams prm;
+    prm.nlev = g.nlev;
+    prm.max_iter = g.max_iter;
+    prm.min_eig = g.min_eig;
+    prm.eps2 = g.eps2;
+    prm.eps2_lo = (float)(g.eps2 * 0.99999);
+    prm.eps2_hi = (float)(g.eps2 * 1.00001);
+    ChainResult r;
+    r.tracked = true;
+    r.matched = false;
+    r.cx = x;
+    r.cy = y;
+    r.x1 = 0.f;
+    r.y1 = 0.f;
+    float projy = 0.f;
+    float ax = x, ay = y, bx = gx, by = gy;
+#pragma unroll 1
+    for (int pass = temporal ? 0 : 1; pass < 3; ++pass) {
+        int slotA, slotB;
+        if (pass == 0) {
+            slotA = SLOT(0, parity ^ 1);
+            slotB = SLOT(0, parity);
+        } else if (pass == 1) {
+            slotA = SLOT(0, parity);
+            slotB = SLOT(1, parity);
+            double ux, uy, pu, pv;                              // infinite-depth prediction (stereo_matcher.py:49-61)
+            undistort_pt(g.cam0, (double)r.cx, (double)r.cy, g.R01, ux, uy);
+            distort_pt(g.cam0, (double)(float)ux, (double)(float)uy, pu, pv);
+            ax = r.cx;
+            ay = r.cy;
+            bx = (float)pu;
+            by = (float)pv;
+            projy = by;
+        } else {
+            slotA = SLOT(1, parity);
+            slotB = SLOT(0, parity);
+            ax = r.x1;
+            ay = r.y1;
+            bx = r.cx;
+            by = r.cy;
+        }
+        const PyrView A = pyr_view(d, g, s, slotA), B = pyr_view(d, g, s, slotB);
+        float ox, oy;
+        const bool st = lk_track_team<WPF>(A, B, g, ax, ay, bx, by, prm, sh, flip, ox, oy);
+        if (pass == 0) {
+            r.cx = ox;
+            r.cy = oy;
+            r.tracked = st && !(ox < 0.f || ox > (float)(g.W - 1) || oy < 0.f || oy > (float)(g.H - 1));
+            if (!r.tracked) break;
+        } else if (pass == 1) {
+            r.x1 = ox;
+            r.y1 = oy;
+            if (!st) break;
+        } else {
+            const float ex = __fsub_rn(r.cx, ox), ey = __fsub_rn(r.cy, oy);
+            const float err = __fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+            const float disp = fabsf(__fsub_rn(projy, r.y1));
+            bool ok = (err < 3.f) && (disp < 20.f);
+            ok = ok && !(r.x1 < 0.f || r.x1 >= (float)g.W || r.y1 < 0.f || r.y1 >= (float)g.H);
+            if (ok) {
+                double a0, b0, a1, b1;
+                undistort_pt(g.cam0, (double)r.cx, (double)r.cy, nullptr, a0, b0);
+                undistort_pt(g.cam0, (double)r.x1, (double)r.y1, nullptr, a1, b1);
+                const double u0x = (double)(float)a0, u0y = (double)(float)b0, u1x = (double)(float)a1;
+                const double l0 = g.E[0] * u0x + g.E[1] * u0y + g.E[2];
+                const double l1 = g.E[3] * u0x + g.E[4] * u0y + g.E[5];
+                const double epi = fabs(u1x * l0) / sqrt(l0 * l0 + l1 * l1);
+                ok = !(epi > g.epi_thr);
+            }
+            r.matched = ok;
+        }
+    }
+    return r;
 }

@@ -5,27 +5,28 @@
 
 #define WARPS_PER_BLOCK 4
 
-__device__ __forceinline__ LKParams make_lk(const Geom& g) {
-    LKParams p;
-    p.nlev = g.nlev;
-    p.max_iter = g.max_iter;
-    p.min_eig = g.min_eig;
-    p.eps2 = g.eps2;
-    return p;
+// Team decomposition of a 128-thread block: WPF = 1 -> four features per block (one warp each), WPF = 4 -> one
+// feature per block.  Returns the feature index; `sh` points at the team's shared scratch.
+template <int WPF>
+__device__ __forceinline__ int team_index(int bx) {
+    return WPF == 1 ? bx * WARPS_PER_BLOCK + (threadIdx.x >> 5) : bx;
 }
 
 // FeatureTracker.track_features, steps 3-8 (feature_tracker.py:85-133) for every previous feature:
 // gyro prediction (K R K^-1) -> temporal LK -> image-bounds cull (> W-1 rule, B6) -> stereo match.
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_track(Geom g, DevState d, int parity) {
+template <int WPF>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_track(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
+                                                                int parity) {
+    __shared__ LKShared sh;
     const int s = blockIdx.y;
-    const int wi = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int wi = team_index<WPF>(blockIdx.x);
+    const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
     if (wi >= g.NMAX) return;
     const GridTable prev = d.grid[parity ^ 1];
     const size_t base = (size_t)s * g.NMAX;
     const int cell = wi / g.gmax, slot = wi - cell * g.gmax;
     if (slot >= prev.count[s * g.NC + cell]) {
-        if (lane == 0) d.t_cell[base + wi] = -1;
+        if (lead) d.t_cell[base + wi] = -1;
         return;
     }
     const float2 p = prev.p0[base + wi];
@@ -35,53 +36,46 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_track(Geom g, DevState
     const double hz = H[6] * (double)p.x + H[7] * (double)p.y + H[8];
     const float gx = (float)(hx / hz), gy = (float)(hy / hz);
 
-    const LKParams prm = make_lk(g);
-    const PyrView Pprev = pyr_view(d, g, s, SLOT(0, parity ^ 1)), Pcur = pyr_view(d, g, s, SLOT(0, parity)),
-                  P1 = pyr_view(d, g, s, SLOT(1, parity));
-    float cx, cy;
-    bool keep = lk_track_warp(Pprev, Pcur, g, p.x, p.y, gx, gy, prm, cx, cy);
-    keep = keep && !(cx < 0.f || cx > (float)(g.W - 1) || cy < 0.f || cy > (float)(g.H - 1));
-    int* cnt = d.counters + s * 8;
-    int new_cell = -1;
-    float x1 = 0.f, y1 = 0.f;
-    if (keep) {
-        const bool ok = stereo_match_warp(Pcur, P1, g, prm, cx, cy, x1, y1);
-        if (ok) new_cell = (int)__fdiv_rn(cy, (float)g.gh) * g.cols + (int)__fdiv_rn(cx, (float)g.gw);
-        if (lane == 0) {
+    const ChainResult r = feature_chain<WPF>(g, d, s, parity, true, p.x, p.y, gx, gy, &sh);
+    if (lead) {
+        int* cnt = d.counters + s * 8;
+        int new_cell = -1;
+        if (r.tracked) {
+            if (r.matched) new_cell = (int)__fdiv_rn(r.cy, (float)g.gh) * g.cols + (int)__fdiv_rn(r.cx, (float)g.gw);
             atomicAdd(&cnt[1], 1);
-            if (ok) atomicAdd(&cnt[2], 1);
+            if (r.matched) atomicAdd(&cnt[2], 1);
         }
-    }
-    if (lane == 0) {
         atomicAdd(&cnt[0], 1);
-        d.t_p0[base + wi] = make_float2(cx, cy);
-        d.t_p1[base + wi] = make_float2(x1, y1);
+        d.t_p0[base + wi] = make_float2(r.cx, r.cy);
+        d.t_p1[base + wi] = make_float2(r.x1, r.y1);
         d.t_cell[base + wi] = new_cell;
     }
 }
 
 // stereo_match of the new-feature candidates (feature_adder.py:79-80)
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_stereo_candidates(Geom g, DevState d, int parity) {
+template <int WPF>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_stereo_candidates(const __grid_constant__ Geom g,
+                                                                            const __grid_constant__ DevState d, int parity) {
+    __shared__ LKShared sh;
     const int s = blockIdx.y;
-    const int wi = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int wi = team_index<WPF>(blockIdx.x);
+    const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
     if (wi >= g.NMAX) return;
     const int cell = wi / g.gmax, j = wi - cell * g.gmax;
     if (j >= d.c_count[s * g.NC + cell]) return;
     const size_t idx = (size_t)s * g.NMAX + wi;
     int resp, x, y;
     kp_decode(d.c_key[idx], g.W, resp, x, y);
-    const LKParams prm = make_lk(g);
-    const PyrView P0 = pyr_view(d, g, s, SLOT(0, parity)), P1 = pyr_view(d, g, s, SLOT(1, parity));
-    float x1, y1;
-    const bool ok = stereo_match_warp(P0, P1, g, prm, (float)x, (float)y, x1, y1);
-    if ((threadIdx.x & 31) == 0) {
-        d.c_p1[idx] = make_float2(x1, y1);
-        d.c_ok[idx] = ok ? 1 : 0;
+    const ChainResult r = feature_chain<WPF>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, &sh);
+    if (lead) {
+        d.c_p1[idx] = make_float2(r.x1, r.y1);
+        d.c_ok[idx] = r.matched ? 1 : 0;
     }
 }
 
 // frame 0: stereo_match of EVERY FAST keypoint before ranking (feature_initializer.py:52-55, B15)
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_stereo_buckets(Geom g, DevState d, int parity) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 8) k_stereo_buckets(const __grid_constant__ Geom g,
+                                                                         const __grid_constant__ DevState d, int parity) {
     const int s = blockIdx.z, cell = blockIdx.y;
     const int j = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int n = min(d.kp_count[s * g.NC + cell], g.KPC);
@@ -89,43 +83,53 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_stereo_buckets(Geom g,
     const size_t idx = ((size_t)s * g.NC + cell) * g.KPC + j;
     int resp, x, y;
     kp_decode(d.kp_key[idx], g.W, resp, x, y);
-    const LKParams prm = make_lk(g);
-    const PyrView P0 = pyr_view(d, g, s, SLOT(0, parity)), P1 = pyr_view(d, g, s, SLOT(1, parity));
-    float x1, y1;
-    const bool ok = stereo_match_warp(P0, P1, g, prm, (float)x, (float)y, x1, y1);
+    const ChainResult r = feature_chain<1>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, nullptr);
     if ((threadIdx.x & 31) == 0) {
-        d.kp_p1[idx] = make_float2(x1, y1);
-        d.kp_ok[idx] = ok ? 1 : 0;
+        d.kp_p1[idx] = make_float2(r.x1, r.y1);
+        d.kp_ok[idx] = r.matched ? 1 : 0;
     }
 }
 
 // ---- flat lists for the per-stage entry points -------------------------------------------------
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_klt_points(Geom g, DevState d, int s, int slot_from, int slot_to,
-                                                                    const float2* prev, const float2* guess, int n, float2* out,
-                                                                    uint8_t* status) {
-    const int wi = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_klt_points(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
+                                                                    int s, int slot_from, int slot_to, const float2* prev,
+                                                                    const float2* guess, int n, float2* out, uint8_t* status,
+                                                                    int wpf) {
+    __shared__ LKShared sh;
+    const int wi = wpf == 1 ? blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5) : blockIdx.x;
     if (wi >= n) return;
-    const LKParams prm = make_lk(g);
+    LKParams prm;
+    prm.nlev = g.nlev;
+    prm.max_iter = g.max_iter;
+    prm.min_eig = g.min_eig;
+    prm.eps2 = g.eps2;
+    prm.eps2_lo = (float)(g.eps2 * 0.99999);
+    prm.eps2_hi = (float)(g.eps2 * 1.00001);
     const PyrView A = pyr_view(d, g, s, slot_from), B = pyr_view(d, g, s, slot_to);
     float ox, oy;
-    const bool st = lk_track_warp(A, B, g, prev[wi].x, prev[wi].y, guess[wi].x, guess[wi].y, prm, ox, oy);
-    if ((threadIdx.x & 31) == 0) {
+    int flip = 0;
+    bool st;
+    if (wpf == 1)
+        st = lk_track_team<1>(A, B, g, prev[wi].x, prev[wi].y, guess[wi].x, guess[wi].y, prm, nullptr, flip, ox, oy);
+    else
+        st = lk_track_team<4>(A, B, g, prev[wi].x, prev[wi].y, guess[wi].x, guess[wi].y, prm, &sh, flip, ox, oy);
+    if ((wpf == 1 ? (threadIdx.x & 31) : threadIdx.x) == 0) {
         out[wi] = make_float2(ox, oy);
         status[wi] = st ? 1 : 0;
     }
 }
 
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_stereo_points(Geom g, DevState d, int s, int parity, const float2* p0,
-                                                                       int n, float2* p1, uint8_t* ok) {
-    const int wi = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+template <int WPF>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_stereo_points(const __grid_constant__ Geom g,
+                                                                       const __grid_constant__ DevState d, int s, int parity,
+                                                                       const float2* p0, int n, float2* p1, uint8_t* ok) {
+    __shared__ LKShared sh;
+    const int wi = team_index<WPF>(blockIdx.x);
     if (wi >= n) return;
-    const LKParams prm = make_lk(g);
-    const PyrView P0 = pyr_view(d, g, s, SLOT(0, parity)), P1 = pyr_view(d, g, s, SLOT(1, parity));
-    float x1, y1;
-    const bool r = stereo_match_warp(P0, P1, g, prm, p0[wi].x, p0[wi].y, x1, y1);
-    if ((threadIdx.x & 31) == 0) {
-        p1[wi] = make_float2(x1, y1);
-        ok[wi] = r ? 1 : 0;
+    const ChainResult r = feature_chain<WPF>(g, d, s, parity, false, p0[wi].x, p0[wi].y, 0.f, 0.f, &sh);
+    if ((WPF == 1 ? (threadIdx.x & 31) : threadIdx.x) == 0) {
+        p1[wi] = make_float2(r.x1, r.y1);
+        ok[wi] = r.matched ? 1 : 0;
     }
 }
 
@@ -150,13 +154,21 @@ __global__ void k_undistort(CamModel cam, const double* xy, int n, const double*
     out[2 * i + 1] = oy;
 }
 
+static inline int teams_grid(int n, int wpf) { return wpf == 1 ? (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : n; }
+
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
-    dim3 grid((g.NMAX + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.S);
-    k_track<<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
+    if (g.wpf == 1)
+        k_track<1><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    else
+        k_track<4><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
 }
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
-    dim3 grid((g.NMAX + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.S);
-    k_stereo_candidates<<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
+    if (g.wpf == 1)
+        k_stereo_candidates<1><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    else
+        k_stereo_candidates<4><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
 }
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid((g.KPC + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.NC, g.S);
@@ -165,13 +177,17 @@ void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStr
 void launch_klt_points(const Geom& g, const DevState& d, int s, int slot_from, int slot_to, const float2* prev,
                        const float2* guess, int n, float2* out, uint8_t* status, cudaStream_t st) {
     if (n <= 0) return;
-    k_klt_points<<<(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, s, slot_from, slot_to, prev,
-                                                                                                 guess, n, out, status);
+    const int wpf = n <= 2048 ? g.wpf : 1;
+    k_klt_points<<<teams_grid(n, wpf), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, s, slot_from, slot_to, prev, guess, n, out, status, wpf);
 }
 void launch_stereo_points(const Geom& g, const DevState& d, int s, int parity, const float2* p0, int n, float2* p1,
                           uint8_t* ok, cudaStream_t st) {
     if (n <= 0) return;
-    k_stereo_points<<<(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, s, parity, p0, n, p1, ok);
+    const int wpf = n <= 2048 ? g.wpf : 1;
+    if (wpf == 1)
+        k_stereo_points<1><<<teams_grid(n, 1), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, s, parity, p0, n, p1, ok);
+    else
+        k_stereo_points<4><<<teams_grid(n, 4), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, s, parity, p0, n, p1, ok);
 }
 void launch_undistort(const CamModel& cam, const double* xy, int n, const double* R, int has_R, int f32_io, int distort,
                       double* out, cudaStream_t st) {

@@ -1,23 +1,33 @@
-// K1: pyramid build.  One launch per level: dst(x,y) = (sum_{i,j} k_i k_j src(2x+i, 2y+j) + 128) >> 8,
-// k = [1 4 6 4 1], BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2)   (cv2.pyrDown as
-// calcOpticalFlowPyrLK uses it; reference call sites feature_tracker.py:102, stereo_matcher.py:64,70;
-// the reference's own PyramidBuilder is a no-op, pyramid_builder.py:30-48).
+// K1: pyramid build.  dst(x,y) = (sum_{i,j} k_i k_j src(2x+i, 2y+j) + 128) >> 8, k = [1 4 6 4 1],
+// BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2)   (cv2.pyrDown as calcOpticalFlowPyrLK uses it; reference call
+// sites feature_tracker.py:102, stereo_matcher.py:64,70; the reference's own PyramidBuilder is a no-op,
+// pyramid_builder.py:30-48).
 //
-// Each CTA produces a 64x32 tile of the destination level.  The (2*64+4) x (2*32+4) source
-// footprint is staged into shared memory by ONE TMA tensor copy (cp.async.bulk.tensor.3d, box
-// 160 x 68 x 1 over the (x, y, image) view of the pyramid arena; out-of-image elements arrive as
-// zeros and are never read because taps are reflected first).  The TMA start column must be a
-// multiple of 16 bytes (measured on B200: any other inner coordinate raises "illegal instruction"),
-// so the box starts 16 columns left of the tile instead of 2.  Horizontal 5-tap pass -> u16
-// shared buffer -> vertical pass; every thread emits 16 output pixels with one 128-bit store.
+// k_pyr_down   one level.  Each CTA produces a 64x16 tile of the destination level.  The (2*64+4) x (2*16+4) source
+//              footprint is staged into shared memory by ONE TMA tensor copy (cp.async.bulk.tensor.3d, box 160 x 36 x 1
+//              over the (x, y, image) view; out-of-image elements arrive as zeros and are never read because taps are
+//              reflected first).  The TMA start column must be a multiple of 16 bytes (measured on B200: any other
+//              inner coordinate raises "illegal instruction"), so the box starts 16 columns left of the tile instead
+//              of 2.  Horizontal 5-tap pass -> u16 shared buffer -> vertical pass -> 32-bit stores, 64 B per row segment.
+// k_pyr_pair   the LAST TWO levels in one launch (they are tiny and launch-latency bound): a CTA owns a 16x8 tile of
+//              level l+1 and the 32x16 block of level l under it; it recomputes the 2-pixel halo of level l it needs
+//              from a 96 x 44 TMA box of level l-1.
 #include "avb_common.cuh"
 
 #define PT_W 64
-#define PT_H 32
+#define PT_H 16
 #define PB_W 160                    // box width: 16 left halo (alignment) + 2*PT_W + 16, multiple of 16 bytes
 #define PB_X 16                     // columns between the box start and the tile's first source column
-#define PB_H 68                     // box height (2*PT_H + 4)
-#define HB_PITCH 72                 // u16 pitch of the horizontal-pass buffer (bank spread)
+#define PB_H 36                     // box height (2*PT_H + 4)
+#define HB_PITCH 66                 // u16 pitch of the horizontal-pass buffer (bank spread)
+
+#define QT_W 16                     // pair kernel: tile of level l+1
+#define QT_H 8
+#define QM_W 36                     // level-l region: 2*QT_W + 4
+#define QM_H 20
+#define QB_W 96                     // box of level l-1: 10 left halo (16-aligned start) + 2*QM_W + 4 = 86 -> 96
+#define QB_X 10
+#define QB_H 44                     // 2*QM_H + 4
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -45,8 +55,8 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-__global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ CUtensorMap src_map, Geom g, DevState d,
-                                                  int level /*dst*/, int parity) {
+__global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Geom g,
+                                                  const __grid_constant__ DevState d, int level /*dst*/, int parity) {
     __shared__ __align__(128) uint8_t tile[PB_H][PB_W];
     __shared__ __align__(16) unsigned short hbuf[PB_H][HB_PITCH];
     __shared__ __align__(8) uint64_t bar;
@@ -71,12 +81,16 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ CUtens
 
     // horizontal pass at the even source columns of this tile
     const int dx0 = PT_W * blockIdx.x, dy0 = PT_H * blockIdx.y;
-    for (int i = tid; i < PB_H * PT_W; i += 128) {
+    const bool inner_x = (2 * dx0 - 2 >= 0) && (2 * (dx0 + PT_W - 1) + 2 < ls.w);
+    for (int i = tid; i < PB_H * PT_W; i += 256) {
         const int r = i / PT_W, x = i % PT_W;
         const int sx = 2 * (dx0 + x);
         int v = 0;
-        if (dx0 + x < ld.w) {
-            const uint8_t* row = tile[r];
+        const uint8_t* row = tile[r];
+        if (inner_x) {
+            const uint8_t* q = row + (sx - x0);
+            v = q[-2] + 4 * q[-1] + 6 * q[0] + 4 * q[1] + q[2];
+        } else if (dx0 + x < ld.w) {
             const int c0 = refl101(sx - 2, ls.w) - x0, c1 = refl101(sx - 1, ls.w) - x0, c2 = sx - x0;
             const int c3 = refl101(sx + 1, ls.w) - x0, c4 = refl101(sx + 2, ls.w) - x0;
             v = row[c0] + 4 * row[c1] + 6 * row[c2] + 4 * row[c3] + row[c4];
@@ -85,33 +99,128 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ CUtens
     }
     __syncthreads();
 
-    // vertical pass: thread -> 16 consecutive destination pixels of one row
-    const int ry = tid >> 2, cx = (tid & 3) * 16;
+    // vertical pass: thread -> 4 consecutive destination pixels of one row
+    const int ry = tid >> 4, cx = (tid & 15) * 4;
     const int dy = dy0 + ry, dx = dx0 + cx;
     if (dy < ld.h && dx < ld.pitch) {
         const int sy = 2 * dy;
         const int r0 = refl101(sy - 2, ls.h) - y0, r1 = refl101(sy - 1, ls.h) - y0, r2 = sy - y0;
         const int r3 = refl101(sy + 1, ls.h) - y0, r4 = refl101(sy + 2, ls.h) - y0;
-        unsigned out[4];
+        unsigned w = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned w = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int x = cx + q * 4 + k;
-                const int v = hbuf[r0][x] + 4 * hbuf[r1][x] + 6 * hbuf[r2][x] + 4 * hbuf[r3][x] + hbuf[r4][x];
-                w |= (unsigned)((v + 128) >> 8) << (8 * k);
-            }
-            out[q] = w;
+        for (int k = 0; k < 4; ++k) {
+            const int x = cx + k;
+            const int v = hbuf[r0][x] + 4 * hbuf[r1][x] + 6 * hbuf[r2][x] + 4 * hbuf[r3][x] + hbuf[r4][x];
+            w |= (unsigned)((v + 128) >> 8) << (8 * k);
         }
         uint8_t* dst = pyr_slot(d, g, s, slot) + ld.off + (size_t)dy * ld.pitch + dx;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<unsigned*>(dst) = w;
+    }
+}
+
+// levels `level` and `level + 1` from level `level - 1`
+__global__ void __launch_bounds__(256) k_pyr_pair(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Geom g,
+                                                  const __grid_constant__ DevState d, int level, int parity) {
+    __shared__ __align__(128) uint8_t tile[QB_H][QB_W];
+    __shared__ unsigned short hbuf[QB_H][QM_W + 2];
+    __shared__ uint8_t mid[QM_H][QM_W + 4];
+    __shared__ unsigned short hbuf2[QM_H][QT_W + 2];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int s = blockIdx.z >> 1, cam = blockIdx.z & 1;
+    const int slot = SLOT(cam, parity);
+    const int img = (level == 1) ? (s * 2 + cam) : (s * SLOTS_PER_STREAM + slot);
+    const LevelGeom l0 = g.lv[level - 1], l1 = g.lv[level], l2 = g.lv[level + 1];
+    const int X2 = QT_W * blockIdx.x, Y2 = QT_H * blockIdx.y;       // tile origin in level+1
+    const int X1 = 2 * X2 - 2, Y1 = 2 * Y2 - 2;                     // region origin in level
+    const int x0 = 2 * X1 - 2 - QB_X, y0 = 2 * Y1 - 2;              // box origin in level-1 (x0 is a multiple of 16)
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, QB_W * QB_H);
+        tma_load_3d(&tile[0][0], &src_map, &bar, x0, y0, img);
+    }
+    mbar_wait(&bar, 0);
+
+    // level: horizontal pass over the box rows, at region columns X1 .. X1+QM_W-1 that exist in the level
+    for (int i = tid; i < QB_H * QM_W; i += 256) {
+        const int r = i / QM_W, x = i % QM_W;
+        const int X = X1 + x;
+        int v = 0;
+        if (X >= 0 && X < l1.w) {
+            const uint8_t* row = tile[r];
+            const int sx = 2 * X;
+            const int c0 = refl101(sx - 2, l0.w) - x0, c1 = refl101(sx - 1, l0.w) - x0, c2 = sx - x0;
+            const int c3 = refl101(sx + 1, l0.w) - x0, c4 = refl101(sx + 2, l0.w) - x0;
+            v = row[c0] + 4 * row[c1] + 6 * row[c2] + 4 * row[c3] + row[c4];
+        }
+        hbuf[r][x] = (unsigned short)v;
+    }
+    __syncthreads();
+    // level: vertical pass -> mid (the region of `level` this CTA needs); its inner 32x16 block goes to memory
+    uint8_t* out1 = pyr_slot(d, g, s, slot) + l1.off;
+    for (int i = tid; i < QM_H * QM_W; i += 256) {
+        const int r = i / QM_W, x = i % QM_W;
+        const int X = X1 + x, Y = Y1 + r;
+        int v = 0;
+        if (X >= 0 && X < l1.w && Y >= 0 && Y < l1.h) {
+            const int sy = 2 * Y;
+            const int r0 = refl101(sy - 2, l0.h) - y0, r1 = refl101(sy - 1, l0.h) - y0, r2 = sy - y0;
+            const int r3 = refl101(sy + 1, l0.h) - y0, r4 = refl101(sy + 2, l0.h) - y0;
+            v = (hbuf[r0][x] + 4 * hbuf[r1][x] + 6 * hbuf[r2][x] + 4 * hbuf[r3][x] + hbuf[r4][x] + 128) >> 8;
+            if (x >= 2 && x < QM_W - 2 && r >= 2 && r < QM_H - 2) out1[(size_t)Y * l1.pitch + X] = (uint8_t)v;
+        }
+        mid[r][x] = (uint8_t)v;
+    }
+    __syncthreads();
+    // level+1: horizontal pass over the region rows
+    for (int i = tid; i < QM_H * QT_W; i += 256) {
+        const int r = i / QT_W, x = i % QT_W;
+        const int X = X2 + x;
+        int v = 0;
+        if (X < l2.w) {
+            const uint8_t* row = mid[r];
+            const int sx = 2 * X;
+            const int c0 = refl101(sx - 2, l1.w) - X1, c1 = refl101(sx - 1, l1.w) - X1, c2 = sx - X1;
+            const int c3 = refl101(sx + 1, l1.w) - X1, c4 = refl101(sx + 2, l1.w) - X1;
+            v = row[c0] + 4 * row[c1] + 6 * row[c2] + 4 * row[c3] + row[c4];
+        }
+        hbuf2[r][x] = (unsigned short)v;
+    }
+    __syncthreads();
+    if (tid < QT_W * QT_H) {
+        const int r = tid / QT_W, x = tid % QT_W;
+        const int X = X2 + x, Y = Y2 + r;
+        if (X < l2.w && Y < l2.h) {
+            const int sy = 2 * Y;
+            const int r0 = refl101(sy - 2, l1.h) - Y1, r1 = refl101(sy - 1, l1.h) - Y1, r2 = sy - Y1;
+            const int r3 = refl101(sy + 1, l1.h) - Y1, r4 = refl101(sy + 2, l1.h) - Y1;
+            const int v = hbuf2[r0][x] + 4 * hbuf2[r1][x] + 6 * hbuf2[r2][x] + 4 * hbuf2[r3][x] + hbuf2[r4][x];
+            (pyr_slot(d, g, s, slot) + l2.off)[(size_t)Y * l2.pitch + X] = (uint8_t)((v + 128) >> 8);
+        }
     }
 }
 
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st) {
-    for (int l = 1; l < g.nlev; ++l) {
+    const int built = g.nlev - 1;                       // levels 1..built
+    const int pair_at = built >= 2 ? built - 1 : 0;     // the pair kernel builds levels pair_at and pair_at + 1
+    for (int l = 1; l <= built; ++l) {
+        if (l == pair_at) {
+            dim3 grid((g.lv[l + 1].w + QT_W - 1) / QT_W, (g.lv[l + 1].h + QT_H - 1) / QT_H, 2 * g.S);
+            k_pyr_pair<<<grid, 256, 0, st>>>(l == 1 ? maps.pair0[parity] : maps.pair, g, d, l, parity);
+            break;
+        }
         dim3 grid((g.lv[l].w + PT_W - 1) / PT_W, (g.lv[l].h + PT_H - 1) / PT_H, 2 * g.S);
-        k_pyr_down<<<grid, 128, 0, st>>>(l == 1 ? maps.l0[parity] : maps.lv[l - 1], g, d, l, parity);
+        k_pyr_down<<<grid, 256, 0, st>>>(l == 1 ? maps.l0[parity] : maps.lv[l - 1], g, d, l, parity);
     }
+}
+
+int avb_pyramid_launches(const Geom& g) {
+    const int built = g.nlev - 1;
+    return built >= 2 ? built - 1 : built;
 }
