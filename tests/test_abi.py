@@ -126,3 +126,71 @@ def test_host_extension_imu_integration_matches_python_rule():
         assert np.abs(R0 - rodrigues((imu.R_cam0_imu.T @ w) * (tc - tp)).T).max() < 1e-15
         assert np.abs(R1 - rodrigues((imu.R_cam1_imu.T @ w) * (tc - tp)).T).max() < 1e-15
         assert imu.imu_buffer == buf[e:]
+
+
+def test_package_exports_match_the_reference_surface():
+    """Same export list as the reference's image_processing/__init__.py:1-12 (+ ImageProcessor with the legacy alias,
+    :14-27); constructor parameter names of the stage classes as the reference's pipeline passes them."""
+    import inspect
+    import image_processing as ip
+    for name in ('ImageProcessingPipeline', 'CameraModel', 'IMUProcessor', 'PyramidBuilder', 'FeatureMetaData',
+                 'FeatureMeasurement', 'FeatureInitializer', 'FeatureAdder', 'FeatureTracker', 'FeaturePruner',
+                 'StereoMatcher', 'FeaturePublisher', 'ImageProcessor'):
+        assert hasattr(ip, name), name
+    assert ip.ImageProcessor.stareo_callback is ip.ImageProcessingPipeline.stereo_callback
+    want = {
+        ip.PyramidBuilder: ['win_size', 'pyramid_levels', 'cam0_curr_img_msg', 'cam1_curr_img_msg'],
+        ip.StereoMatcher: ['lk_params', 'imu_processor', 'pyramid_builder', 'camera_model', 'stereo_threshold'],
+        ip.FeatureInitializer: ['detector', 'stereo_matcher', 'config', 'cam0_curr_img_msg', 'curr_features',
+                                'next_feature_id', 'grid_row', 'grid_col', 'grid_min_feature_num'],
+        ip.FeatureAdder: ['detector', 'stereo_matcher', 'config', 'cam0_curr_img_msg', 'curr_features', 'next_feature_id',
+                          'grid_row', 'grid_col', 'grid_max_feature_num', 'grid_min_feature_num'],
+        ip.FeatureTracker: ['lk_params', 'imu_processor', 'stereo_matcher', 'cam0_intrinsics', 'cam0_distortion_model',
+                            'cam0_distortion_coeffs', 'cam1_intrinsics', 'cam1_distortion_model', 'cam1_distortion_coeffs',
+                            'prev_cam0_pyramid', 'curr_cam0_pyramid', 'prev_features', 'curr_features', 'num_features',
+                            'grid_row', 'grid_col', 'ransac_threshold'],
+        ip.FeaturePruner: ['grid_max_feature_num'],
+        ip.FeaturePublisher: ['cam0_intrinsics', 'cam0_dist_model', 'cam0_dist_coeffs', 'cam1_intrinsics',
+                              'cam1_dist_model', 'cam1_dist_coeffs'],
+        ip.CameraModel: ['intrinsics', 'distortion_model', 'distortion_coeffs'],
+        ip.IMUProcessor: ['T_imu_cam0', 'T_imu_cam1'],
+    }
+    for cls, names in want.items():
+        params = [p for p in inspect.signature(cls.__init__).parameters if p != 'self']
+        assert params[:len(names)] == names, (cls.__name__, params)
+
+
+def test_host_side_stage_logic_without_gpu():
+    """FeaturePruner and FeatureTracker.predict_feature_tracking are pure host code: check them against the rules
+    (stable lifetime ranking, B9; H = K R K^-1 in float64 -> float32)."""
+    from image_processing import FeatureMetaData, FeaturePruner, FeatureTracker, IMUProcessor
+    from oracle.configs import config_default
+    cfg = config_default()
+    feats = []
+    for i, life in enumerate([3, 7, 7, 1, 7, 2, 9]):
+        f = FeatureMetaData()
+        f.id, f.lifetime = i, life
+        feats.append(f)
+    pr = FeaturePruner(cfg.grid_max_feature_num)
+    pr.curr_features, pr.config = [list(feats), feats[:2]], cfg
+    pr.prune_features()
+    assert [f.id for f in pr.curr_features[0]] == [6, 1, 2, 4, 0] and len(pr.curr_features[1]) == 2
+
+    class _SM:
+        stereo_match = None
+    imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    tr = FeatureTracker(cfg.lk_params, imu, _SM(), cfg.cam0_intrinsics, 'radtan', cfg.cam0_distortion_coeffs,
+                        cfg.cam1_intrinsics, 'radtan', cfg.cam1_distortion_coeffs, None, None, [], [], {}, 4, 5, 3)
+    from image_processing.imu_processor import rodrigues
+    R = rodrigues(np.array([0.01, -0.02, 0.015]))
+    pts = np.array([[10.5, 20.25], [700.0, 400.0]], np.float32)
+    got = tr.predict_feature_tracking(pts, R, cfg.cam0_intrinsics)
+    fx, fy, cx, cy = cfg.cam0_intrinsics
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    H = K @ R @ np.linalg.inv(K)
+    exp = []
+    for p in pts:
+        h = H @ np.array([p[0], p[1], 1.0])
+        exp.append([h[0] / h[2], h[1] / h[2]])
+    assert got.dtype == np.float32 and np.array_equal(got, np.array(exp, np.float32))
+    assert tr.get_grid_size(np.zeros((480, 752), np.uint8)) == (120, 151)

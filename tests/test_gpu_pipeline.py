@@ -152,3 +152,112 @@ def test_multi_stream_context_equals_single_streams():
             for a, b in zip(c.features(s), singles[s][k][2]):
                 assert np.array_equal(a, b)
     c.close()
+
+
+@pytest.mark.parametrize('name', ['ref_default_s0', 'ref_c1_gyro_s2'])
+def test_staged_pipeline_matches_reference_golden(name, golden_dir):
+    """mode='staged' = the reference's own orchestration over this package's stage classes (PyramidBuilder,
+    StereoMatcher, FeatureInitializer, FeatureTracker, FeatureAdder, FeaturePruner, FeaturePublisher), every stage a
+    separate libavb call.  Must give what the unmodified reference gave, incl. the u0/v0 dtype quirk (B11)."""
+    from image_processing import ImageProcessor
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    gr, gc, gmin, gmax, skw = CASES[name]
+    cfg = FrontEndConfig(grid_row=gr, grid_col=gc, grid_min=gmin, grid_max=gmax)
+    ip = ImageProcessor(cfg, mode='staged')
+    frames = []
+
+    def on_frame(k, msg, fm):
+        feats = [f for cell in ip.prev_features for f in cell]
+        cells = [c for c, cell in enumerate(ip.prev_features) for _ in cell]
+        frames.append(dict(ids=np.array([f.id for f in feats], np.int64), cell=np.array(cells, np.int64),
+                           life=np.array([f.lifetime for f in feats], np.int64),
+                           p0=np.array([f.cam0_point for f in feats], np.float64).reshape(-1, 2),
+                           p1=np.array([f.cam1_point for f in feats], np.float64).reshape(-1, 2),
+                           pub=np.array([[f.u0, f.v0, f.u1, f.v1] for f in fm.features], np.float64).reshape(-1, 4),
+                           u0_f64=len(fm.features) > 0 and np.asarray(fm.features[0].u0).dtype == np.float64,
+                           counters=dict(ip.num_features)))
+
+    msgs = run_stream(ip, SlidingTextureStream(**skw), on_frame=on_frame)
+    n = int(g['n_frames'][0])
+    ref = [dict(ids=g[f'f{k}_ids'], cell=g[f'f{k}_cell'], life=g[f'f{k}_life'], p0=g[f'f{k}_p0'],
+                p1=g[f'f{k}_p1'], pub=g[f'f{k}_pub']) for k in range(n)]
+    worst = _compare(frames, ref)
+    print(f'staged {name}: worst position deviation {worst:.3g} px')
+    for k, (fm, f) in enumerate(zip(msgs, frames)):
+        assert [x.id for x in fm.features] == list(g[f'f{k}_pub_ids'])
+        assert bool(f['u0_f64']) == bool(g[f'f{k}_u0_is_f64'][0]) or len(fm.features) == 0
+        if k > 0:
+            c = f['counters']
+            assert [c.get('before_tracking', -1), c.get('after_tracking', -1), c.get('after_matching', -1),
+                    c.get('after_ransac', -1)] == list(g[f'f{k}_counters'])
+    assert ip.next_feature_id == int(g['next_feature_id'][0])
+    ip.context.close()
+
+
+def test_stage_classes_individually():
+    """StereoMatcher / FastDetector / CameraModel / FeaturePublisher with the reference's call signatures."""
+    from image_processing import (CameraModel, FastDetector, FeatureMetaData, FeaturePublisher, IMUProcessor, PyramidBuilder,
+                                  StereoMatcher, create_context)
+    from oracle import cv_semantics as cs
+    cfg = FrontEndConfig()
+    st = SlidingTextureStream(n_frames=2, seed=4, sigma=2.5)
+    f0 = st.frame(0)
+    ctx = create_context(cfg, 752, 480, use_graph=False)
+    imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    cam = CameraModel(cfg.cam0_intrinsics, cfg.cam0_distortion_model, cfg.cam0_distortion_coeffs)
+    pb = PyramidBuilder(cfg.win_size, cfg.pyramid_levels, f0.cam0_msg, f0.cam1_msg)
+    pyr0, pyr1 = pb.create_image_pyramids()
+    assert pyr0 is f0.cam0_image and pb.curr_cam1_pyramid is f0.cam1_image
+    det = FastDetector(cfg.fast_threshold, lambda img: ctx)
+    kps = det.detect(f0.cam0_image)
+    exs, eys, ers = cs.fast_detect(f0.cam0_image, cfg.fast_threshold)
+    assert [k.pt for k in kps] == [(float(x), float(y)) for x, y in zip(exs, eys)]
+    assert [k.response for k in kps] == [float(r) for r in ers]
+    sm = StereoMatcher(cfg.lk_params, imu, pb, cam, cfg.stereo_threshold)
+    assert len(sm.stereo_match([])[0]) == 0
+    pts0 = [k.pt for k in kps[:400]]
+    p1, ok = sm.stereo_match(pts0)
+    port = FrontEndPort(cfg, backend='cv2')
+    ep1, eok = port.stereo_match(f0.cam0_image, f0.cam1_image, pts0)
+    assert (ok == eok).mean() >= 0.995
+    both = ok & eok
+    assert both.sum() > 200 and np.abs(p1[both] - ep1[both]).max() <= 0.01
+    pub = FeaturePublisher(cfg.cam0_intrinsics, cfg.cam0_distortion_model, cfg.cam0_distortion_coeffs,
+                           cfg.cam1_intrinsics, cfg.cam1_distortion_model, cfg.cam1_distortion_coeffs)
+    feats = []
+    for i in np.nonzero(both)[0][:20]:
+        fm = FeatureMetaData()
+        fm.id, fm.lifetime, fm.cam0_point, fm.cam1_point = int(i), 1, pts0[i], p1[i]
+        feats.append(fm)
+    pub.cam0_curr_img_msg, pub.cam1_curr_img_msg, pub.curr_features = f0.cam0_msg, f0.cam1_msg, [feats]
+    msg = pub.publish()
+    assert msg.timestamp == f0.cam0_msg.timestamp and [m.id for m in msg.features] == [f.id for f in feats]
+    eu0 = cs.undistort_radtan(np.array([f.cam0_point for f in feats]), cfg.cam0_intrinsics, cfg.cam0_distortion_coeffs)
+    eu1 = cs.undistort_radtan(np.array([f.cam1_point for f in feats]), cfg.cam1_intrinsics, cfg.cam1_distortion_coeffs)
+    got = np.array([[m.u0, m.v0, m.u1, m.v1] for m in msg.features], np.float64)
+    assert np.abs(got[:, :2] - eu0).max() < 1e-12 and np.abs(got[:, 2:] - eu1).max() < 1e-6
+    ctx.close()
+
+
+def test_multi_stream_front_end_replay_equals_single_pipelines():
+    """MultiStreamFrontEnd + replay (deterministic lock-step driver, one launch chain for all streams) publishes
+    exactly what one ImageProcessor per stream publishes, IMU handling included."""
+    from image_processing import ImageProcessor
+    from multi_stream import MultiStreamFrontEnd, replay, stream_stats
+    cfg = FrontEndConfig(grid_row=5, grid_col=6)
+    kws = [dict(n_frames=6, seed=30 + s, sigma=2.0 + 0.4 * s, drift=(1.0 + 0.3 * s, -0.5), gyro=(0.01 * s, -0.02, 0.03),
+                noise=0.5 * s) for s in range(3)]
+    singles = []
+    for kw in kws:
+        ip = ImageProcessor(cfg)
+        singles.append(run_stream(ip, SlidingTextureStream(**kw)))
+        ip.context.close()
+    fe = MultiStreamFrontEnd(cfg, 752, 480, 3)
+    multi = replay(fe, [SlidingTextureStream(**kw) for kw in kws])
+    for s in range(3):
+        assert len(multi[s]) == len(singles[s]) == 6
+        for a, b in zip(multi[s], singles[s]):
+            assert a.timestamp == b.timestamp
+            assert [(f.id, f.u0, f.v0, f.u1, f.v1) for f in a.features] == [(f.id, f.u0, f.v0, f.u1, f.v1) for f in b.features]
+        assert stream_stats(s, multi[s])['features'] == sum(len(m.features) for m in singles[s])
+    fe.close()

@@ -203,6 +203,96 @@ static PyObject* py_process_frame(PyObject* self, PyObject* args) {
     return out;
 }
 
+/* process_frames(ctx:int, imgs0:sequence, imgs1:sequence, R|None (S x 9 doubles, C-contiguous), fm_type)
+ *   -> [(features, header), ...] for the S lock-stepped streams of a context (one launch chain for all of them). */
+static PyObject* py_process_frames(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    PyObject *l0, *l1, *Robj, *tpobj;
+    if (!PyArg_ParseTuple(args, "KOOOO", &handle, &l0, &l1, &Robj, &tpobj)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx || !PyType_Check(tpobj)) {
+        PyErr_SetString(PyExc_TypeError, "process_frames(ctx, imgs0, imgs1, R|None, FeatureMeasurement)");
+        return NULL;
+    }
+    int W = 0, H = 0, S = 0;
+    avb_get_geometry(ctx, &W, &H, &S);
+    PyObject* s0 = PySequence_Fast(l0, "imgs0 must be a sequence");
+    if (!s0) return NULL;
+    PyObject* s1 = PySequence_Fast(l1, "imgs1 must be a sequence");
+    if (!s1) {
+        Py_DECREF(s0);
+        return NULL;
+    }
+    PyObject* out = NULL;
+    Py_buffer bR;
+    int haveR = 0;
+    if (PySequence_Fast_GET_SIZE(s0) != S || PySequence_Fast_GET_SIZE(s1) != S) {
+        PyErr_Format(PyExc_ValueError, "expected %d images per camera", S);
+        goto done;
+    }
+    if (Robj != Py_None) {
+        if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS) < 0) goto done;
+        haveR = 1;
+        if (bR.len != (Py_ssize_t)S * 72 || bR.itemsize != 8) {
+            PyErr_Format(PyExc_ValueError, "R must be %d C-contiguous 3x3 float64 matrices", S);
+            goto done;
+        }
+    }
+    {
+        uint8_t* st = avb_input_staging(ctx);
+        const size_t ib = (size_t)W * H;
+        for (int s = 0; s < S; ++s) {
+            for (int cam = 0; cam < 2; ++cam) {
+                Py_buffer b;
+                PyObject* img = PySequence_Fast_GET_ITEM(cam ? s1 : s0, s);
+                if (PyObject_GetBuffer(img, &b, PyBUF_STRIDES) < 0) goto done;
+                int bad;
+                Py_BEGIN_ALLOW_THREADS
+                bad = copy_image(st + ((size_t)s * 2 + cam) * ib, &b, W, H);
+                Py_END_ALLOW_THREADS
+                PyBuffer_Release(&b);
+                if (bad) {
+                    PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride", H, W);
+                    goto done;
+                }
+            }
+        }
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = avb_process_frame(ctx, NULL, NULL, W, haveR ? (const double*)bR.buf : NULL);
+        Py_END_ALLOW_THREADS
+        if (rc != AVB_OK) {
+            PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+            goto done;
+        }
+        resolve_layout((PyTypeObject*)tpobj);
+        PyObject* res = PyList_New(S);
+        if (!res) goto done;
+        for (int s = 0; s < S; ++s) {
+            const avb_frame_header* h;
+            const int64_t* ids;
+            const double* meas;
+            avb_get_result(ctx, s, &h, &ids, &meas);
+            PyObject* list = build_list((PyTypeObject*)tpobj, h, ids, meas);
+            PyObject* hd = list ? header_tuple(h) : NULL;
+            PyObject* pair = (list && hd) ? PyTuple_Pack(2, list, hd) : NULL;
+            Py_XDECREF(list);
+            Py_XDECREF(hd);
+            if (!pair) {
+                Py_DECREF(res);
+                goto done;
+            }
+            PyList_SET_ITEM(res, s, pair);
+        }
+        out = res;
+    }
+done:
+    if (haveR) PyBuffer_Release(&bR);
+    Py_DECREF(s0);
+    Py_DECREF(s1);
+    return out;
+}
+
 /* features_from_result(ctx:int, s:int, fm_type) -> (features, header tuple): list construction only, for contexts
  * driven through avb_process_frame* elsewhere (multi-stream drivers). */
 static PyObject* py_features_from_result(PyObject* self, PyObject* args) {
@@ -369,6 +459,7 @@ static PyObject* py_integrate_imu(PyObject* self, PyObject* args) {
 
 static PyMethodDef methods[] = {
     {"process_frame", py_process_frame, METH_VARARGS, "One stereo frame: host images in, (FeatureMeasurement list, header) out."},
+    {"process_frames", py_process_frames, METH_VARARGS, "One stereo frame for every stream of a multi-stream context."},
     {"features_from_result", py_features_from_result, METH_VARARGS, "FeatureMeasurement list of stream s from the last frame."},
     {"integrate_imu", py_integrate_imu, METH_VARARGS, "Gyro window integration (imu_processor.py:28-67)."},
     {NULL, NULL, 0, NULL}};

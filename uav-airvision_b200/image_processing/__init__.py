@@ -5,8 +5,16 @@ the `stareo_callback` alias.  Put this directory's parent on sys.path ahead of t
 from .pipeline import ImageProcessingPipeline, create_context, current_context
 from .camera_model import CameraModel
 from .imu_processor import IMUProcessor
+from .pyramid_builder import PyramidBuilder
 from .feature_meta_data import FeatureMetaData
 from .feature_measurment import FeatureMeasurement
+from .feature_initializer import FeatureInitializer
+from .feature_adder import FeatureAdder
+from .feature_tracker import FeatureTracker
+from .feature_pruner import FeaturePruner
+from .stereo_matcher import StereoMatcher
+from .feature_publisher import FeaturePublisher
+from .fast_detector import FastDetector
 
 
 class ImageProcessor(ImageProcessingPipeline):

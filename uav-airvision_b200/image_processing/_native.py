@@ -167,6 +167,9 @@ class Context:
         self.staging = self._staging_block[:img_bytes].reshape(self.S, 2, self.height, self.width)
         self._ident = np.tile(np.eye(3).reshape(-1), self.S)
         self._views = {}
+        self.stereo_threshold = float(ac.stereo_threshold)
+        self._staged_frames = 0          # frames made current through begin_frame (stage-class flow)
+        self._cur0 = None
 
     # -- lifecycle -------------------------------------------------------------------------------------
     def close(self):
@@ -273,6 +276,25 @@ class Context:
 
     def advance(self):
         self._ck(self._lib.avb_advance(self._h))
+
+    def begin_frame(self, img0, img1, s=0):
+        """Stage-class flow (PyramidBuilder.create_image_pyramids): the frame that was current becomes the previous
+        one (its device pyramids stay), the new images are uploaded and their pyramids built."""
+        if self._staged_frames:
+            self.advance()
+        self.upload(img0, img1, s)
+        self.build_pyramids()
+        self._staged_frames += 1
+        self._cur0 = img0
+
+    def ensure_current_cam0(self, img):
+        """FAST runs on the current cam0 image of the context; a detector handed a different image uploads it first."""
+        if img is self._cur0:
+            return
+        if self._cur0 is not None and img.shape == self._cur0.shape and np.array_equal(img, self._cur0):
+            return
+        self.upload(img, img)
+        self._cur0 = img
 
     def build_pyramids(self):
         self._ck(self._lib.avb_build_pyramids(self._h))
