@@ -23,6 +23,7 @@
 #include <structmember.h>
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/avb.h"
@@ -457,10 +458,72 @@ static PyObject* py_integrate_imu(PyObject* self, PyObject* args) {
     return PyLong_FromLong(ret);
 }
 
+/* ---- PNG scanline reconstruction (EuRoC cam0/cam1 frames are 8-bit grayscale PNGs) ------------------------- */
+
+/* png_unfilter(raw: bytes-like (h * (1 + w*bpp)), w, h, bpp, out: writable buffer of h*w*bpp bytes)
+ * Undoes the per-row PNG filters 0-4 (None, Sub, Up, Average, Paeth; PNG spec section 6) into `out`, which may be
+ * libavb's pinned staging block.  The inflate step stays in Python's zlib. */
+static PyObject* py_png_unfilter(PyObject* self, PyObject* args) {
+    Py_buffer raw, out;
+    int w, h, bpp;
+    if (!PyArg_ParseTuple(args, "y*iiiw*", &raw, &w, &h, &bpp, &out)) return NULL;
+    const Py_ssize_t stride = (Py_ssize_t)w * bpp;
+    int err = 0;
+    if (w <= 0 || h <= 0 || bpp <= 0 || raw.len != (Py_ssize_t)h * (stride + 1) || out.len < (Py_ssize_t)h * stride) {
+        err = 1;
+    } else {
+        const unsigned char* src = (const unsigned char*)raw.buf;
+        unsigned char* dst = (unsigned char*)out.buf;
+        Py_BEGIN_ALLOW_THREADS
+        for (int y = 0; y < h && !err; ++y) {
+            const unsigned char ft = src[(Py_ssize_t)y * (stride + 1)];
+            const unsigned char* in = src + (Py_ssize_t)y * (stride + 1) + 1;
+            unsigned char* cur = dst + (Py_ssize_t)y * stride;
+            const unsigned char* up = y ? cur - stride : NULL;
+            switch (ft) {
+                case 0:
+                    memcpy(cur, in, stride);
+                    break;
+                case 1:
+                    for (Py_ssize_t x = 0; x < stride; ++x) cur[x] = (unsigned char)(in[x] + (x >= bpp ? cur[x - bpp] : 0));
+                    break;
+                case 2:
+                    for (Py_ssize_t x = 0; x < stride; ++x) cur[x] = (unsigned char)(in[x] + (up ? up[x] : 0));
+                    break;
+                case 3:
+                    for (Py_ssize_t x = 0; x < stride; ++x) {
+                        const int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0;
+                        cur[x] = (unsigned char)(in[x] + ((a + b) >> 1));
+                    }
+                    break;
+                case 4:
+                    for (Py_ssize_t x = 0; x < stride; ++x) {
+                        const int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+                        const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+                        const int pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                        cur[x] = (unsigned char)(in[x] + pr);
+                    }
+                    break;
+                default:
+                    err = 2;
+            }
+        }
+        Py_END_ALLOW_THREADS
+    }
+    PyBuffer_Release(&raw);
+    PyBuffer_Release(&out);
+    if (err) {
+        PyErr_SetString(PyExc_ValueError, err == 1 ? "png_unfilter: size mismatch" : "png_unfilter: unknown filter type");
+        return NULL;
+    }
+    Py_RETURN_NONE;
+}
+
 static PyMethodDef methods[] = {
     {"process_frame", py_process_frame, METH_VARARGS, "One stereo frame: host images in, (FeatureMeasurement list, header) out."},
     {"process_frames", py_process_frames, METH_VARARGS, "One stereo frame for every stream of a multi-stream context."},
     {"features_from_result", py_features_from_result, METH_VARARGS, "FeatureMeasurement list of stream s from the last frame."},
+    {"png_unfilter", py_png_unfilter, METH_VARARGS, "Undo PNG row filters into a caller buffer."},
     {"integrate_imu", py_integrate_imu, METH_VARARGS, "Gyro window integration (imu_processor.py:28-67)."},
     {NULL, NULL, 0, NULL}};
 

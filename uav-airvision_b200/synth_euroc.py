@@ -126,3 +126,186 @@ class SlidingTextureStream:
                 yield 'imu', pending
                 pending = next(imu_it, None)
             yield 'stereo', f
+
+
+# ------------------------------------------------------------------------------------------------
+# Rendered 3-D sequence (sequence-level tests: downstream MSCKF ATE parity, EuRoC on-disk round trip)
+# ------------------------------------------------------------------------------------------------
+
+gt_msg = namedtuple('gt_msg', ['timestamp', 'p', 'q', 'v', 'bw', 'ba'])
+
+
+def _rodrigues(v):
+    th = float(np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))
+    if th < 1e-12:
+        return np.eye(3)
+    r = v / th
+    K = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def _quat_wxyz(R):
+    """Hamilton quaternion (w, x, y, z) of a rotation matrix, w >= 0 (EuRoC ground-truth column order)."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    return q if q[0] >= 0 else -q
+
+
+class RoomSceneStream:
+    """Stereo + IMU stream of a rig moving inside a textured box room, rendered through the radtan / extrinsic model
+    of a ConfigEuRoC-shaped calibration (T_imu_cam0/1 = Kalibr T_cam_imu: IMU frame -> camera frame).
+
+    World: z up, gravity (0, 0, -9.81).  The rig rests for `static_s` seconds (the MSCKF initialises gravity from its
+    first 200 IMU samples, reference msckf.py:172-175), then follows a smooth Lissajous-like path with small
+    rotations.  IMU samples come from central differences of the analytic pose (specific force R^T (a + g), body
+    rate), plus optional white noise.  Deterministic for a given seed."""
+
+    G = 9.81
+
+    def __init__(self, calib, n_frames=300, seed=0, rate=20.0, imu_rate=200.0, t0=1000.0, static_s=1.5,
+                 half=(4.0, 3.5), floor=-1.5, ceil=2.0, tex_px_per_m=140.0, tex_sigma=3.0, tex_size=2048,
+                 gyro_noise=2e-4, acc_noise=2e-3, pixel_noise=0.0, amp=1.0):
+        self.calib = calib
+        self.w, self.h = int(calib.cam0_resolution[0]), int(calib.cam0_resolution[1])
+        self.n, self.seed = int(n_frames), int(seed)
+        self.rate, self.imu_rate, self.t0, self.static_s = float(rate), float(imu_rate), float(t0), float(static_s)
+        self.lo = np.array([-half[0], -half[1], floor])
+        self.hi = np.array([half[0], half[1], ceil])
+        self.scale, self.tex_size = float(tex_px_per_m), int(tex_size)
+        self.gyro_noise, self.acc_noise, self.pixel_noise, self.amp = gyro_noise, acc_noise, pixel_noise, float(amp)
+        self._tex = [make_texture(tex_size, tex_size, seed * 101 + 17 * f + 3, tex_sigma) for f in range(6)]
+        self._rays = [self._pixel_rays(calib.cam0_intrinsics, calib.cam0_distortion_coeffs),
+                      self._pixel_rays(calib.cam1_intrinsics, calib.cam1_distortion_coeffs)]
+        self._T_ic = [np.linalg.inv(calib.T_imu_cam0), np.linalg.inv(calib.T_imu_cam1)]    # camera -> IMU
+        # IMU x up, z (the optical axis, roughly) along world +x
+        self._R0 = np.array([[0.0, 0.0, 1.0], [0.0, -1.0, 0.0], [1.0, 0.0, 0.0]])
+        self._imu_cache = None
+
+    # -- geometry ---------------------------------------------------------------------------------
+    def _pixel_rays(self, intr, dist):
+        """Normalized ray (x, y, 1) of every pixel centre: inverse of the radtan model by fixed-point iteration."""
+        fx, fy, cx, cy = (float(v) for v in intr)
+        k1, k2, p1, p2 = (float(v) for v in dist[:4])
+        u, v = np.meshgrid(np.arange(self.w, dtype=np.float64), np.arange(self.h, dtype=np.float64))
+        x0, y0 = (u - cx) / fx, (v - cy) / fy
+        x, y = x0.copy(), y0.copy()
+        for _ in range(30):
+            r2 = x * x + y * y
+            ic = 1.0 / (1.0 + (k2 * r2 + k1) * r2)
+            dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+            dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+            x, y = (x0 - dx) * ic, (y0 - dy) * ic
+        return np.stack([x.ravel(), y.ravel(), np.ones(x.size)], axis=1)
+
+    def _ramp(self, t):
+        s = np.clip((t - self.static_s) / 3.0, 0.0, 1.0)
+        return s * s * s * (s * (6 * s - 15) + 10)
+
+    def pose(self, t):
+        """(R_wi, p_wi) of the IMU at time t seconds after t0."""
+        s = self._ramp(t) * self.amp
+        tt = t - self.static_s
+        p = s * np.array([0.7 * np.sin(0.55 * tt), 0.9 * np.sin(0.40 * tt + 1.0) - 0.9 * np.sin(1.0),
+                          0.35 * np.sin(0.75 * tt)])
+        a = s * np.array([0.10 * np.sin(0.45 * tt), 0.12 * np.sin(0.33 * tt + 0.5) - 0.12 * np.sin(0.5),
+                          0.22 * np.sin(0.27 * tt)])
+        return self._R0 @ _rodrigues(a), p
+
+    def imu_sample(self, t, h=1e-3):
+        Rm, pm = self.pose(t - h)
+        R, p = self.pose(t)
+        Rp, pp = self.pose(t + h)
+        acc_w = (pp - 2 * p + pm) / (h * h)
+        W = (Rm.T @ Rp - Rp.T @ Rm) / (4 * h)                 # skew(omega_body) + O(h^2)
+        gyro = np.array([W[2, 1], W[0, 2], W[1, 0]])
+        acc = R.T @ (acc_w + np.array([0.0, 0.0, self.G]))
+        return gyro, acc
+
+    # -- rendering --------------------------------------------------------------------------------
+    def _render(self, R_wc, c):
+        d = self._rays_cam @ R_wc.T
+        with np.errstate(divide='ignore', invalid='ignore'):
+            tpos = np.where(d > 0, (self.hi - c) / d, np.where(d < 0, (self.lo - c) / d, np.inf))
+        axis = np.argmin(tpos, axis=1)
+        tmin = tpos[np.arange(len(axis)), axis]
+        hit = c + d * tmin[:, None]
+        face = axis * 2 + (d[np.arange(len(axis)), axis] > 0)
+        out = np.zeros(len(axis))
+        for f in range(6):
+            m = face == f
+            if not m.any():
+                continue
+            ax = f // 2
+            ua, va = [(1, 2), (0, 2), (0, 1)][ax]
+            tu = hit[m, ua] * self.scale + 0.37 * self.tex_size
+            tv = hit[m, va] * self.scale + 0.61 * self.tex_size
+            iu, iv = np.floor(tu).astype(np.int64), np.floor(tv).astype(np.int64)
+            fu, fv = tu - iu, tv - iv
+            T, n = self._tex[f], self.tex_size
+            i0, i1, j0, j1 = iu % n, (iu + 1) % n, iv % n, (iv + 1) % n
+            out[m] = ((1 - fu) * (1 - fv) * T[j0, i0] + fu * (1 - fv) * T[j0, i1]
+                      + (1 - fu) * fv * T[j1, i0] + fu * fv * T[j1, i1])
+        return out.reshape(self.h, self.w)
+
+    def frame(self, k):
+        t = k / self.rate
+        ts = self.t0 + t
+        R_wi, p = self.pose(t)
+        imgs = []
+        for cam in range(2):
+            T = self._T_ic[cam]
+            self._rays_cam = self._rays[cam]
+            img = self._render(R_wi @ T[:3, :3], p + R_wi @ T[:3, 3])
+            if self.pixel_noise > 0:
+                img = img + np.random.default_rng(self.seed * 7919 + 2 * k + cam).normal(0.0, self.pixel_noise, img.shape)
+            imgs.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+        m0, m1 = img_msg(ts, imgs[0]), img_msg(ts, imgs[1])
+        return stereo_msg(ts, imgs[0], imgs[1], m0, m1)
+
+    def frames(self):
+        for k in range(self.n):
+            yield self.frame(k)
+
+    def imu(self):
+        if self._imu_cache is None:
+            rng = np.random.default_rng(self.seed + 12345)
+            n_imu = int(np.floor((self.n - 1) / self.rate * self.imu_rate)) + 1
+            out = []
+            for j in range(n_imu + 1):
+                t = j / self.imu_rate
+                gyro, acc = self.imu_sample(t)
+                gyro = gyro + rng.normal(0.0, self.gyro_noise, 3)
+                acc = acc + rng.normal(0.0, self.acc_noise, 3)
+                out.append(imu_msg(self.t0 + t, gyro, acc))
+            self._imu_cache = out
+        return iter(self._imu_cache)
+
+    def groundtruth(self):
+        """gt_msg per IMU sample: position, Hamilton quaternion (w, x, y, z) of R_wi, velocity, zero biases."""
+        n_imu = int(np.floor((self.n - 1) / self.rate * self.imu_rate)) + 1
+        h = 1e-3
+        for j in range(n_imu + 1):
+            t = j / self.imu_rate
+            R, p = self.pose(t)
+            v = (self.pose(t + h)[1] - self.pose(t - h)[1]) / (2 * h)
+            yield gt_msg(self.t0 + t, p, _quat_wxyz(R), v, np.zeros(3), np.zeros(3))
+
+    def events(self):
+        imu_it = iter(self.imu())
+        pending = next(imu_it, None)
+        for f in self.frames():
+            while pending is not None and pending.timestamp <= f.timestamp:
+                yield 'imu', pending
+                pending = next(imu_it, None)
+            yield 'stereo', f
