@@ -10,6 +10,7 @@
 #include "avb_common.cuh"
 
 static thread_local std::string g_create_error;
+int g_avb_pdl = 1;
 
 struct avb_ctx {
     avb_config cfg;
@@ -148,6 +149,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     // dependent chain; many -> 1 warp per feature for throughput.  AVB_WPF=1|4 overrides (experiments).
     g.wpf = ((long long)g.S * g.NMAX <= 4736) ? 4 : 1;      // 4736 = 148 SMs x 32 resident teams
     if (const char* e = getenv("AVB_WPF")) g.wpf = (atoi(e) == 4) ? 4 : 1;
+    if (const char* e = getenv("AVB_PDL")) g_avb_pdl = atoi(e) ? 1 : 0;
     g.max_iter = std::min(std::max(cfg->max_iteration, 0), 100);
     g.min_eig = cfg->min_eig_threshold;
     const double eps = std::min(std::max(cfg->track_precision, 0.0), 10.0);
@@ -450,11 +452,13 @@ extern "C" int avb_fill_rotations(const avb_ctx* c, uint8_t* block, const double
     return AVB_OK;
 }
 
-static int run_frame(avb_ctx* c, int variant /*0 host images in h_in, 1 device images already copied*/, bool wait) {
+// variant 0: the whole block lies in the pinned staging (one H2D node inside the graph); 1: the block was placed in
+// d.in[p] by copies ordered before this on c->st; 2: like 1, and ev_t0 was already recorded before those copies.
+static int run_frame(avb_ctx* c, int variant, bool wait) {
     const Geom& g = c->g;
     const int p = c->parity ^ 1;
     const size_t inb = in_block_bytes(g);
-    CK(cudaEventRecord(c->ev_t0, c->st));
+    if (variant != 2) CK(cudaEventRecord(c->ev_t0, c->st));
     if (!c->first_frame && c->cfg.use_graph) {
         CK(cudaGraphLaunch((variant == 0 ? c->graph : c->graph_dev)[p], c->st));
     } else {
@@ -474,28 +478,53 @@ static int run_frame(avb_ctx* c, int variant /*0 host images in h_in, 1 device i
     return AVB_OK;
 }
 
+static bool is_page_locked(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
                                  const double* R_p_c0) {
     if (!c) return AVB_E_INVALID;
     const Geom& g = c->g;
     CK(cudaSetDevice(c->cfg.device));
-    if (img0 && img1) {
-        if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
-        const size_t ib = (size_t)g.W * g.H;
-        for (int s = 0; s < g.S; ++s) {
-            for (int cam = 0; cam < 2; ++cam) {
-                const uint8_t* src = cam ? img1[s] : img0[s];
-                if (!src) return fail(c, AVB_E_INVALID, "null image pointer (stream %d cam %d)", s, cam);
-                uint8_t* dst = c->h_in + ((size_t)s * 2 + cam) * ib;
-                if (stride == g.W)
-                    memcpy(dst, src, ib);
-                else
-                    for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
+    if (!(img0 && img1)) {              // the caller filled the pinned staging block in place
+        avb_fill_rotations(c, c->h_in, R_p_c0);
+        return run_frame(c, 0, true);
+    }
+    if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
+    // Pipelined intake: each image is staged into pinned memory (or, when the caller's buffer is itself page-locked
+    // and dense, taken from where it lies) and its H2D copy is enqueued before the next image is touched, so the PCIe
+    // transfer of one image overlaps the host copy of the next.  The kernels then run from the graph variant that has
+    // no H2D node.
+    const int p = c->parity ^ 1;
+    const size_t ib = (size_t)g.W * g.H;
+    CK(cudaEventRecord(c->ev_t0, c->st));
+    for (int s = 0; s < g.S; ++s) {
+        for (int cam = 0; cam < 2; ++cam) {
+            const uint8_t* src = cam ? img1[s] : img0[s];
+            if (!src) return fail(c, AVB_E_INVALID, "null image pointer (stream %d cam %d)", s, cam);
+            const size_t off = ((size_t)s * 2 + cam) * ib;
+            if (stride == g.W && is_page_locked(src)) {
+                CK(cudaMemcpyAsync(c->d.in[p] + off, src, ib, cudaMemcpyHostToDevice, c->st));
+                continue;
             }
+            uint8_t* dst = c->h_in + off;
+            if (stride == g.W)
+                memcpy(dst, src, ib);
+            else
+                for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
+            CK(cudaMemcpyAsync(c->d.in[p] + off, dst, ib, cudaMemcpyHostToDevice, c->st));
         }
     }
     avb_fill_rotations(c, c->h_in, R_p_c0);
-    return run_frame(c, 0, true);
+    const size_t ro = in_images_bytes(g);
+    CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st));
+    return run_frame(c, 2, true);
 }
 
 extern "C" int avb_enqueue_frame_device(avb_ctx* c, const uint8_t* d_block) {

@@ -155,6 +155,33 @@ __host__ __device__ inline void kp_decode(unsigned key, int W, int& resp, int& x
     x = (int)(lin % (unsigned)W);
 }
 
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------------
+// The frame is a chain of small dependent kernels; with the ProgrammaticStreamSerialization attribute the next
+// kernel's CTAs are scheduled while the current one drains and sit in griddepcontrol.wait until it has completed and
+// flushed, which hides most of the ~3 us launch gap per kernel boundary.  Every kernel of the chain executes
+// pdl_wait() before it touches memory and pdl_launch_dependents() right after (a no-op without the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+extern int g_avb_pdl;              // 1: chain kernels are launched with the programmatic attribute (AVB_PDL=0 disables)
+
 // ---- launchers implemented in the stage files -------------------------------------------
 // TMA views (x, y, image).  Level 0: one map per parity over the input block, image = s*2 + cam.
 // Levels >= 1: one map per level over the arena, image = s*4 + slot.  `fast0` has the FAST box shape.

@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) k_select(const __grid_constant
     __shared__ int n_feat;
     __shared__ unsigned long long fin[SEL_WARPS * AVB_MAX_CAP];
 
+    pdl_wait();
+    pdl_launch_dependents();
     const int cell = blockIdx.x, s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t kbase = ((size_t)s * g.NC + cell) * g.KPC;
     const int n = min(d.kp_count[s * g.NC + cell], g.KPC);
@@ -154,7 +156,7 @@ int avb_set_smem_limits(size_t select_bytes, size_t grid_bytes) {
 
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st) {
     const size_t smem = (size_t)g.KPC * sizeof(unsigned);
-    k_select<<<dim3(g.NC, g.S), 32 * SEL_WARPS, smem, st>>>(g, d, parity, first_frame);
+    launch_k(k_select, dim3(g.NC, g.S), dim3(32 * SEL_WARPS), smem, st, g_avb_pdl && !first_frame, g, d, parity, first_frame);
 }
 
 // k_finish: one 1024-thread CTA per stream closes the frame.
@@ -179,6 +181,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
     __shared__ int off_new[AVB_MAX_CELLS + 1];  // exclusive scan of the new-feature counts
     __shared__ int nnew[AVB_MAX_CELLS];
 
+    pdl_wait();
+    pdl_launch_dependents();
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const GridTable prev = d.grid[parity ^ 1], cur = d.grid[parity];
@@ -374,5 +378,5 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
 }
 
 void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st) {
-    k_finish<<<g.S, FIN_THREADS, (size_t)g.NMAX * 3 * sizeof(int), st>>>(g, d, parity, first_frame);
+    launch_k(k_finish, dim3(g.S), dim3(FIN_THREADS), (size_t)g.NMAX * 3 * sizeof(int), st, g_avb_pdl != 0, g, d, parity, first_frame);
 }

@@ -28,38 +28,69 @@
 
 #include "../../include/avb.h"
 
-/* ---- FeatureMeasurement construction ------------------------------------------------------------------ */
-
+/* ---- FeatureMeasurement: the stereo measurement the MSCKF reads (id, u0, v0, u1, v1) -------------------------
+ * Same attribute set as the reference's plain Python class (image_processing/feature_measurment.py:1-9, read at
+ * msckf.py:430-438); here a C struct with member descriptors so that a frame's 300 measurements cost 300 allocations
+ * instead of 1800 (object + int + four floats each). */
 typedef struct {
-    PyTypeObject* type;            /* borrowed; identity check only */
-    Py_ssize_t off[5];             /* slot offsets of id, u0, v0, u1, v1; -1 = generic setattr path */
-} fm_layout;
+    PyObject_HEAD
+    long long id;
+    double u0, v0, u1, v1;
+} FMObject;
 
-static fm_layout g_layout = {NULL, {-1, -1, -1, -1, -1}};
-static PyObject* g_names[5];
+static PyMemberDef FM_members[] = {
+    {"id", T_LONGLONG, offsetof(FMObject, id), 0, "feature id"},
+    {"u0", T_DOUBLE, offsetof(FMObject, u0), 0, "cam0 normalized x"},
+    {"v0", T_DOUBLE, offsetof(FMObject, v0), 0, "cam0 normalized y"},
+    {"u1", T_DOUBLE, offsetof(FMObject, u1), 0, "cam1 normalized x"},
+    {"v1", T_DOUBLE, offsetof(FMObject, v1), 0, "cam1 normalized y"},
+    {NULL}};
 
-static int resolve_layout(PyTypeObject* tp) {
-    static const char* names[5] = {"id", "u0", "v0", "u1", "v1"};
-    if (g_layout.type == tp) return 0;
-    g_layout.type = tp;
-    int slots = 1;
-    for (int i = 0; i < 5; ++i) {
-        g_layout.off[i] = -1;
-        PyObject* d = PyObject_GetAttrString((PyObject*)tp, names[i]);      /* slot member descriptor */
-        if (d && Py_TYPE(d) == &PyMemberDescr_Type) {
-            PyMemberDef* m = ((PyMemberDescrObject*)d)->d_member;
-            if (m && m->type == T_OBJECT_EX) g_layout.off[i] = m->offset;
-        }
-        if (!d) PyErr_Clear();
-        Py_XDECREF(d);
-        if (g_layout.off[i] < 0) slots = 0;
-    }
-    if (!slots)
-        for (int i = 0; i < 5; ++i) g_layout.off[i] = -1;
+static int FM_init(FMObject* self, PyObject* args, PyObject* kw) {
+    static char* names[] = {"id", "u0", "v0", "u1", "v1", NULL};
+    long long id = 0;
+    double u0 = 0, v0 = 0, u1 = 0, v1 = 0;
+    if (!PyArg_ParseTupleAndKeywords(args, kw, "|Ldddd", names, &id, &u0, &v0, &u1, &v1)) return -1;
+    self->id = id;
+    self->u0 = u0;
+    self->v0 = v0;
+    self->u1 = u1;
+    self->v1 = v1;
     return 0;
 }
 
+static PyObject* FM_repr(FMObject* self) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "FeatureMeasurement(id=%lld, u0=%.9g, v0=%.9g, u1=%.9g, v1=%.9g)", self->id, self->u0, self->v0,
+             self->u1, self->v1);
+    return PyUnicode_FromString(buf);
+}
+
+static PyTypeObject FMType = {
+    PyVarObject_HEAD_INIT(NULL, 0).tp_name = "image_processing.FeatureMeasurement",
+    .tp_basicsize = sizeof(FMObject),
+    .tp_flags = Py_TPFLAGS_DEFAULT | Py_TPFLAGS_BASETYPE,
+    .tp_doc = "Stereo measurement of one feature in normalized coordinates: id, u0, v0, u1, v1.",
+    .tp_members = FM_members,
+    .tp_init = (initproc)FM_init,
+    .tp_new = PyType_GenericNew,
+    .tp_repr = (reprfunc)FM_repr,
+};
+
+/* Any other class with id/u0/v0/u1/v1 attributes can be requested instead (generic setattr path). */
+static PyObject* g_names[5];
+
 static PyObject* make_feature(PyTypeObject* tp, long long id, const double* m) {
+    if (tp == &FMType) {
+        FMObject* o = (FMObject*)FMType.tp_alloc(&FMType, 0);
+        if (!o) return NULL;
+        o->id = id;
+        o->u0 = m[0];
+        o->v0 = m[1];
+        o->u1 = m[2];
+        o->v1 = m[3];
+        return (PyObject*)o;
+    }
     PyObject* vals[5];
     vals[0] = PyLong_FromLongLong(id);
     vals[1] = PyFloat_FromDouble(m[0]);
@@ -67,24 +98,13 @@ static PyObject* make_feature(PyTypeObject* tp, long long id, const double* m) {
     vals[3] = PyFloat_FromDouble(m[2]);
     vals[4] = PyFloat_FromDouble(m[3]);
     PyObject* o = NULL;
-    int ok = vals[0] && vals[1] && vals[2] && vals[3] && vals[4];
-    if (ok) {
-        if (g_layout.off[0] >= 0) {                 /* __slots__ class: fill the slots directly, no __init__ */
-            o = tp->tp_alloc(tp, 0);
-            if (o) {
-                for (int i = 0; i < 5; ++i) {
-                    *(PyObject**)((char*)o + g_layout.off[i]) = vals[i];
-                    vals[i] = NULL;
-                }
-            }
-        } else {                                    /* any other class with id/u0/v0/u1/v1 attributes */
-            o = PyObject_CallNoArgs((PyObject*)tp);
-            if (o) {
-                for (int i = 0; i < 5; ++i) {
-                    if (PyObject_SetAttr(o, g_names[i], vals[i]) < 0) {
-                        Py_CLEAR(o);
-                        break;
-                    }
+    if (vals[0] && vals[1] && vals[2] && vals[3] && vals[4]) {
+        o = PyObject_CallNoArgs((PyObject*)tp);
+        if (o) {
+            for (int i = 0; i < 5; ++i) {
+                if (PyObject_SetAttr(o, g_names[i], vals[i]) < 0) {
+                    Py_CLEAR(o);
+                    break;
                 }
             }
         }
@@ -92,6 +112,8 @@ static PyObject* make_feature(PyTypeObject* tp, long long id, const double* m) {
     for (int i = 0; i < 5; ++i) Py_XDECREF(vals[i]);
     return o;
 }
+
+static int resolve_layout(PyTypeObject* tp) { (void)tp; return 0; }
 
 static PyObject* build_list(PyTypeObject* tp, const avb_frame_header* h, const int64_t* ids, const double* meas) {
     const Py_ssize_t n = (Py_ssize_t)h->n_features;
@@ -166,16 +188,22 @@ static PyObject* py_process_frame(PyObject* self, PyObject* args) {
         PyBuffer_Release(&bR);
         haveR = 1;
     }
-    uint8_t* st = avb_input_staging(ctx);
     int bad = 0, rc = 0;
-    Py_BEGIN_ALLOW_THREADS
-    bad = copy_image(st, &b0, W, H) || copy_image(st + (size_t)W * H, &b1, W, H);
-    if (!bad) rc = avb_process_frame(ctx, NULL, NULL, W, haveR ? R : NULL);
-    Py_END_ALLOW_THREADS
+    bad = b0.ndim != 2 || b0.itemsize != 1 || b0.shape[0] != H || b0.shape[1] != W || b0.strides[1] != 1 ||
+          b1.ndim != 2 || b1.itemsize != 1 || b1.shape[0] != H || b1.shape[1] != W || b1.strides[1] != 1 ||
+          b0.strides[0] != b1.strides[0] || b0.strides[0] < W;
+    if (!bad) {
+        const uint8_t* p0 = (const uint8_t*)b0.buf;
+        const uint8_t* p1 = (const uint8_t*)b1.buf;
+        const int stride = (int)b0.strides[0];
+        Py_BEGIN_ALLOW_THREADS
+        rc = avb_process_frame(ctx, &p0, &p1, stride, haveR ? R : NULL);    /* staging + pipelined H2D + frame + D2H */
+        Py_END_ALLOW_THREADS
+    }
     PyBuffer_Release(&b0);
     PyBuffer_Release(&b1);
     if (bad) {
-        PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride", H, W);
+        PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride and equal row stride", H, W);
         return NULL;
     }
     if (rc != AVB_OK) {
@@ -534,5 +562,14 @@ PyMODINIT_FUNC PyInit__avbhost(void) {
     for (int i = 0; i < 5; ++i) g_names[i] = PyUnicode_InternFromString(names[i]);
     s_timestamp = PyUnicode_InternFromString("timestamp");
     s_angular_velocity = PyUnicode_InternFromString("angular_velocity");
-    return PyModule_Create(&moddef);
+    if (PyType_Ready(&FMType) < 0) return NULL;
+    PyObject* m = PyModule_Create(&moddef);
+    if (!m) return NULL;
+    Py_INCREF(&FMType);
+    if (PyModule_AddObject(m, "FeatureMeasurement", (PyObject*)&FMType) < 0) {
+        Py_DECREF(&FMType);
+        Py_DECREF(m);
+        return NULL;
+    }
+    return m;
 }

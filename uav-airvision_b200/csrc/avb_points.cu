@@ -18,6 +18,8 @@ template <int WPF>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_track(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
                                                                 int parity) {
     __shared__ LKShared sh;
+    pdl_wait();
+    pdl_launch_dependents();
     const int s = blockIdx.y;
     const int wi = team_index<WPF>(blockIdx.x);
     const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
@@ -57,6 +59,8 @@ template <int WPF>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_stereo_candidates(const __grid_constant__ Geom g,
                                                                             const __grid_constant__ DevState d, int parity) {
     __shared__ LKShared sh;
+    pdl_wait();
+    pdl_launch_dependents();
     const int s = blockIdx.y;
     const int wi = team_index<WPF>(blockIdx.x);
     const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
@@ -159,16 +163,16 @@ static inline int teams_grid(int n, int wpf) { return wpf == 1 ? (n + WARPS_PER_
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
     if (g.wpf == 1)
-        k_track<1><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+        launch_k(k_track<1>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
     else
-        k_track<4><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+        launch_k(k_track<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
 }
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
     if (g.wpf == 1)
-        k_stereo_candidates<1><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+        launch_k(k_stereo_candidates<1>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
     else
-        k_stereo_candidates<4><<<grid, 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+        launch_k(k_stereo_candidates<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
 }
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid((g.KPC + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.NC, g.S);

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ CUtens
         mbar_init(&bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    pdl_wait();
+    pdl_launch_dependents();
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, PB_W * PB_H);
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(256) k_pyr_pair(const __grid_constant__ CUtens
         mbar_init(&bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    pdl_wait();
+    pdl_launch_dependents();
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, QB_W * QB_H);
@@ -212,11 +216,11 @@ void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int p
     for (int l = 1; l <= built; ++l) {
         if (l == pair_at) {
             dim3 grid((g.lv[l + 1].w + QT_W - 1) / QT_W, (g.lv[l + 1].h + QT_H - 1) / QT_H, 2 * g.S);
-            k_pyr_pair<<<grid, 256, 0, st>>>(l == 1 ? maps.pair0[parity] : maps.pair, g, d, l, parity);
+            launch_k(k_pyr_pair, grid, dim3(256), 0, st, g_avb_pdl && l > 1, l == 1 ? maps.pair0[parity] : maps.pair, g, d, l, parity);
             break;
         }
         dim3 grid((g.lv[l].w + PT_W - 1) / PT_W, (g.lv[l].h + PT_H - 1) / PT_H, 2 * g.S);
-        k_pyr_down<<<grid, 256, 0, st>>>(l == 1 ? maps.l0[parity] : maps.lv[l - 1], g, d, l, parity);
+        launch_k(k_pyr_down, grid, dim3(256), 0, st, g_avb_pdl && l > 1, l == 1 ? maps.l0[parity] : maps.lv[l - 1], g, d, l, parity);
     }
 }
 
