@@ -260,3 +260,21 @@ def test_multi_stream_front_end_replay_equals_single_pipelines():
             assert [(f.id, f.u0, f.v0, f.u1, f.v1) for f in a.features] == [(f.id, f.u0, f.v0, f.u1, f.v1) for f in b.features]
         assert stream_stats(s, multi[s])['features'] == sum(len(m.features) for m in singles[s])
     fe.close()
+
+
+@pytest.mark.parametrize('wpf', ['1', '4'])
+def test_both_lk_lane_mappings_match_reference_golden(wpf, golden_dir, monkeypatch):
+    """The throughput mapping (one warp per feature, packed loads + dp2a) and the latency mapping (four warps per
+    feature, parallel per-level templates) are the same arithmetic: both must reproduce the reference's dumps."""
+    monkeypatch.setenv('AVB_WPF', wpf)
+    name = 'ref_c2_s1'
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    gr, gc, gmin, gmax, skw = CASES[name]
+    cfg = FrontEndConfig(grid_row=gr, grid_col=gc, grid_min=gmin, grid_max=gmax)
+    msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**skw))
+    n = int(g['n_frames'][0])
+    ref = [dict(ids=g[f'f{k}_ids'], cell=g[f'f{k}_cell'], life=g[f'f{k}_life'], p0=g[f'f{k}_p0'],
+                p1=g[f'f{k}_p1'], pub=g[f'f{k}_pub']) for k in range(n)]
+    worst = _compare(frames, ref)
+    print(f'AVB_WPF={wpf}: worst position deviation {worst:.3g} px')
+    assert nid == int(g['next_feature_id'][0])

@@ -188,7 +188,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(cudaEventCreate(&c->ev_t1));
     CKC(dalloc(c, &d.in[0], inb));
     CKC(dalloc(c, &d.in[1], inb));
-    CKC(dalloc(c, &d.pyr, S * SLOTS_PER_STREAM * g.slot_bytes));
+    CKC(dalloc(c, &d.pyr, S * SLOTS_PER_STREAM * g.slot_bytes + 256));   // + slack: LK reads whole aligned words
     CKC(dalloc(c, &d.kp_key, S * NC * g.KPC));
     CKC(dalloc(c, &d.kp_count, S * NC));
     CKC(dalloc(c, &d.kp_p1, S * NC * g.KPC));

@@ -71,6 +71,19 @@ __device__ __forceinline__ void team_sum_exact(const int (&v)[N], long long (&ou
     }
 }
 
+// 2-way dot product of two SIGNED 16-bit values (operand a) with two UNSIGNED bytes (lower / upper half of b) plus c.
+// The fourth bilinear weight is 2^14 minus the other three rounded weights and can come out as -1, hence signed.
+__device__ __forceinline__ int dp2a_lo_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     const float s = (float)(1 << LK_W_BITS);
     const float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
@@ -237,23 +250,48 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
                 break;
             }
             lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
-            int cur[NPX + 1], nxt[NPX + 1];
-            load_row<NPX + 1>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row, cur);
-            {
-                const unsigned p0 = (unsigned)cur[0] | ((unsigned)cur[1] << 8) | ((unsigned)cur[2] << 16) | ((unsigned)cur[3] << 24);
-                const unsigned p1 = (unsigned)cur[4] | ((unsigned)cur[5] << 8) | ((unsigned)cur[6] << 16) | ((unsigned)cur[7] << 24);
-                const unsigned q0 = __shfl_down_sync(0xffffffffu, p0, LPR);
-                const unsigned q1 = __shfl_down_sync(0xffffffffu, p1, LPR);
-                nxt[NPX] = __shfl_down_sync(0xffffffffu, cur[NPX], LPR);
-                nxt[0] = q0 & 0xff; nxt[1] = (q0 >> 8) & 0xff; nxt[2] = (q0 >> 16) & 0xff; nxt[3] = q0 >> 24;
-                nxt[4] = q1 & 0xff; nxt[5] = (q1 >> 8) & 0xff; nxt[6] = (q1 >> 16) & 0xff; nxt[7] = q1 >> 24;
+            // this lane's 9 bytes of row (iny + row) from column inx + c0, packed: P0 = b0..b3, P1 = b4..b7, P2 = b8
+            unsigned P0, P1, P2;
+            if (inx >= 0 && inx + 17 <= cols && iny >= 0 && iny + 16 <= rows) {   // warp-uniform: footprint inside the level
+                // three aligned 32-bit loads + funnel shifts instead of nine byte loads (rows are 16-byte aligned; the
+                // <= 3 bytes read past the footprint stay inside the row pitch / the padded allocation)
+                const uint8_t* a = imgB + (size_t)(iny + L.row) * pitch + (inx + L.c0);
+                const unsigned sh = ((unsigned)(size_t)a & 3u) * 8u;
+                const unsigned* aw = reinterpret_cast<const unsigned*>((size_t)a & ~(size_t)3);
+                const unsigned W0 = __ldg(aw), W1 = __ldg(aw + 1), W2 = __ldg(aw + 2);
+                P0 = __funnelshift_r(W0, W1, sh);
+                P1 = __funnelshift_r(W1, W2, sh);
+                P2 = (W2 >> sh) & 0xffu;
+            } else {
+                int cur[NPX + 1];
+                load_row<NPX + 1>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row, cur);
+                P0 = (unsigned)cur[0] | ((unsigned)cur[1] << 8) | ((unsigned)cur[2] << 16) | ((unsigned)cur[3] << 24);
+                P1 = (unsigned)cur[4] | ((unsigned)cur[5] << 8) | ((unsigned)cur[6] << 16) | ((unsigned)cur[7] << 24);
+                P2 = (unsigned)cur[8];
             }
+            const unsigned N0 = __shfl_down_sync(0xffffffffu, P0, LPR);      // the row below, from lane + 2
+            const unsigned N1 = __shfl_down_sync(0xffffffffu, P1, LPR);
+            const unsigned N2 = __shfl_down_sync(0xffffffffu, P2, LPR);
+            // bilinear sample k = w00 b_k + w01 b_{k+1} + w10 n_k + w11 n_{k+1}: two 2-way 16x8-bit dot products
+            // (dp2a) on byte pairs; odd k read the pairs from the words shifted by one byte
+            const unsigned Q0 = __funnelshift_r(P0, P1, 8), Q1 = __funnelshift_r(P1, P2, 8);
+            const unsigned M0 = __funnelshift_r(N0, N1, 8), M1 = __funnelshift_r(N1, N2, 8);
+            const unsigned Wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16);
+            const unsigned Wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);     // w11 may be -1
+            const int rnd = 1 << (LK_W_BITS - 6);
+            int jv[NPX];
+            jv[0] = dp2a_lo_su(Wt, P0, dp2a_lo_su(Wb, N0, rnd)) >> (LK_W_BITS - 5);
+            jv[1] = dp2a_lo_su(Wt, Q0, dp2a_lo_su(Wb, M0, rnd)) >> (LK_W_BITS - 5);
+            jv[2] = dp2a_hi_su(Wt, P0, dp2a_hi_su(Wb, N0, rnd)) >> (LK_W_BITS - 5);
+            jv[3] = dp2a_hi_su(Wt, Q0, dp2a_hi_su(Wb, M0, rnd)) >> (LK_W_BITS - 5);
+            jv[4] = dp2a_lo_su(Wt, P1, dp2a_lo_su(Wb, N1, rnd)) >> (LK_W_BITS - 5);
+            jv[5] = dp2a_lo_su(Wt, Q1, dp2a_lo_su(Wb, M1, rnd)) >> (LK_W_BITS - 5);
+            jv[6] = dp2a_hi_su(Wt, P1, dp2a_hi_su(Wb, N1, rnd)) >> (LK_W_BITS - 5);
+            jv[7] = dp2a_hi_su(Wt, Q1, dp2a_hi_su(Wb, M1, rnd)) >> (LK_W_BITS - 5);
             int sb[2] = {0, 0};
 #pragma unroll
             for (int k = 0; k < NPX; ++k) {
-                const int jv = (cur[k] * w00 + cur[k + 1] * w01 + nxt[k] * w10 + nxt[k + 1] * w11 + (1 << (LK_W_BITS - 6))) >>
-                               (LK_W_BITS - 5);
-                const int diff = jv - (int)tI[k];
+                const int diff = jv[k] - (int)tI[k];
                 sb[0] += diff * (int)tIx[k];            // tIx/tIy are zero for inactive slots
                 sb[1] += diff * (int)tIy[k];
             }
