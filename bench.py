@@ -44,7 +44,7 @@ UNIT = 'frames/s'
 
 
 def workload(name):
-    from oracle.configs import config_c2, config_c3      # plain attribute bags (no oracle arithmetic)
+    from frontend_config import config_c2, config_c3
     if name == 'c2':
         return config_c2(), dict(width=752, height=480, seed=7, sigma=2.2, drift=(1.6, 0.7),
                                  gyro=(0.01, -0.02, 0.03), noise=1.0), \

@@ -23,6 +23,7 @@ from collections import namedtuple
 import numpy as np
 
 from . import cv_semantics as cs
+from . import ransac as rs
 
 feature_msg = namedtuple('feature_msg', ['timestamp', 'features'])
 PortFeature = namedtuple('PortFeature', ['id', 'u0', 'v0', 'u1', 'v1'])
@@ -145,6 +146,7 @@ class FrontEndPort:
         self.prev_ts = None
         self.next_feature_id = 0
         self.first_frame = True
+        self.frame_index = 0
         self.num_features = {}
         self._set_table(*self._empty())
 
@@ -229,7 +231,7 @@ class FrontEndPort:
                         p1[sel].astype(np.float32), np.ones(n, bool))
 
     # -- frame k>0: tracker (feature_tracker.py:74-157) ------------------------------------------
-    def _track(self, img0, img1, R_p_c, gh, gw):
+    def _track(self, img0, img1, R_p_c, gh, gw, R_p_c1=None):
         cfg = self.cfg
         nf = self.num_features
         nf['before_tracking'] = len(self.ids)
@@ -249,11 +251,28 @@ class FrontEndPort:
             self.tap('temporal', dict(prev=self.p0.copy(), pred=pred.copy(), cur=cur.copy(),
                                       st=st.copy(), keep=keep.copy()))
         ids, life, cur = self.ids[keep], self.life[keep], cur[keep]
+        prev0, prev1 = self.p0[keep], self.p1[keep]
         nf['after_tracking'] = len(cur)
         p1, ok = self.stereo_match(img0, img1, cur)
-        ids, life, cur, p1 = ids[ok], life[ok], cur[ok], p1[ok]
+        ids, life, cur, p1, prev0, prev1 = ids[ok], life[ok], cur[ok], p1[ok], prev0[ok], prev1[ok]
         nf['after_matching'] = len(cur)
-        nf['after_ransac'] = len(cur)                      # RANSAC is an all-ones stub (B2)
+        if getattr(cfg, 'two_point_ransac', False) and len(cur):
+            # NOT in the reference (all-ones stub, B2): oracle/ransac.py, applied per camera, survivors need both
+            be, seed = self.be, int(getattr(cfg, 'ransac_seed', 0))
+            inl = np.ones(len(cur), bool)
+            for cam, (a, b, K, D, R) in enumerate((
+                    (prev0, cur, cfg.cam0_intrinsics, cfg.cam0_distortion_coeffs, R_p_c),
+                    (prev1, p1, cfg.cam1_intrinsics, cfg.cam1_distortion_coeffs, R_p_c1))):
+                u_prev = be.undistort(np.asarray(a, np.float32), K, D, R)
+                u_cur = be.undistort(np.asarray(b, np.float32), K, D)
+                m = rs.two_point_ransac(u_prev, u_cur, K, cfg.ransac_threshold, seed=seed,
+                                        frame_index=self.frame_index, cam=cam)
+                if self.tap is not None:
+                    self.tap('ransac', dict(cam=cam, prev=np.array(a), cur=np.array(b), R=np.array(R), mask=m.copy(),
+                                            frame_index=self.frame_index))
+                inl &= m
+            ids, life, cur, p1 = ids[inl], life[inl], cur[inl], p1[inl]
+        nf['after_ransac'] = len(cur)                      # reference: all-ones stub (B2) -> same as after_matching
         cell = _cells(cur, gh, gw, cfg.grid_col) if len(cur) else np.zeros(0, np.int64)
         order = np.argsort(cell, kind='stable')            # per-cell append in list order
         self._set_table(ids[order], life[order] + 1, cell[order], cur[order], p1[order],
@@ -335,8 +354,8 @@ class FrontEndPort:
             self._initialize(img0, img1, gh, gw)
             self.first_frame = False
         else:
-            R0, _ = self._integrate_imu(self.prev_ts, ts)
-            self._track(img0, img1, R0, gh, gw)
+            R0, R1 = self._integrate_imu(self.prev_ts, ts)
+            self._track(img0, img1, R0, gh, gw, R1)
             self._add(img0, img1, gh, gw)
             self._prune()
         out = self._publish(ts)
@@ -344,6 +363,7 @@ class FrontEndPort:
             self.tap('grid', dict(ids=self.ids.copy(), life=self.life.copy(), cell=self.cell.copy(),
                                   p0=self.p0.copy(), p1=self.p1.copy(), fresh=self.fresh.copy()))
         self.prev_img0, self.prev_ts = img0, ts
+        self.frame_index += 1
         return out
 
     stareo_callback = stereo_callback
