@@ -53,7 +53,7 @@ def workload(name):
     if name == 'c3':
         return config_c3(), dict(width=1280, height=1024, seed=11, sigma=1.8, drift=(1.2, 0.9)), \
             'C3: 1280x1024 stereo, grid 10x10 x max 20 = 2000 features, 5-level pyramid (intrinsics scaled with ' \
-            'the image; RANSAC off = reference parity)'
+            'the image), batched two-point RANSAC on (not a reference stage: the reference stubs it out; oracle/ransac.py defines it)'
     raise SystemExit(f'unknown workload {name}')
 
 
@@ -119,7 +119,8 @@ def make_sequence(skw, n_frames):
 
 
 def rotations_for(cfg, stream):
-    """cam0_R_p_c per frame exactly as the pipeline's IMUProcessor produces it with the synchronous driver."""
+    """(cam0_R_p_c, cam1_R_p_c) per frame exactly as the pipeline's IMUProcessor produces them with the synchronous
+    driver; the second one is read by the RANSAC kernel only (workload c3)."""
     from image_processing import IMUProcessor
     imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
     out, prev = [], None
@@ -128,7 +129,7 @@ def rotations_for(cfg, stream):
             imu.imu_callback(msg)
             continue
         imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = prev, msg.cam0_msg
-        out.append(np.eye(3) if prev is None else imu.integrate_imu_data()[0])
+        out.append((np.eye(3), np.eye(3)) if prev is None else tuple(imu.integrate_imu_data()))
         prev = msg.cam0_msg
     return out
 
@@ -260,7 +261,7 @@ def main():
     for k, f in enumerate(frames):
         hb[k, :img_bytes] = f.cam0_image.reshape(-1)
         hb[k, img_bytes:2 * img_bytes] = f.cam1_image.reshape(-1)
-        ctx.fill_rotations(hb[k], Rs[k])
+        ctx.fill_rotations(hb[k], Rs[k][0], Rs[k][1])
     dev_blocks = host_blocks.cuda(non_blocking=False)
     ptr = dev_blocks.data_ptr()
     ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local)
@@ -353,11 +354,12 @@ def main():
         nblk = WM + 1 + KM + 2                            # + 2 frames for the serialised stage timing
         mblocks = torch.zeros((nblk, mbb), dtype=torch.uint8, device='cuda')
         imgs = dev_blocks[:, :2 * img_bytes]
-        Hs = dev_blocks[:, ctx.rot_offset:ctx.rot_offset + 72]
+        rs_ = ctx.rot_stride                              # H | cam0_R_p_c | cam1_R_p_c per stream
+        Hs = dev_blocks[:, ctx.rot_offset:ctx.rot_offset + rs_]
         for k in range(nblk):
             src = torch.arange(S, device='cuda') * 2 + k      # stream s starts 2*s frames into the sequence
             mblocks[k, :S * 2 * img_bytes] = imgs[src].reshape(-1)
-            mblocks[k, rot_off:rot_off + S * 72] = Hs[src].reshape(-1)
+            mblocks[k, rot_off:rot_off + S * rs_] = Hs[src].reshape(-1)
         mptr = mblocks.data_ptr()
         mext = torch.cuda.ExternalStream(mctx.cuda_stream(), device=local)
         for k in range(WM + 1):

@@ -26,6 +26,7 @@
  *                                 (FeatureInitializer / FeatureTracker / FeatureAdder / FeaturePruner /
  *                                  FeaturePublisher fused into one CUDA-graph launch per frame)
  *   avb_get_features              pipeline.prev_features (state read-back)  image_processing/pipeline.py:145-148
+ *   avb_two_point_ransac          (none: all-ones stub)                 image_processing/feature_tracker.py:135-136
  */
 #ifndef AVB_H_
 #define AVB_H_
@@ -36,7 +37,7 @@
 extern "C" {
 #endif
 
-#define AVB_ABI_VERSION 1
+#define AVB_ABI_VERSION 2
 
 #define AVB_OK              0
 #define AVB_E_INVALID      -1   /* bad argument / unsupported configuration */
@@ -59,7 +60,10 @@ typedef struct avb_config {
     int32_t num_streams;              /* S independent pipelines processed per launch       */
     int32_t device;                   /* CUDA device ordinal                                */
     int32_t use_graph;                /* 1: replay the per-frame kernel chain as a CUDA graph */
-    int32_t ransac;                   /* 0 = reference parity (all-ones stub, feature_tracker.py:135-136) */
+    int32_t ransac;                   /* 0 = reference parity (all-ones stub, feature_tracker.py:135-136);
+                                         1 = two-point RANSAC between k_track and the grid rebuild (config C3) */
+    int32_t ransac_seed;              /* key of the counter-based draws (with stream frame index, camera, hypothesis) */
+    int32_t reserved0;                /* keeps the doubles below 8-byte aligned; must be 0   */
     double  track_precision;          /* cfg.track_precision (LK epsilon, px)               */
     double  min_eig_threshold;        /* cv2 default 1e-4                                   */
     double  stereo_threshold;         /* cfg.stereo_threshold                               */
@@ -96,23 +100,29 @@ int  avb_get_geometry(const avb_ctx* ctx, int* width, int* height, int* num_stre
 int  avb_reset(avb_ctx* ctx);                         /* back to first_frame = True for all streams */
 
 /* One frame's input for all streams is a single "input block": S*2 images of width*height bytes in
- * [stream][cam] order, padded to 256 B, then S 3x3 row-major double matrices H = K R_p_c K^-1.
+ * [stream][cam] order, padded to 256 B, then per stream 27 doubles: H = K0 R_p_c0 K0^-1 (gyro prediction,
+ * feature_tracker.py:159-177), R_p_c0 and R_p_c1 (the two rotations IMUProcessor.integrate_imu_data returns,
+ * imu_processor.py:55-66; read by the RANSAC kernel only), each 3x3 row-major.
  * avb_input_staging returns the context's pinned block, which the caller may fill in place (zero-copy
  * intake); avb_process_frame(…, img0 = img1 = NULL) consumes it as is. */
 uint8_t* avb_input_staging(avb_ctx* ctx);
 size_t   avb_input_block_bytes(const avb_ctx* ctx);
 size_t   avb_input_rotation_offset(const avb_ctx* ctx);
-/* Writes H = K0 R K0^-1 for every stream into `block` (host memory, block layout above).
- * R_p_c0 = S*9 doubles (cam0_R_p_c of IMUProcessor.integrate_imu_data); NULL = identity. */
-int      avb_fill_rotations(const avb_ctx* ctx, uint8_t* block, const double* R_p_c0);
+size_t   avb_input_rotation_stride(const avb_ctx* ctx);   /* bytes per stream in the rotation section (27 doubles) */
+/* Writes the rotation section for every stream into `block` (host memory, block layout above).
+ * R_p_c0 / R_p_c1 = S*9 doubles each (cam0_R_p_c, cam1_R_p_c of IMUProcessor.integrate_imu_data);
+ * R_p_c0 NULL = identity for both; R_p_c1 NULL = the same gyro rotation seen from cam1,
+ * R_cam0_to_cam1 R_p_c0 R_cam0_to_cam1^T. */
+int      avb_fill_rotations(const avb_ctx* ctx, uint8_t* block, const double* R_p_c0, const double* R_p_c1);
 
 /* ---- hot path -------------------------------------------------------------------------- */
 
 /* One stereo frame for every stream.  img0[s]/img1[s]: host uint8, row stride = stride bytes
- * (NULL arrays: take the pinned staging).  R_p_c0: S*9 doubles, cam0_R_p_c from the IMU
- * integration (identity on frame 0).  Blocks until the results are in host memory. */
+ * (NULL arrays: take the pinned staging).  R_p_c0 / R_p_c1: S*9 doubles each, the camera rotations from the
+ * IMU integration (NULL rules of avb_fill_rotations; identity on frame 0).  Blocks until the results are in
+ * host memory. */
 int  avb_process_frame(avb_ctx* ctx, const uint8_t* const* img0, const uint8_t* const* img1,
-                       int stride, const double* R_p_c0);
+                       int stride, const double* R_p_c0, const double* R_p_c1);
 
 /* Same, the whole input block already resident in device memory (layout above). */
 int  avb_process_frame_device(avb_ctx* ctx, const uint8_t* d_block);
@@ -160,6 +170,14 @@ int  avb_undistort_points(avb_ctx* ctx, const double* intrinsics4, const double*
                           const double* xy, int n, const double* R, int f32_io, double* out_xy);
 int  avb_distort_points(avb_ctx* ctx, const double* intrinsics4, const double* distortion4,
                         const double* xy, int n, int f32_io, double* out_xy);
+
+/* Two-point RANSAC between the previous and the current frame of ONE camera (k_ransac on a flat list).  Not a
+ * reference interface: the reference's masks are an all-ones stub (feature_tracker.py:135-136); this is the stage
+ * BASELINE config C3 names, defined by oracle/ransac.py.  prev_xy / cur_xy: n pixel positions (f32 pairs);
+ * R_p_c: the camera's gyro rotation (9 doubles, NULL = identity); draws are keyed by (seed, frame_index, cam). */
+int  avb_two_point_ransac(avb_ctx* ctx, const double* intrinsics4, const double* distortion4, const float* prev_xy,
+                          const float* cur_xy, int n, const double* R_p_c, double threshold_px, int seed,
+                          int frame_index, int cam, uint8_t* inlier);
 
 /* ---- measurement hooks ------------------------------------------------------------------ */
 

@@ -31,14 +31,30 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert set(names) == set(_native.EXPORTS)
-    assert lib.avb_abi_version() == 1
+    assert lib.avb_abi_version() == 2
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every avb_config and avb_frame_header field, as gcc lays out include/avb.h, equal the
+    ctypes mirrors."""
+    import subprocess
     from image_processing import _native
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "avb.h"', 'int main(void) {']
+    for cname, cls in (('avb_config', _native.AvbConfig), ('avb_frame_header', _native.AvbFrameHeader)):
+        prog.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in cls._fields_:
+            prog.append(f'  printf("{cname}.{f[0]} %zu\\n", offsetof({cname}, {f[0]}));')
+    prog += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(prog))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in (('avb_config', _native.AvbConfig), ('avb_frame_header', _native.AvbFrameHeader)):
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f in cls._fields_:
+            assert int(got[f'{cname}.{f[0]}']) == getattr(cls, f[0]).offset, f'{cname}.{f[0]}'
     assert C.sizeof(_native.AvbFrameHeader) == 48
-    # 14 int32 + 4 double + 4*4 double + 2*9 double
-    assert C.sizeof(_native.AvbConfig) == 14 * 4 + (4 + 16 + 18) * 8
 
 
 def test_no_cpu_fallback_without_device():

@@ -33,7 +33,7 @@ def run(max_iter, levels, wpf, n=14):
     for k, f in enumerate(frames):
         hb[k, :ib] = f.cam0_image.reshape(-1)
         hb[k, ib:2 * ib] = f.cam1_image.reshape(-1)
-        ctx.fill_rotations(hb[k], Rs[k])
+        ctx.fill_rotations(hb[k], Rs[k][0], Rs[k][1])
     dev = host.cuda()
     for k in range(4):
         ctx.process_device(dev.data_ptr() + k * bb)

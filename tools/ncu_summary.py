@@ -1,0 +1,89 @@
+"""Condense ncu CSV exports into the small tables kept under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/<tag>_launches.csv          -> per-kernel count / avg us / share
+  python tools/ncu_summary.py raw gpurun_out/<tag>_s64.raw.csv                -> per-kernel key metrics of a --set full capture
+"""
+from __future__ import annotations
+
+import csv
+import sys
+from collections import OrderedDict, defaultdict
+
+KEY_METRICS = [
+    ('gpu__time_duration.sum', 'dur'),
+    ('dram__bytes_read.sum', 'dram_rd'),
+    ('dram__bytes_write.sum', 'dram_wr'),
+    ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct'),
+    ('lts__t_bytes.sum', 'l2_bytes'),
+    ('lts__t_sector_hit_rate.pct', 'l2_hit_pct'),
+    ('l1tex__t_sector_hit_rate.pct', 'l1_hit_pct'),
+    ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ_pct'),
+    ('smsp__inst_executed.sum', 'inst'),
+    ('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'alu_pct'),
+    ('smsp__issue_active.avg.pct', 'issue_pct'),
+    ('launch__registers_per_thread', 'regs'),
+    ('launch__occupancy_limit_registers', 'occ_lim_regs'),
+    ('smsp__cycles_active.avg', 'cycles'),
+]
+
+
+def short(name):
+    return name.split('(')[0].replace('void ', '').strip()
+
+
+def launches(path):
+    rows = defaultdict(list)
+    with open(path, newline='') as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r.get('Metric Name') != 'gpu__time_duration.sum':
+            continue
+        v = float(r['Metric Value'].replace(',', ''))
+        unit = r['Metric Unit']
+        v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'usecond': 1.0, 'nsecond': 1e-3, 'msecond': 1e3}.get(unit, 1.0)
+        rows[short(r['Kernel Name']) + ' grid ' + r['Grid Size'].replace(' ', '')].append(v)
+    tot = sum(sum(v) for v in rows.values())
+    print('| kernel (grid) | launches | avg us | total us | share |\n|---|---|---|---|---|')
+    for k, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
+        print(f'| {k} | {len(v)} | {sum(v) / len(v):.1f} | {sum(v):.0f} | {100 * sum(v) / tot:.1f} % |')
+    print(f'\ntotal {tot:.0f} us over {sum(len(v) for v in rows.values())} launches')
+
+
+def raw(path):
+    with open(path, newline='') as f:
+        rd = csv.reader(f)
+        hdr = next(rd)
+        units = next(rd)
+        col = {h: i for i, h in enumerate(hdr)}
+        seen = OrderedDict()
+        for r in rd:
+            if len(r) != len(hdr):
+                continue
+            name = short(r[col['Kernel Name']]) + ' grid ' + r[col['Grid Size']].replace(' ', '')
+            seen.setdefault(name, []).append(r)
+    names = [n for _, n in KEY_METRICS]
+    print('| kernel (grid) | n | ' + ' | '.join(names) + ' |\n|---|---|' + '---|' * len(names))
+    for k, rs in seen.items():
+        cells = []
+        for m, _ in KEY_METRICS:
+            if m not in col:
+                cells.append('-')
+                continue
+            vals = []
+            for r in rs:
+                try:
+                    vals.append(float(r[col[m]].replace(',', '')))
+                except ValueError:
+                    pass
+            if not vals:
+                cells.append('-')
+                continue
+            v = sum(vals) / len(vals)
+            u = units[col[m]]
+            cells.append(f'{v:.4g} {u}'.strip())
+        print(f'| {k} | {len(rs)} | ' + ' | '.join(cells) + ' |')
+
+
+if __name__ == '__main__':
+    {'launches': launches, 'raw': raw}[sys.argv[1]](sys.argv[2])

@@ -41,7 +41,8 @@ def main():
             hb[k, (2 * s) * ib:(2 * s + 1) * ib] = f.cam0_image.reshape(-1)
             hb[k, (2 * s + 1) * ib:(2 * s + 2) * ib] = f.cam1_image.reshape(-1)
         import numpy as np
-        ctx.fill_rotations(hb[k], np.stack([Rs[k + 2 * s] for s in range(S)]))
+        ctx.fill_rotations(hb[k], np.stack([Rs[k + 2 * s][0] for s in range(S)]),
+                           np.stack([Rs[k + 2 * s][1] for s in range(S)]))
     dev = host.cuda()
     for k in range(F):
         ctx.process_device(dev.data_ptr() + k * bb)

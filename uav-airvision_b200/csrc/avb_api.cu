@@ -1,5 +1,6 @@
 // C-ABI of libavb (include/avb.h): context, memory, CUDA-graph frame path, per-stage entry points.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -107,7 +108,8 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
         return fail(c, AVB_E_INVALID, "need 0 <= grid_min <= grid_max <= %d", AVB_MAX_CAP);
     if (cfg->num_streams < 1 || cfg->num_streams > 4096) return fail(c, AVB_E_INVALID, "num_streams must be 1..4096");
     if (cfg->fast_threshold < 1 || cfg->fast_threshold > 254) return fail(c, AVB_E_INVALID, "fast_threshold must be 1..254");
-    if (cfg->ransac) return fail(c, AVB_E_INVALID, "two-point RANSAC is not part of the reference path (all-ones stub); ransac=1 unsupported");
+    if (cfg->ransac != 0 && cfg->ransac != 1) return fail(c, AVB_E_INVALID, "ransac must be 0 or 1");
+    if (cfg->ransac && !(cfg->ransac_threshold > 0.0)) return fail(c, AVB_E_INVALID, "ransac_threshold must be positive");
     if ((size_t)cfg->width * cfg->height >= (1u << 24)) return fail(c, AVB_E_INVALID, "image too large for the 24-bit scan index");
 
     c = new avb_ctx();
@@ -161,6 +163,10 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     memcpy(g.R01, cfg->R_cam0_to_cam1, sizeof g.R01);
     memcpy(g.E, cfg->essential, sizeof g.E);
     g.epi_thr = cfg->stereo_threshold * (4.0 / (2 * g.cam0.fx + 2 * g.cam0.fy));
+    g.ransac = cfg->ransac;
+    g.ransac_seed = cfg->ransac_seed;
+    g.ransac_iters = (int)ceil(log(1.0 - 0.99) / log(1.0 - 0.7 * 0.7));     // success probability 0.99, inlier ratio 0.7
+    g.ransac_thr = cfg->ransac_threshold;
     if (g.NMAX > 8192) {
         delete c;
         return fail(nullptr, AVB_E_INVALID, "grid_num*grid_max = %d exceeds 8192", g.NMAX);
@@ -214,16 +220,19 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(dalloc(c, &d.next_id, S));
     CKC(dalloc(c, &d.counters, S * 8));
     CKC(dalloc(c, &d.frame_index, S));
+    if (g.ransac) {
+        CKC(dalloc(c, &d.r_idx, 2 * S * NM));
+        CKC(dalloc(c, &d.r_und, 2 * S * NM));
+        CKC(dalloc(c, &d.r_raw, 2 * S * NM));
+        CKC(dalloc(c, &d.r_bits, 2 * S * NM));
+    }
     c->out_stride = out_stride_bytes(g.NMAX);
     CKC(dalloc(c, &d.out, S * c->out_stride));
     CKC(cudaHostAlloc((void**)&c->h_in, inb, cudaHostAllocDefault));
     CKC(cudaHostAlloc((void**)&c->h_out, S * c->out_stride, cudaHostAllocDefault));
     memset(c->h_in, 0, inb);
     memset(c->h_out, 0, S * c->out_stride);
-    {   // identity H until the caller provides rotations
-        double* H = reinterpret_cast<double*>(c->h_in + in_images_bytes(g));
-        for (size_t s = 0; s < S; ++s) H[s * 9 + 0] = H[s * 9 + 4] = H[s * 9 + 8] = 1.0;
-    }
+    avb_fill_rotations(c, c->h_in, nullptr, nullptr);      // identity until the caller provides rotations
 
     // dynamic shared memory of the bookkeeping kernels
     const size_t sel_smem = (size_t)g.KPC * 4;
@@ -350,6 +359,7 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
         launch_select(g, d, p, 1, c->st);
     } else {
         launch_track(g, d, p, c->st);
+        if (g.ransac) launch_ransac(g, d, p, c->st);
         cudaStreamWaitEvent(c->st, c->ev_join, 0);
         launch_select(g, d, p, 0, c->st);
         launch_stereo_candidates(g, d, p, c->st);
@@ -379,6 +389,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     launch_pyramid(g, d, c->maps, p, c->st);
     CK(cudaEventRecord(ev[3], c->st));
     launch_track(g, d, p, c->st);
+    if (g.ransac) launch_ransac(g, d, p, c->st);       // counted with the track stage
     CK(cudaEventRecord(ev[4], c->st));
     launch_select(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[5], c->st));
@@ -401,7 +412,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
     // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
-    return 2 + avb_pyramid_launches(c->g) + 4;
+    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {
@@ -427,27 +438,40 @@ static int build_graphs(avb_ctx* c) {
 
 extern "C" size_t avb_input_block_bytes(const avb_ctx* c) { return c ? in_block_bytes(c->g) : 0; }
 extern "C" size_t avb_input_rotation_offset(const avb_ctx* c) { return c ? in_images_bytes(c->g) : 0; }
+extern "C" size_t avb_input_rotation_stride(const avb_ctx* c) { return c ? AVB_ROT_DOUBLES * sizeof(double) : 0; }
 
-extern "C" int avb_fill_rotations(const avb_ctx* c, uint8_t* block, const double* R_p_c0) {
+extern "C" int avb_fill_rotations(const avb_ctx* c, uint8_t* block, const double* R_p_c0, const double* R_p_c1) {
     // H = K R_p_c K^-1 (feature_tracker.py:166-171) in double: (K @ R) @ inv(K), inv(K) in closed form
     if (!c || !block) return AVB_E_INVALID;
     const Geom& g = c->g;
-    double* H = reinterpret_cast<double*>(block + in_images_bytes(g));
+    double* sec = reinterpret_cast<double*>(block + in_images_bytes(g));
     const double fx = g.cam0.fx, fy = g.cam0.fy, cx = g.cam0.cx, cy = g.cam0.cy;
     const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
     const double Ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
+    auto mul = [](const double* A, const double* B, double* C) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+    };
     for (int s = 0; s < g.S; ++s) {
-        double* h = H + (size_t)s * 9;
+        double* h = sec + (size_t)s * AVB_ROT_DOUBLES;
         if (!R_p_c0) {
-            for (int i = 0; i < 9; ++i) h[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            for (int i = 0; i < AVB_ROT_DOUBLES; ++i) h[i] = ((i % 9) % 4 == 0) ? 1.0 : 0.0;
             continue;
         }
         const double* R = R_p_c0 + (size_t)s * 9;
         double KR[9];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) KR[i * 3 + j] = K[i * 3] * R[j] + K[i * 3 + 1] * R[3 + j] + K[i * 3 + 2] * R[6 + j];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) h[i * 3 + j] = KR[i * 3] * Ki[j] + KR[i * 3 + 1] * Ki[3 + j] + KR[i * 3 + 2] * Ki[6 + j];
+        mul(K, R, KR);
+        mul(KR, Ki, h);
+        memcpy(h + 9, R, 9 * sizeof(double));
+        if (R_p_c1) {
+            memcpy(h + 18, R_p_c1 + (size_t)s * 9, 9 * sizeof(double));
+        } else {                        // the same gyro rotation seen from cam1: R01 R0 R01^T
+            double T[9], R01t[9];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) R01t[i * 3 + j] = g.R01[j * 3 + i];
+            mul(g.R01, R, T);
+            mul(T, R01t, h + 18);
+        }
     }
     return AVB_OK;
 }
@@ -488,12 +512,12 @@ static bool is_page_locked(const void* p) {
 }
 
 extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
-                                 const double* R_p_c0) {
+                                 const double* R_p_c0, const double* R_p_c1) {
     if (!c) return AVB_E_INVALID;
     const Geom& g = c->g;
     CK(cudaSetDevice(c->cfg.device));
     if (!(img0 && img1)) {              // the caller filled the pinned staging block in place
-        avb_fill_rotations(c, c->h_in, R_p_c0);
+        avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
         return run_frame(c, 0, true);
     }
     if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
@@ -521,7 +545,7 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
             CK(cudaMemcpyAsync(c->d.in[p] + off, dst, ib, cudaMemcpyHostToDevice, c->st));
         }
     }
-    avb_fill_rotations(c, c->h_in, R_p_c0);
+    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     const size_t ro = in_images_bytes(g);
     CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st));
     return run_frame(c, 2, true);
@@ -742,6 +766,29 @@ extern "C" int avb_undistort_points(avb_ctx* c, const double* intr, const double
 extern "C" int avb_distort_points(avb_ctx* c, const double* intr, const double* dist, const double* xy, int n, int f32_io,
                                   double* out_xy) {
     return undist_common(c, intr, dist, xy, n, nullptr, f32_io, 1, out_xy);
+}
+
+extern "C" int avb_two_point_ransac(avb_ctx* c, const double* intr, const double* dist, const float* prev_xy, const float* cur_xy,
+                                    int n, const double* R_p_c, double threshold_px, int seed, int frame_index, int cam,
+                                    uint8_t* inlier) {
+    if (!c || !intr || !dist || n < 0 || !(threshold_px > 0.0)) return AVB_E_INVALID;
+    if (n == 0) return AVB_OK;
+    if (!prev_xy || !cur_xy || !inlier) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    int r = ensure_scratch(c, n);
+    if (r != AVB_OK) return r;
+    const CamModel cm = {intr[0], intr[1], intr[2], intr[3], dist[0], dist[1], dist[2], dist[3]};
+    const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    CK(cudaMemcpyAsync(c->s_a, prev_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->s_b, cur_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->s_R, R_p_c ? R_p_c : ident, 9 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));       // `ident` lives on this stack frame
+    launch_ransac_points(c->g, cm, c->s_R, c->s_a, c->s_b, n, reinterpret_cast<float4*>(c->s_da), reinterpret_cast<int*>(c->s_db),
+                         c->s_st, frame_index, cam, seed, threshold_px, c->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(inlier, c->s_st, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AVB_OK;
 }
 
 extern "C" int avb_time_pyramid(avb_ctx* c, int iters, float* ms_avg) {

@@ -11,6 +11,7 @@
 #define AVB_HALF 7
 #define AVB_MAX_CAP 32             // grid_max_feature_num upper bound (one warp ballots a cell's candidates)
 #define AVB_MAX_CELLS 1024
+#define AVB_ROT_DOUBLES 27         // per stream and frame: H (9) | cam0_R_p_c (9) | cam1_R_p_c (9)
 
 // Image slots of a stream: slot = cam * 2 + parity (parity = frame index & 1).  Level 0 of a slot is the
 // uploaded image itself inside the input block of that parity; levels >= 1 live in the pyramid arena.
@@ -54,6 +55,9 @@ struct Geom {
     double R01[9];                 // R_cam0_to_cam1
     double E[9];                   // essential
     double epi_thr;                // stereo_threshold * 4/(2fx+2fy)
+    int ransac;                    // 1: k_ransac runs between k_track and k_select (not the reference's behaviour)
+    int ransac_seed, ransac_iters; // counter-based draws; ceil(log(1-0.99)/log(1-0.7^2)) = 7 hypotheses
+    double ransac_thr;             // cfg.ransac_threshold (px)
 };
 
 // Feature table in grid order: cell c owns slots [c*gmax, c*gmax + count[c]).
@@ -85,7 +89,8 @@ __host__ __device__ inline float* out_p1(uint8_t* base, int nmax) { return (floa
 
 // All device buffers of a context (kernel parameter, by value).
 struct DevState {
-    uint8_t* in[2];                // input block per parity: [S][2 cams][H*W] images, then [S][9] doubles (H = K R K^-1)
+    uint8_t* in[2];                // input block per parity: [S][2 cams][H*W] images, then [S][27] doubles
+                                   // (H = K0 R0 K0^-1 | R0 = cam0_R_p_c | R1 = cam1_R_p_c)
     uint8_t* pyr;                  // [S][4 slots][slot_bytes], levels 1..L
     // FAST buckets
     unsigned* kp_key;              // [S][NC][KPC]  (response << 24) | (0xFFFFFF - (y*W + x))
@@ -107,7 +112,12 @@ struct DevState {
     int* n_new;                    // [S][NC]  new features given ids this frame (before pruning)
     uint8_t* new_rank;             // [S][NMAX] rank of a fresh feature among its cell's new ones
     long long* next_id;            // [S]
-    int* counters;                 // [S][8]: before_tracking, after_tracking, after_matching, n_fast, n_cand
+    int* counters;                 // [S][8]: before_tracking, after_tracking, after_matching, n_fast, n_cand, after_ransac
+    // two-point RANSAC scratch, [2 cams][S][NMAX] (allocated only when Geom::ransac)
+    int* r_idx;
+    float4* r_und;
+    int* r_raw;
+    uint8_t* r_bits;
     uint8_t* out;                  // [S][out_stride] device mirror of the result block
     int* frame_index;              // [S]
 };
@@ -122,10 +132,10 @@ __host__ __device__ inline size_t in_images_bytes(const Geom& g) {
     return (((size_t)g.S * 2 * g.W * g.H) + 255) & ~(size_t)255;
 }
 __host__ __device__ inline size_t in_block_bytes(const Geom& g) {
-    return in_images_bytes(g) + (((size_t)g.S * 9 * sizeof(double)) + 255 & ~(size_t)255);
+    return in_images_bytes(g) + (((size_t)g.S * AVB_ROT_DOUBLES * sizeof(double)) + 255 & ~(size_t)255);
 }
 __host__ __device__ inline const double* frame_H(const DevState& d, const Geom& g, int s, int parity) {
-    return reinterpret_cast<const double*>(d.in[parity] + in_images_bytes(g)) + (size_t)s * 9;
+    return reinterpret_cast<const double*>(d.in[parity] + in_images_bytes(g)) + (size_t)s * AVB_ROT_DOUBLES;
 }
 
 __device__ __forceinline__ PyrView pyr_view(const DevState& d, const Geom& g, int s, int slot) {
@@ -197,6 +207,10 @@ void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int p
 int  avb_pyramid_launches(const Geom& g);
 void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_ransac(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, const float2* prev, const float2* cur, int n,
+                          float4* und, int* raw_idx, uint8_t* bits, int frame_index, int cam_key, int seed, double thr_px,
+                          cudaStream_t st);
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
         h->before_tracking = cn[0];
         h->after_tracking = cn[1];
         h->after_matching = cn[2];
-        h->after_ransac = cn[2];       // RANSAC is an all-ones stub in the reference (B2)
+        h->after_ransac = g.ransac ? cn[5] : cn[2];    // reference: all-ones stub (B2) -> same as after_matching
         h->has_new = has_new;
         h->n_fast = cn[3];
         h->n_candidates = cn[4];

@@ -6,7 +6,7 @@
  * list of FeatureMeasurement out; reference image_processing/pipeline.py:46-150, feature_publisher.py:109-121,
  * imu_processor.py:28-67) and does the per-frame work natively:
  *
- *   process_frame(ctx, img0, img1, R|None, FeatureMeasurement) -> (features, header tuple)
+ *   process_frame(ctx, img0, img1, R|None (3x3 or 2x3x3), FeatureMeasurement) -> (features, header tuple)
  *       copies the two host images into libavb's pinned staging block (GIL released), runs avb_process_frame
  *       (H2D + CUDA-graph frame + D2H), and materialises the FeatureMeasurement list straight from the pinned
  *       result block
@@ -170,21 +170,23 @@ static PyObject* py_process_frame(PyObject* self, PyObject* args) {
         PyBuffer_Release(&b0);
         return NULL;
     }
-    double R[9];
+    double R[18];                       /* cam0_R_p_c [, cam1_R_p_c] */
+    int haveR1 = 0;
     if (Robj != Py_None) {
         if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) {
             PyBuffer_Release(&b0);
             PyBuffer_Release(&b1);
             return NULL;
         }
-        if (bR.len != 72 || bR.itemsize != 8) {
+        if ((bR.len != 72 && bR.len != 144) || bR.itemsize != 8) {
             PyBuffer_Release(&b0);
             PyBuffer_Release(&b1);
             PyBuffer_Release(&bR);
-            PyErr_SetString(PyExc_ValueError, "R must be a C-contiguous 3x3 float64 array");
+            PyErr_SetString(PyExc_ValueError, "R must be a C-contiguous float64 array: 3x3 (cam0_R_p_c) or 2x3x3 (cam0, cam1)");
             return NULL;
         }
-        memcpy(R, bR.buf, 72);
+        memcpy(R, bR.buf, (size_t)bR.len);
+        haveR1 = bR.len == 144;
         PyBuffer_Release(&bR);
         haveR = 1;
     }
@@ -197,7 +199,7 @@ static PyObject* py_process_frame(PyObject* self, PyObject* args) {
         const uint8_t* p1 = (const uint8_t*)b1.buf;
         const int stride = (int)b0.strides[0];
         Py_BEGIN_ALLOW_THREADS
-        rc = avb_process_frame(ctx, &p0, &p1, stride, haveR ? R : NULL);    /* staging + pipelined H2D + frame + D2H */
+        rc = avb_process_frame(ctx, &p0, &p1, stride, haveR ? R : NULL, haveR1 ? R + 9 : NULL);    /* staging + pipelined H2D + frame + D2H */
         Py_END_ALLOW_THREADS
     }
     PyBuffer_Release(&b0);
@@ -262,8 +264,8 @@ static PyObject* py_process_frames(PyObject* self, PyObject* args) {
     if (Robj != Py_None) {
         if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS) < 0) goto done;
         haveR = 1;
-        if (bR.len != (Py_ssize_t)S * 72 || bR.itemsize != 8) {
-            PyErr_Format(PyExc_ValueError, "R must be %d C-contiguous 3x3 float64 matrices", S);
+        if ((bR.len != (Py_ssize_t)S * 72 && bR.len != (Py_ssize_t)S * 144) || bR.itemsize != 8) {
+            PyErr_Format(PyExc_ValueError, "R must be (%d,3,3) float64 (cam0_R_p_c) or (2,%d,3,3) (cam0, cam1), C-contiguous", S, S);
             goto done;
         }
     }
@@ -288,7 +290,8 @@ static PyObject* py_process_frames(PyObject* self, PyObject* args) {
         }
         int rc;
         Py_BEGIN_ALLOW_THREADS
-        rc = avb_process_frame(ctx, NULL, NULL, W, haveR ? (const double*)bR.buf : NULL);
+        rc = avb_process_frame(ctx, NULL, NULL, W, haveR ? (const double*)bR.buf : NULL,
+                               haveR && bR.len == (Py_ssize_t)S * 144 ? (const double*)bR.buf + (size_t)S * 9 : NULL);
         Py_END_ALLOW_THREADS
         if (rc != AVB_OK) {
             PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));

@@ -13,10 +13,11 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libavb.so')
 EXPORTS = (
     'avb_abi_version', 'avb_last_error', 'avb_create', 'avb_destroy', 'avb_capacity', 'avb_num_cells',
     'avb_reset', 'avb_input_staging', 'avb_input_block_bytes', 'avb_input_rotation_offset',
+    'avb_input_rotation_stride',
     'avb_fill_rotations', 'avb_process_frame', 'avb_process_frame_device', 'avb_enqueue_frame_device',
     'avb_sync', 'avb_get_result', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
-    'avb_undistort_points', 'avb_distort_points', 'avb_last_frame_ms', 'avb_kernels_per_frame',
+    'avb_undistort_points', 'avb_distort_points', 'avb_two_point_ransac', 'avb_last_frame_ms', 'avb_kernels_per_frame',
     'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device', 'avb_get_geometry',
 )
 
@@ -27,6 +28,7 @@ class AvbConfig(C.Structure):
         ('max_iteration', C.c_int32), ('fast_threshold', C.c_int32), ('grid_row', C.c_int32),
         ('grid_col', C.c_int32), ('grid_min_feature_num', C.c_int32), ('grid_max_feature_num', C.c_int32),
         ('num_streams', C.c_int32), ('device', C.c_int32), ('use_graph', C.c_int32), ('ransac', C.c_int32),
+        ('ransac_seed', C.c_int32), ('reserved0', C.c_int32),
         ('track_precision', C.c_double), ('min_eig_threshold', C.c_double), ('stereo_threshold', C.c_double),
         ('ransac_threshold', C.c_double),
         ('cam0_intrinsics', C.c_double * 4), ('cam0_distortion', C.c_double * 4),
@@ -78,8 +80,10 @@ def load():
     lib.avb_input_block_bytes.restype = C.c_size_t
     lib.avb_input_rotation_offset.argtypes = [vp]
     lib.avb_input_rotation_offset.restype = C.c_size_t
-    lib.avb_fill_rotations.argtypes = [vp, u8p, f64p]
-    lib.avb_process_frame.argtypes = [vp, vp, vp, ip, f64p]
+    lib.avb_input_rotation_stride.argtypes = [vp]
+    lib.avb_input_rotation_stride.restype = C.c_size_t
+    lib.avb_fill_rotations.argtypes = [vp, u8p, f64p, f64p]
+    lib.avb_process_frame.argtypes = [vp, vp, vp, ip, f64p, f64p]
     lib.avb_process_frame_device.argtypes = [vp, vp]
     lib.avb_enqueue_frame_device.argtypes = [vp, vp]
     lib.avb_get_result.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -91,12 +95,13 @@ def load():
     lib.avb_stereo_match.argtypes = [vp, ip, f32p, ip, f32p, u8p]
     lib.avb_undistort_points.argtypes = [vp, f64p, f64p, f64p, ip, f64p, ip, f64p]
     lib.avb_distort_points.argtypes = [vp, f64p, f64p, f64p, ip, ip, f64p]
+    lib.avb_two_point_ransac.argtypes = [vp, f64p, f64p, f32p, f32p, ip, f64p, C.c_double, ip, ip, ip, u8p]
     lib.avb_last_frame_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.avb_cuda_stream.argtypes = [vp]
     lib.avb_cuda_stream.restype = C.c_void_p
     lib.avb_time_pyramid.argtypes = [vp, ip, C.POINTER(C.c_float)]
     lib.avb_profile_frame_device.argtypes = [vp, vp, C.POINTER(C.c_float)]
-    if lib.avb_abi_version() != 1:
+    if lib.avb_abi_version() != 2:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
     return lib
@@ -140,7 +145,10 @@ class Context:
         ac.fast_threshold = int(cfg.fast_threshold)
         ac.grid_row, ac.grid_col = int(cfg.grid_row), int(cfg.grid_col)
         ac.grid_min_feature_num, ac.grid_max_feature_num = int(cfg.grid_min_feature_num), int(cfg.grid_max_feature_num)
-        ac.num_streams, ac.device, ac.use_graph, ac.ransac = int(num_streams), int(device), int(bool(use_graph)), 0
+        ac.num_streams, ac.device, ac.use_graph = int(num_streams), int(device), int(bool(use_graph))
+        # not reference fields (the reference's RANSAC is an all-ones stub): see frontend_config.FrontEndConfig
+        ac.ransac = int(bool(getattr(cfg, 'two_point_ransac', False)))
+        ac.ransac_seed = int(getattr(cfg, 'ransac_seed', 0))
         ac.stereo_threshold = float(cfg.stereo_threshold)
         ac.ransac_threshold = float(getattr(cfg, 'ransac_threshold', 3))
         ac.cam0_intrinsics[:] = [float(v) for v in cfg.cam0_intrinsics]
@@ -161,6 +169,8 @@ class Context:
         self.max_level = ac.max_level
         self.block_bytes = lib.avb_input_block_bytes(self._h)
         self.rot_offset = lib.avb_input_rotation_offset(self._h)
+        self.rot_stride = lib.avb_input_rotation_stride(self._h)
+        self.ransac = bool(ac.ransac)
         base = lib.avb_input_staging(self._h)
         img_bytes = self.S * 2 * self.width * self.height
         self._staging_block = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(self.block_bytes,))
@@ -191,21 +201,24 @@ class Context:
         self._ck(self._lib.avb_reset(self._h))
 
     # -- hot path ----------------------------------------------------------------------------------------
-    def process_staged(self, R_p_c0=None):
+    def process_staged(self, R_p_c0=None, R_p_c1=None):
         """One frame from the pinned staging block (caller filled self.staging[s, cam])."""
         R = self._ident if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
-        self._ck(self._lib.avb_process_frame(self._h, None, None, self.width, _ptr(R)))
+        R1 = None if (R_p_c0 is None or R_p_c1 is None) else np.ascontiguousarray(R_p_c1, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_process_frame(self._h, None, None, self.width, _ptr(R), _ptr(R1)))
 
-    def process(self, imgs0, imgs1, R_p_c0=None):
+    def process(self, imgs0, imgs1, R_p_c0=None, R_p_c1=None):
         """One frame: imgs0[s], imgs1[s] are (H, W) uint8 arrays (copied into pinned staging)."""
         for s in range(self.S):
             self.staging[s, 0] = imgs0[s]
             self.staging[s, 1] = imgs1[s]
-        self.process_staged(R_p_c0)
+        self.process_staged(R_p_c0, R_p_c1)
 
-    def fill_rotations(self, block, R_p_c0=None):
+    def fill_rotations(self, block, R_p_c0=None, R_p_c1=None):
+        """Rotation section of an input block: cam0_R_p_c / cam1_R_p_c per stream (None: identity / conjugated)."""
         R = None if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
-        self._ck(self._lib.avb_fill_rotations(self._h, _ptr(block), _ptr(R)))
+        R1 = None if (R is None or R_p_c1 is None) else np.ascontiguousarray(R_p_c1, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_fill_rotations(self._h, _ptr(block), _ptr(R), _ptr(R1)))
 
     def process_device(self, d_block_ptr: int):
         self._ck(self._lib.avb_process_frame_device(self._h, C.c_void_p(d_block_ptr)))
@@ -347,3 +360,19 @@ class Context:
         D = np.ascontiguousarray(np.asarray(distortion, dtype=np.float64)[:4])
         self._ck(self._lib.avb_distort_points(self._h, _ptr(K), _ptr(D), _ptr(p), len(p), int(f32_io), _ptr(out)))
         return out
+
+    def two_point_ransac(self, intrinsics, distortion, prev_xy, cur_xy, R_p_c=None, threshold=3.0, seed=0,
+                         frame_index=0, cam=0):
+        """Inlier mask of the two-point RANSAC between two frames of one camera (k_ransac; not a reference stage:
+        feature_tracker.py:135-136 is an all-ones stub).  prev_xy / cur_xy: (N, 2) pixel positions."""
+        a = np.ascontiguousarray(prev_xy, dtype=np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(cur_xy, dtype=np.float32).reshape(-1, 2)
+        if len(a) != len(b):
+            raise ValueError('prev_xy and cur_xy differ in length')
+        out = np.zeros(len(a), dtype=np.uint8)
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        D = np.ascontiguousarray(np.asarray(distortion, dtype=np.float64)[:4])
+        R = None if R_p_c is None else np.ascontiguousarray(R_p_c, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_two_point_ransac(self._h, _ptr(K), _ptr(D), _ptr(a), _ptr(b), len(a), _ptr(R),
+                                                float(threshold), int(seed), int(frame_index), int(cam), _ptr(out)))
+        return out.astype(bool)

@@ -127,7 +127,9 @@ class ImageProcessingPipeline:
         imu.cam0_curr_img_msg = cam0_msg
         R = None
         if not self.first_frame:
-            R, _ = imu.integrate_imu_data()
+            R, R1 = imu.integrate_imu_data()
+            if ctx.ransac:              # the RANSAC kernel compensates each camera with its own gyro rotation
+                R = np.ascontiguousarray(np.stack([R, R1]), dtype=np.float64)
         # host images -> pinned staging -> H2D -> CUDA-graph frame -> D2H -> FeatureMeasurement list, all in C
         feats, hdr = _avbhost.process_frame(ctx._h.value, cam0_msg.image, cam1_msg.image, R, FeatureMeasurement)
         self.next_feature_id = hdr[1]

@@ -41,7 +41,7 @@ class MultiStreamFrontEnd:
         self.first_frame = True
         self.next_feature_id = [0] * self.S
         self.num_features = [defaultdict(int) for _ in range(self.S)]
-        self._R = np.empty((self.S, 3, 3))
+        self._R = np.empty((2, self.S, 3, 3))          # [cam][stream]; cam 1 is passed on only with RANSAC on
 
     def close(self):
         self.ctx.close()
@@ -55,11 +55,11 @@ class MultiStreamFrontEnd:
             raise ValueError(f'expected {self.S} stereo messages')
         R = None
         if not self.first_frame:
-            R = self._R
             for s, m in enumerate(stereo_msgs):
                 imu = self.imu[s]
                 imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = self.prev_msg[s], m.cam0_msg
-                R[s] = imu.integrate_imu_data()[0]
+                self._R[0, s], self._R[1, s] = imu.integrate_imu_data()
+            R = self._R if self.ctx.ransac else self._R[0]
         res = _avbhost.process_frames(self.ctx._h.value, [m.cam0_msg.image for m in stereo_msgs],
                                       [m.cam1_msg.image for m in stereo_msgs], R, FeatureMeasurement)
         out = []

@@ -73,7 +73,7 @@ class SlidingTextureStream:
 
     def __init__(self, width=752, height=480, n_frames=20, seed=0, sigma=2.5,
                  disparity=12.0, drift=(1.3, 0.6), rate=20.0, imu_rate=200.0,
-                 gyro=(0.0, 0.0, 0.0), t0=1000.0, noise=0.0):
+                 gyro=(0.0, 0.0, 0.0), t0=1000.0, noise=0.0, movers=()):
         self.w, self.h, self.n = int(width), int(height), int(n_frames)
         self.seed, self.sigma = int(seed), float(sigma)
         self.disparity = float(disparity)
@@ -88,6 +88,24 @@ class SlidingTextureStream:
         self._tex = make_texture(self.h + 2 * margin_y + 2, self.w + 2 * margin_x + 2,
                                  self.seed, self.sigma)
         self._rng_seed = self.seed * 7919 + 13
+        # independently moving square patches (cx, cy, half, vx, vy): their own texture, same disparity in both cameras,
+        # own image velocity -> stereo-consistent features whose temporal motion contradicts the camera motion
+        # (what the two-point RANSAC stage is there to reject)
+        self.movers = [tuple(float(v) for v in m) for m in movers]
+        self._mover_tex = [make_texture(int(2 * m[2]) + 8, int(2 * m[2]) + 8, self.seed + 1000 + i, self.sigma)
+                           for i, m in enumerate(self.movers)]
+
+    def _paste_movers(self, img, k, shift_x):
+        for (cx, cy, half, vx, vy), tex in zip(self.movers, self._mover_tex):
+            px, py = cx + vx * k - shift_x - half, cy + vy * k - half      # top-left corner of the patch (fractional)
+            x_lo, y_lo = int(np.ceil(px)), int(np.ceil(py))
+            size = int(2 * half)
+            x_a, x_b = max(x_lo, 0), min(x_lo + size, self.w)
+            y_a, y_b = max(y_lo, 0), min(y_lo + size, self.h)
+            if x_a >= x_b or y_a >= y_b:
+                continue
+            img[y_a:y_b, x_a:x_b] = _sample(tex, x_a - px + 2.0, y_a - py + 2.0, y_b - y_a, x_b - x_a)
+        return img
 
     def frame(self, k: int):
         ts = self.t0 + k / self.rate
@@ -97,6 +115,9 @@ class SlidingTextureStream:
         # cam1 sees scene content shifted LEFT by the disparity: a cam0 point (x, y)
         # appears at (x - d, y) in cam1
         img1 = _sample(self._tex, x0 + self.disparity, y0, self.h, self.w)
+        if self.movers:
+            img0 = self._paste_movers(img0, k, 0.0)
+            img1 = self._paste_movers(img1, k, self.disparity)
         if self.noise > 0:
             rng = np.random.default_rng(self._rng_seed + k)
             n0 = rng.normal(0.0, self.noise, size=img0.shape)
