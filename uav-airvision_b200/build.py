@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(LIB, deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-        _run([nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) +
+        _run([nvcc] + NVCC_FLAGS + os.environ.get('AVB_EXTRA_NVCC', '').split() + (['-Xptxas', '-v'] if verbose else []) +
              [os.path.join(CSRC, f) for f in SOURCES] + ['-o', LIB], verbose, 'nvcc (libavb.so)')
     if force or _stale(HOST_EXT, [os.path.join(CSRC, 'avb_host.c'), LIB, os.path.abspath(__file__)]):
         inc = sysconfig.get_paths()['include']

@@ -210,14 +210,15 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(dalloc(c, &d.t_p0, S * NM));
     CKC(dalloc(c, &d.t_p1, S * NM));
     CKC(dalloc(c, &d.t_cell, S * NM));
+    CKC(dalloc(c, &d.t_und, S * NM));
+    CKC(dalloc(c, &d.c_und, S * NM));
     CKC(dalloc(c, &d.c_key, S * NM));
     CKC(dalloc(c, &d.c_src, S * NM));
     CKC(dalloc(c, &d.c_p1, S * NM));
     CKC(dalloc(c, &d.c_ok, S * NM));
     CKC(dalloc(c, &d.c_count, S * NC));
     CKC(dalloc(c, &d.n_new, S * NC));
-    CKC(dalloc(c, &d.new_rank, S * NM));
-    CKC(dalloc(c, &d.next_id, S));
+    CKC(dalloc(c, &d.next_id, 2 * S));
     CKC(dalloc(c, &d.counters, S * 8));
     CKC(dalloc(c, &d.frame_index, S));
     if (g.ransac) {
@@ -331,7 +332,7 @@ extern "C" int avb_reset(avb_ctx* c) {
     CK(cudaStreamSynchronize(c->st));
     const Geom& g = c->g;
     for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(c->d.grid[p].count, 0, (size_t)g.S * g.NC * sizeof(int), c->st));
-    CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)g.S * sizeof(long long), c->st));
+    CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)2 * g.S * sizeof(long long), c->st));
     CK(cudaMemsetAsync(c->d.frame_index, 0, (size_t)g.S * sizeof(int), c->st));
     CK(cudaStreamSynchronize(c->st));
     c->parity = 1;

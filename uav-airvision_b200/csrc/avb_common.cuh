@@ -103,15 +103,16 @@ struct DevState {
     float2* t_p0;                  // [S][NMAX] tracked cam0 position in the current frame
     float2* t_p1;                  // [S][NMAX]
     int* t_cell;                   // [S][NMAX] new cell, -1 = lost
+    double4* t_und;                // [S][NMAX] normalized coordinates (u0 v0 u1 v1) of the tracked feature
     // new-feature candidates, [cell][gmax], in descending key order
     unsigned* c_key;               // [S][NMAX]
     int* c_src;                    // [S][NMAX] index into the cell's FAST bucket
     float2* c_p1;                  // [S][NMAX]
     uint8_t* c_ok;                 // [S][NMAX]
+    double4* c_und;                // [S][NMAX] normalized coordinates of the candidate (valid when c_ok)
     int* c_count;                  // [S][NC]
     int* n_new;                    // [S][NC]  new features given ids this frame (before pruning)
-    uint8_t* new_rank;             // [S][NMAX] rank of a fresh feature among its cell's new ones
-    long long* next_id;            // [S]
+    long long* next_id;            // [2 parities][S]: read from the previous frame's parity, written to this frame's
     int* counters;                 // [S][8]: before_tracking, after_tracking, after_matching, n_fast, n_cand, after_ransac
     // two-point RANSAC scratch, [2 cams][S][NMAX] (allocated only when Geom::ransac)
     int* r_idx;

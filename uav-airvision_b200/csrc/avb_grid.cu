@@ -6,6 +6,8 @@
 //                  + FeaturePublisher.publish (feature_publisher.py:90-121), one CTA per stream
 // Every ranking is max-by-key: key = (response << 24 | inverted scan index) reproduces Python's stable
 // sorted(..., reverse=True) over detections in scan order (B9); lifetime ranking is stable by list position.
+#include <algorithm>
+
 #include "avb_lk.cuh"
 
 __global__ void k_clear_frame(Geom g, DevState d) {
@@ -149,7 +151,7 @@ int avb_set_smem_limits(size_t select_bytes, size_t grid_bytes) {
     cudaError_t e = cudaSuccess;
     if (select_bytes > 48 * 1024)
         e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_bytes);
-    if (e == cudaSuccess && grid_bytes > 48 * 1024)
+    if (e == cudaSuccess && grid_bytes > 16 * 1024)      // k_finish also holds ~29 KB of static shared memory
         e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_bytes);
     return e == cudaSuccess ? 0 : -1;
 }
@@ -160,13 +162,18 @@ void launch_select(const Geom& g, const DevState& d, int parity, int first_frame
 }
 
 // k_finish: one 1024-thread CTA per stream closes the frame.
-//   phase 1  stable counting sort of the tracked survivors by their new cell, in the previous frame's flattened grid
-//            order (feature_tracker.py:139-155, B16)
-//   phase 2  one warp per cell: append the first `gmin` stereo inliers of the cell's candidate list
-//            (feature_adder.py:102-108, B8), prune to `gmax` by lifetime with a stable rank (feature_pruner.py:13-19, B9)
-//   phase 3  exclusive scans over the cells -> ids in cell-major order (B10); one thread per (feature, camera) undistorts
-//            to normalized coordinates with that camera's model and fills the packed result block
-//            (feature_publisher.py:90-121; dtype quirk B11)
+//   phase 1  per-cell survivor histogram (tracked features by their NEW cell) and per-cell count of new features
+//            (the first `gmin` stereo inliers of the cell's candidate list, feature_adder.py:102-108, B8).  Everything
+//            phase 3 needs to know about OTHER cells follows from these two numbers per cell: final count
+//            min(nt + nn, gmax), id offsets (B10), and whether the frame holds fresh features (dtype quirk B11).
+//   phase 2  exclusive scans over the cells
+//   phase 3  one warp per cell, one lane per output slot: stable placement of the survivors in the previous frame's
+//            flattened grid order (feature_tracker.py:139-155, B16), append the new features, prune to `gmax` by
+//            lifetime with a stable rank (feature_pruner.py:13-19, B9), then straight from registers: id assignment,
+//            undistortion with the owning camera's model and the packed result block
+//            (feature_publisher.py:90-121) plus the grid table of the new frame.
+// The global loads of a phase are independent of each other (one memory round trip per phase); the values a slot
+// needs travel in registers from the gather to the result block.
 // Dynamic smem: cellof[NMAX] | seg[NMAX] | slife[NMAX] (int).
 #define FIN_THREADS 1024
 __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ Geom g, const __grid_constant__ DevState d, int parity,
@@ -174,192 +181,251 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
     extern __shared__ int smem_i32[];
     int* cellof = smem_i32;
     int* seg = smem_i32 + g.NMAX;
-    int* slife = smem_i32 + 2 * g.NMAX;
-    __shared__ int cnt[AVB_MAX_CELLS + 1];      // survivors per cell, then the cell's final feature count
+    int* slife = smem_i32 + 2 * g.NMAX;         // lifetime by table slot
+    __shared__ int cnt[AVB_MAX_CELLS + 1];      // tracked survivors per (new) cell
+    __shared__ int nnew[AVB_MAX_CELLS + 1];     // new features of the cell (before pruning)
     __shared__ int off[AVB_MAX_CELLS + 1];      // segment start of a cell in seg[]
     __shared__ int off_cnt[AVB_MAX_CELLS + 1];  // exclusive scan of the final counts
     __shared__ int off_new[AVB_MAX_CELLS + 1];  // exclusive scan of the new-feature counts
-    __shared__ int nnew[AVB_MAX_CELLS];
+    __shared__ unsigned cmask[AVB_MAX_CELLS];   // stereo inliers among the cell's candidates (bit = list position)
+    __shared__ int s_fresh;                     // any new feature survives pruning
+    __shared__ int route[FIN_THREADS / 32][32];
 
     pdl_wait();
     pdl_launch_dependents();
+#ifdef AVB_DEBUG_CLOCKS
+    long long dbg_t[5];
+    dbg_t[0] = clock64();
+#endif
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const GridTable prev = d.grid[parity ^ 1], cur = d.grid[parity];
     const size_t base = (size_t)s * g.NMAX;
 
     for (int c = tid; c <= g.NC; c += FIN_THREADS) cnt[c] = 0;
+    if (tid == 0) s_fresh = 0;
     __syncthreads();
     for (int i = tid; i < g.NMAX; i += FIN_THREADS) {
         const int c = first_frame ? -1 : d.t_cell[base + i];
+        const int li = first_frame ? 0 : prev.life[base + i];
         cellof[i] = c;
+        slife[i] = li;
         if (c >= 0) atomicAdd(&cnt[c], 1);
     }
-    __syncthreads();
-    if (warp == 0) {                    // exclusive scan of the survivor counts
-        int run = 0;
-        for (int b0 = 0; b0 < g.NC; b0 += 32) {
-            const int c = b0 + lane;
-            const int v = c < g.NC ? cnt[c] : 0;
-            int inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (c < g.NC) off[c] = run + inc - v;
-            run += __shfl_sync(0xffffffffu, inc, 31);
+    for (int c = warp; c < g.NC; c += FIN_THREADS / 32) {       // new features per cell
+        const int nc = d.c_count[s * g.NC + c];                 // both loads in flight together: c_ok past the count is
+        const uint8_t okv = lane < g.gmax ? d.c_ok[base + c * g.gmax + lane] : 0;     // stale but masked
+        const unsigned bn = __ballot_sync(0xffffffffu, lane < nc && okv);
+        if (lane == 0) {
+            nnew[c] = min(__popc(bn), g.gmin);
+            cmask[c] = bn;
         }
     }
     __syncthreads();
+#ifdef AVB_DEBUG_CLOCKS
+    dbg_t[1] = clock64();
+#endif
+    if (warp == 0) {                    // exclusive scans over the cells
+        int run_s = 0, run_c = 0, run_n = 0, fresh = 0;
+        for (int b0 = 0; b0 < g.NC; b0 += 32) {
+            const int c = b0 + lane;
+            const int vs = c < g.NC ? cnt[c] : 0;
+            const int vn = c < g.NC ? nnew[c] : 0;
+            const int vc = min(vs + vn, g.gmax);
+            fresh |= (vn > 0 && vs < g.gmax) ? 1 : 0;           // a lifetime-1 feature ranks after every tracked one
+            int is = vs, ic = vc, in = vn;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ts = __shfl_up_sync(0xffffffffu, is, o), tc = __shfl_up_sync(0xffffffffu, ic, o),
+                          tn = __shfl_up_sync(0xffffffffu, in, o);
+                if (lane >= o) {
+                    is += ts;
+                    ic += tc;
+                    in += tn;
+                }
+            }
+            if (c < g.NC) {
+                off[c] = run_s + is - vs;
+                off_cnt[c] = run_c + ic - vc;
+                off_new[c] = run_n + in - vn;
+            }
+            run_s += __shfl_sync(0xffffffffu, is, 31);
+            run_c += __shfl_sync(0xffffffffu, ic, 31);
+            run_n += __shfl_sync(0xffffffffu, in, 31);
+        }
+        fresh = __any_sync(0xffffffffu, fresh);
+        if (lane == 0) {
+            off_cnt[g.NC] = run_c;
+            off_new[g.NC] = run_n;
+            s_fresh = fresh;
+        }
+    }
+    __syncthreads();
+    const int total = off_cnt[g.NC], total_new = off_new[g.NC], has_new = s_fresh;
+    uint8_t* ob = d.out + (size_t)s * out_stride_bytes(g.NMAX);
+    const long long next_id = d.next_id[(parity ^ 1) * g.S + s];
+#ifdef AVB_DEBUG_CLOCKS
+    dbg_t[2] = clock64();
+#endif
 
-    for (int c = warp; c < g.NC; c += FIN_THREADS / 32) {
-        const int nt = cnt[c], o0 = off[c];
+    // the cells are dealt out to the CTAs of the stream (gridDim.y), one warp each; phases 1-2 are cheap and repeated
+    // by every CTA so that no inter-CTA synchronisation exists
+    for (int c = blockIdx.y * (FIN_THREADS / 32) + warp; c < g.NC; c += gridDim.y * (FIN_THREADS / 32)) {
+        const int nt = cnt[c], o0 = off[c], nn = nnew[c];
+        // candidate side first: its loads do not depend on the placement below
+        const size_t cb = base + (size_t)c * g.gmax;
+        const unsigned bn = cmask[c];
+        const bool okj = (bn >> lane) & 1u;
+        const int nrank = __popc(bn & lt);
+        const bool is_new = okj && nrank < g.gmin;
+        unsigned ckey = 0;
+        float2 cp1 = make_float2(0.f, 0.f);
+        if (is_new) {
+            ckey = d.c_key[cb + lane];
+            cp1 = d.c_p1[cb + lane];
+        }
+#ifdef AVB_DEBUG_CLOCKS
+        long long q0 = clock64(), q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+#endif
         if (nt) {                       // stable placement: survivors of this cell in table order
             int placed = 0;
             for (int b0 = 0; b0 < g.NMAX && placed < nt; b0 += 32) {
                 const int wi = b0 + lane;
                 const bool v = wi < g.NMAX && cellof[wi] == c;
                 const unsigned b = __ballot_sync(0xffffffffu, v);
-                if (v) {
-                    const int pos = o0 + placed + __popc(b & lt);
-                    seg[pos] = wi;
-                    slife[pos] = prev.life[base + wi];
-                }
+                if (v) seg[o0 + placed + __popc(b & lt)] = wi;
                 placed += __popc(b);
             }
         }
-        // new features: the first `gmin` stereo inliers of the candidate list (already in descending key order)
-        const int nc = d.c_count[s * g.NC + c];
-        const bool okj = lane < nc && d.c_ok[base + c * g.gmax + lane];
-        const unsigned bn = __ballot_sync(0xffffffffu, okj);
-        const int nrank = __popc(bn & lt);
-        const bool is_new = okj && nrank < g.gmin;
-        const int nn = min(__popc(bn), g.gmin);
-        const int total = nt + nn;
-        const bool prune = total > g.gmax;
         __syncwarp();
+        const int total_c = nt + nn, fc = min(total_c, g.gmax);
+        const bool prune = total_c > g.gmax;
 
-        const size_t obase = base + (size_t)c * g.gmax;
-        for (int i = lane; i < nt; i += 32) {
+        // where does each source land?  tracked survivor i -> pos (rank by lifetime when pruning), new feature -> nt + nrank
+        // gmax <= 32: one lane per output slot; sources are routed through shared memory (tracked) or shuffles (new)
+#ifdef AVB_DEBUG_CLOCKS
+        q1 = clock64();
+#endif
+        route[warp][lane] = -1;         // output slot -> table slot of the tracked feature that lands there
+        __syncwarp();
+        for (int i0 = 0; i0 < nt; i0 += 32) {
+            const int i = i0 + lane;
+            const int wi = i < nt ? seg[o0 + i] : 0;
+            const int li = i < nt ? slife[wi] : 0;
             int pos = i;
-            const int li = slife[o0 + i];
             if (prune) {                // stable sort by lifetime, descending (feature_pruner.py:18)
                 int rank = 0;
-                for (int j = 0; j < nt; ++j) {
-                    const int lj = slife[o0 + j];
-                    rank += (lj > li) || (lj == li && j < i);
+                if (nt <= 32) {         // the usual case: lifetimes travel by shuffle
+                    for (int j = 0; j < nt; ++j) {
+                        const int lj = __shfl_sync(0xffffffffu, li, j);
+                        rank += (lj > li) || (lj == li && j < i);
+                    }
+                } else {
+                    for (int j = 0; j < nt; ++j) {
+                        const int lj = slife[seg[o0 + j]];
+                        rank += (lj > li) || (lj == li && j < i);
+                    }
                 }
                 pos = rank;
             }
-            if (pos < g.gmax) {
-                const int wi = seg[o0 + i];
-                cur.ids[obase + pos] = prev.ids[base + wi];
-                cur.life[obase + pos] = li + 1;
-                cur.p0[obase + pos] = d.t_p0[base + wi];
-                cur.p1[obase + pos] = d.t_p1[base + wi];
-                cur.fresh[obase + pos] = 0;
-            }
-        }
-        if (is_new) {                   // lifetime 1 ranks after every tracked feature (lifetime >= 2)
-            const int pos = nt + nrank;
-            if (pos < g.gmax) {
-                int resp, x, y;
-                kp_decode(d.c_key[base + c * g.gmax + lane], g.W, resp, x, y);
-                cur.ids[obase + pos] = -1;
-                cur.life[obase + pos] = 1;
-                cur.p0[obase + pos] = make_float2((float)x, (float)y);
-                cur.p1[obase + pos] = d.c_p1[base + c * g.gmax + lane];
-                cur.fresh[obase + pos] = 1;
-                d.new_rank[obase + pos] = (uint8_t)nrank;
-            }
+            if (i < nt && pos < g.gmax) route[warp][pos] = wi;
         }
         __syncwarp();
-        if (lane == 0) {
-            const int fc = min(total, g.gmax);
-            cur.count[s * g.NC + c] = fc;
-            cnt[c] = fc;                // from here on: the cell's final count
-            nnew[c] = nn;
-        }
-    }
-    __syncthreads();
-
-    if (warp == 0) {                    // exclusive scans over the cells
-        int run_c = 0, run_n = 0;
-        for (int b0 = 0; b0 < g.NC; b0 += 32) {
-            const int c = b0 + lane;
-            const int vc = c < g.NC ? cnt[c] : 0;
-            const int vn = c < g.NC ? nnew[c] : 0;
-            int ic = vc, in = vn;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int tc = __shfl_up_sync(0xffffffffu, ic, o), tn = __shfl_up_sync(0xffffffffu, in, o);
-                if (lane >= o) {
-                    ic += tc;
-                    in += tn;
-                }
+        const int my_src = route[warp][lane];
+        // new features occupy slots nt + nrank (lifetime 1 ranks after every tracked feature, lifetime >= 2)
+        int new_from = -1;              // candidate lane whose feature lands in this output slot
+        {
+            const int want = lane - nt;                     // rank among the new ones this slot would hold
+            if (want >= 0 && want < nn && lane < g.gmax) {
+                // the lane with is_new and nrank == want: the (want+1)-th set bit of bn
+                unsigned m = bn;
+                for (int k = 0; k < want; ++k) m &= m - 1;
+                new_from = __ffs(m) - 1;
             }
-            if (c < g.NC) {
-                off_cnt[c] = run_c + ic - vc;
-                off_new[c] = run_n + in - vn;
-            }
-            run_c += __shfl_sync(0xffffffffu, ic, 31);
-            run_n += __shfl_sync(0xffffffffu, in, 31);
         }
-        if (lane == 0) {
-            off_cnt[g.NC] = run_c;
-            off_new[g.NC] = run_n;
-        }
-    }
-    __syncthreads();
-    const int total = off_cnt[g.NC], total_new = off_new[g.NC];
+        const unsigned key_in = __shfl_sync(0xffffffffu, ckey, new_from < 0 ? 0 : new_from);
+        const float cpx = __shfl_sync(0xffffffffu, cp1.x, new_from < 0 ? 0 : new_from);
+        const float cpy = __shfl_sync(0xffffffffu, cp1.y, new_from < 0 ? 0 : new_from);
 
-    int any_fresh = 0;
-    for (int i = tid; i < g.NMAX; i += FIN_THREADS) {
-        const int c = i / g.gmax, j = i - c * g.gmax;
-        if (j < cnt[c]) any_fresh |= cur.fresh[base + i];
-    }
-    const int has_new = __syncthreads_or(any_fresh);
-
-    uint8_t* ob = d.out + (size_t)s * out_stride_bytes(g.NMAX);
-    const long long next_id = d.next_id[s];
-    for (int w = tid; w < 2 * g.NMAX; w += FIN_THREADS) {
-        const int i = w >> 1, cam = w & 1;
-        const int c = i / g.gmax, j = i - c * g.gmax;
-        if (j >= cnt[c]) continue;
-        const int pos = off_cnt[c] + j;
-        double* m = out_meas(ob, g.NMAX) + 4 * pos;
-        if (cam == 0) {
-            long long id = cur.ids[base + i];
-            if (cur.fresh[base + i]) {
-                id = next_id + off_new[c] + d.new_rank[base + i];
-                cur.ids[base + i] = id;
+#ifdef AVB_DEBUG_CLOCKS
+        q2 = clock64();
+#endif
+        if (lane < fc) {
+            const size_t o = cb + lane;
+            const int pos = off_cnt[c] + lane;
+            long long id;
+            int life;
+            float2 p0, p1;
+            const bool fresh = my_src < 0;
+            double4 un = make_double4(0.0, 0.0, 0.0, 0.0);       // normalized coordinates precomputed by the LK kernels
+            if (!fresh) {
+                id = prev.ids[base + my_src];
+                life = slife[my_src] + 1;
+                p0 = d.t_p0[base + my_src];
+                p1 = d.t_p1[base + my_src];
+                un = d.t_und[base + my_src];
+            } else {
+                if (!first_frame) un = d.c_und[cb + new_from];
+                int resp, x, y;
+                kp_decode(key_in, g.W, resp, x, y);
+                id = next_id + off_new[c] + (lane - nt);    // ids in cell-major order (B10)
+                life = 1;
+                p0 = make_float2((float)x, (float)y);
+                p1 = make_float2(cpx, cpy);
             }
-            const float2 p0 = cur.p0[base + i];
-            double u0, v0;
-            undistort_pt(g.cam0, (double)p0.x, (double)p0.y, nullptr, u0, v0);
+            cur.ids[o] = id;
+            cur.life[o] = life;
+            cur.p0[o] = p0;
+            cur.p1[o] = p1;
+            cur.fresh[o] = fresh ? 1 : 0;
+#ifdef AVB_DEBUG_CLOCKS
+            q3 = clock64();
+#endif
+            double u0, v0, u1, v1;
+            if (first_frame) {          // frame 0 comes through k_stereo_buckets, which keeps no normalized coordinates
+                undistort_pt(g.cam0, (double)p0.x, (double)p0.y, nullptr, u0, v0);
+                undistort_pt(g.cam1, (double)p1.x, (double)p1.y, nullptr, u1, v1);
+            } else {                    // ChainResult::u0..v1
+                u0 = un.x;
+                v0 = un.y;
+                u1 = un.z;
+                v1 = un.w;
+            }
             if (!has_new) {             // all-float32 point list -> cv2 returns float32 (B11)
                 u0 = (double)(float)u0;
                 v0 = (double)(float)v0;
             }
+#ifdef AVB_DEBUG_CLOCKS
+            q4 = clock64();
+            if (tid == 0 && c == 0) {
+                d.counters[s * 8 + 6] = (int)(q0 - dbg_t[2]) | ((int)(q2 - q0) << 16);
+                dbg_t[3] = q4;
+            }
+#endif
+            double* m = out_meas(ob, g.NMAX) + 4 * pos;
             out_ids(ob)[pos] = id;
             m[0] = u0;
             m[1] = v0;
-            out_cell(ob, g.NMAX)[pos] = c;
-            out_life(ob, g.NMAX)[pos] = cur.life[base + i];
-            out_p0(ob, g.NMAX)[2 * pos] = p0.x;
-            out_p0(ob, g.NMAX)[2 * pos + 1] = p0.y;
-        } else {
-            const float2 p1 = cur.p1[base + i];
-            double u1, v1;
-            undistort_pt(g.cam1, (double)p1.x, (double)p1.y, nullptr, u1, v1);
             m[2] = (double)(float)u1;
             m[3] = (double)(float)v1;
+            out_cell(ob, g.NMAX)[pos] = c;
+            out_life(ob, g.NMAX)[pos] = life;
+            out_p0(ob, g.NMAX)[2 * pos] = p0.x;
+            out_p0(ob, g.NMAX)[2 * pos + 1] = p0.y;
             out_p1(ob, g.NMAX)[2 * pos] = p1.x;
             out_p1(ob, g.NMAX)[2 * pos + 1] = p1.y;
         }
+        if (lane == 0) cur.count[s * g.NC + c] = fc;
+#ifdef AVB_DEBUG_CLOCKS
+        if (tid == 0 && c == 0) d.counters[s * 8 + 7] = (int)(clock64() - dbg_t[3]) | ((int)(dbg_t[3] - q2) << 16);
+#endif
     }
-    if (tid == 0) {
+#ifdef AVB_DEBUG_CLOCKS
+    dbg_t[3] = clock64();
+    __syncthreads();
+    dbg_t[4] = clock64();
+#endif
+    if (tid == 0 && blockIdx.y == 0) {
         avb_frame_header* h = reinterpret_cast<avb_frame_header*>(ob);
         const int* cn = d.counters + s * 8;
         h->n_features = total;
@@ -372,11 +438,21 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
         h->n_fast = cn[3];
         h->n_candidates = cn[4];
         h->frame_index = d.frame_index[s];
-        d.next_id[s] = next_id + total_new;
+#ifdef AVB_DEBUG_CLOCKS                 // phase durations in SM cycles instead of the counters (debug builds only)
+        h->before_tracking = (int)(dbg_t[1] - dbg_t[0]);
+        h->after_tracking = (int)(dbg_t[2] - dbg_t[1]);
+        h->after_matching = (int)(dbg_t[3] - dbg_t[2]);
+        h->after_ransac = (int)(dbg_t[4] - dbg_t[3]);
+        h->n_fast = d.counters[s * 8 + 6];
+        h->n_candidates = d.counters[s * 8 + 7];
+#endif
+        d.next_id[parity * g.S + s] = next_id + total_new;
         d.frame_index[s] += 1;
     }
 }
 
 void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st) {
-    launch_k(k_finish, dim3(g.S), dim3(FIN_THREADS), (size_t)g.NMAX * 3 * sizeof(int), st, g_avb_pdl != 0, g, d, parity, first_frame);
+    const int per_cta = FIN_THREADS / 32;
+    const int nct = std::min((g.NC + per_cta - 1) / per_cta, 8);
+    launch_k(k_finish, dim3(g.S, nct), dim3(FIN_THREADS), (size_t)g.NMAX * 3 * sizeof(int), st, g_avb_pdl != 0, g, d, parity, first_frame);
 }

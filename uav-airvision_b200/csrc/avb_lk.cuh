@@ -545,6 +545,10 @@ struct ChainResult {
     bool matched;                   // stereo inlier
     float cx, cy;                   // cam0 position in the current frame
     float x1, y1;                   // cam1 position
+    double u0, v0, u1, v1;          // matched only: normalized coordinates as FeaturePublisher.publish undistorts them
+                                    // (cam0 point with the cam0 model, cam1 point with the cam1 model,
+                                    // feature_publisher.py:104-113), precomputed here where the work is spread over
+                                    // the whole GPU instead of the one CTA per stream of k_finish
 };
 
 template <int WPF>
@@ -565,6 +569,7 @@ __device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevSta
     r.cy = y;
     r.x1 = 0.f;
     r.y1 = 0.f;
+    r.u0 = r.v0 = r.u1 = r.v1 = 0.0;
     float projy = 0.f;
     float ax = x, ay = y, bx = gx, by = gy;
 #pragma unroll 1
@@ -619,6 +624,11 @@ __device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevSta
                 const double l1 = g.E[3] * u0x + g.E[4] * u0y + g.E[5];
                 const double epi = fabs(u1x * l0) / sqrt(l0 * l0 + l1 * l1);
                 ok = !(epi > g.epi_thr);
+                if (ok) {
+                    r.u0 = a0;
+                    r.v0 = b0;
+                    undistort_pt(g.cam1, (double)r.x1, (double)r.y1, nullptr, r.u1, r.v1);
+                }
             }
             r.matched = ok;
         }

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_trac
         d.t_p0[base + wi] = make_float2(r.cx, r.cy);
         d.t_p1[base + wi] = make_float2(r.x1, r.y1);
         d.t_cell[base + wi] = new_cell;
+        if (new_cell >= 0) d.t_und[base + wi] = make_double4(r.u0, r.v0, r.u1, r.v1);
     }
 }
 
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_ster
     if (lead) {
         d.c_p1[idx] = make_float2(r.x1, r.y1);
         d.c_ok[idx] = r.matched ? 1 : 0;
+        if (r.matched) d.c_und[idx] = make_double4(r.u0, r.v0, r.u1, r.v1);
     }
 }
 
