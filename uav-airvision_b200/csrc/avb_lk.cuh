@@ -616,19 +616,33 @@ __device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevSta
             bool ok = (err < 3.f) && (disp < 20.f);
             ok = ok && !(r.x1 < 0.f || r.x1 >= (float)g.W || r.y1 < 0.f || r.y1 >= (float)g.H);
             if (ok) {
-                double a0, b0, a1, b1;
-                undistort_pt(g.cam0, (double)r.cx, (double)r.cy, nullptr, a0, b0);
-                undistort_pt(g.cam0, (double)r.x1, (double)r.y1, nullptr, a1, b1);
+                // Three undistortions are due: (cx, cy) and (x1, y1) through the cam0 model for the epipolar test (B3)
+                // and (x1, y1) through the cam1 model for the publisher.  Lanes 0, 1, 2 take one each (one FP64
+                // chain for the warp instead of three), the results come back by shuffle.
+                const int l = threadIdx.x & 31;
+                const bool c1 = l == 2;
+                CamModel cm;
+                cm.fx = c1 ? g.cam1.fx : g.cam0.fx;
+                cm.fy = c1 ? g.cam1.fy : g.cam0.fy;
+                cm.cx = c1 ? g.cam1.cx : g.cam0.cx;
+                cm.cy = c1 ? g.cam1.cy : g.cam0.cy;
+                cm.k1 = c1 ? g.cam1.k1 : g.cam0.k1;
+                cm.k2 = c1 ? g.cam1.k2 : g.cam0.k2;
+                cm.p1 = c1 ? g.cam1.p1 : g.cam0.p1;
+                cm.p2 = c1 ? g.cam1.p2 : g.cam0.p2;
+                double ux, uy;
+                undistort_pt(cm, (double)(l == 0 ? r.cx : r.x1), (double)(l == 0 ? r.cy : r.y1), nullptr, ux, uy);
+                const double a0 = __shfl_sync(0xffffffffu, ux, 0), b0 = __shfl_sync(0xffffffffu, uy, 0);
+                const double a1 = __shfl_sync(0xffffffffu, ux, 1);
                 const double u0x = (double)(float)a0, u0y = (double)(float)b0, u1x = (double)(float)a1;
                 const double l0 = g.E[0] * u0x + g.E[1] * u0y + g.E[2];
                 const double l1 = g.E[3] * u0x + g.E[4] * u0y + g.E[5];
                 const double epi = fabs(u1x * l0) / sqrt(l0 * l0 + l1 * l1);
                 ok = !(epi > g.epi_thr);
-                if (ok) {
-                    r.u0 = a0;
-                    r.v0 = b0;
-                    undistort_pt(g.cam1, (double)r.x1, (double)r.y1, nullptr, r.u1, r.v1);
-                }
+                r.u0 = a0;
+                r.v0 = b0;
+                r.u1 = __shfl_sync(0xffffffffu, ux, 2);
+                r.v1 = __shfl_sync(0xffffffffu, uy, 2);
             }
             r.matched = ok;
         }
