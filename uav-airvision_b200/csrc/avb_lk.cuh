@@ -418,36 +418,53 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
         float cx = __fsub_rn(nx, (float)AVB_HALF), cy = __fsub_rn(ny, (float)AVB_HALF);
         float pdx = 0.f, pdy = 0.f;
         const uint8_t* imgB = pyr_level(B, g, level);
+        // window tests as single unsigned compares: in range <=> -WIN <= inx < cols; inside <=> 0 <= inx, inx + 16 < cols
+        const unsigned x_rng = (unsigned)(cols + AVB_WIN), y_rng = (unsigned)(rows + AVB_WIN);
+        const unsigned x_in = (unsigned)max(cols - 16, 0), y_in = (unsigned)max(rows - 16, 0);
+        const uint8_t* lane_base = imgB + L.row * pitch + L.c0;      // this lane's first sample for a window at (0, 0)
         for (int j = 0; j < prm.max_iter; ++j) {
             const int inx = __float2int_rd(cx), iny = __float2int_rd(cy);
-            if (inx < -AVB_WIN || inx >= cols || iny < -AVB_WIN || iny >= rows) {
+            if ((unsigned)(inx + AVB_WIN) >= x_rng || (unsigned)(iny + AVB_WIN) >= y_rng) {
                 if (level == 0) status = false;
                 break;
             }
             int sb1 = 0, sb2 = 0;
             if (L.npx) {
-                int cur[4], nxt[4];
-                if (inx >= 0 && inx + 16 < cols && iny >= 0 && iny + 16 < rows) {   // team-uniform: window inside the level
-                    const uint8_t* p = imgB + (iny + L.row) * pitch + (inx + L.c0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        cur[k] = __ldg(p + k);
-                        nxt[k] = __ldg(p + pitch + k);
-                    }
-                } else {
-                    load_row<4>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row, cur);
-                    load_row<4>(imgB, cols, rows, pitch, inx + L.c0, iny + L.row + 1, nxt);
+                // this lane's 4 bytes of window row L.row and of the row below it, packed little-endian
+                unsigned P, N;
+                if ((unsigned)inx < x_in && (unsigned)iny < y_in) {         // team-uniform: window inside the level
+                    // two aligned 32-bit loads per row + one funnel shift (rows are 16-byte aligned, so both rows share
+                    // the byte phase; the <= 3 bytes read past the sample stay inside the row pitch / padded allocation)
+                    const uint8_t* a = lane_base + iny * pitch + inx;
+                    const unsigned sh8 = ((unsigned)(size_t)a & 3u) * 8u;
+                    const unsigned* aw = reinterpret_cast<const unsigned*>((size_t)a & ~(size_t)3);
+                    const unsigned* bw = reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(aw) + pitch);
+                    const unsigned A0 = __ldg(aw), A1 = __ldg(aw + 1), B0 = __ldg(bw), B1 = __ldg(bw + 1);
+                    P = __funnelshift_r(A0, A1, sh8);
+                    N = __funnelshift_r(B0, B1, sh8);
+                } else {                                                     // REFLECT_101 on both axes
+                    const uint8_t* r0 = imgB + refl101(iny + L.row, rows) * pitch;
+                    const uint8_t* r1 = imgB + refl101(iny + L.row + 1, rows) * pitch;
+                    const int x0 = inx + L.c0;
+                    const int c0 = refl101(x0, cols), c1 = refl101(x0 + 1, cols), c2 = refl101(x0 + 2, cols),
+                              c3 = refl101(x0 + 3, cols);
+                    P = (unsigned)__ldg(r0 + c0) | ((unsigned)__ldg(r0 + c1) << 8) | ((unsigned)__ldg(r0 + c2) << 16) |
+                        ((unsigned)__ldg(r0 + c3) << 24);
+                    N = (unsigned)__ldg(r1 + c0) | ((unsigned)__ldg(r1 + c1) << 8) | ((unsigned)__ldg(r1 + c2) << 16) |
+                        ((unsigned)__ldg(r1 + c3) << 24);
                 }
                 int w00, w01, w10, w11;
                 lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int jv = (cur[k] * w00 + cur[k + 1] * w01 + nxt[k] * w10 + nxt[k + 1] * w11 + (1 << (LK_W_BITS - 6))) >>
-                                   (LK_W_BITS - 5);
-                    const int diff = jv - tI[k];
-                    sb1 += diff * tIx[k];
-                    sb2 += diff * tIy[k];
-                }
+                // bilinear sample k = w00 b_k + w01 b_{k+1} + w10 n_k + w11 n_{k+1} as two 2-way 16x8-bit dot products
+                const unsigned Wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16);
+                const unsigned Wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);     // w11 may be -1
+                const int rnd = 1 << (LK_W_BITS - 6);
+                const int j0 = dp2a_lo_su(Wt, P, dp2a_lo_su(Wb, N, rnd)) >> (LK_W_BITS - 5);
+                const int j1 = dp2a_lo_su(Wt, P >> 8, dp2a_lo_su(Wb, N >> 8, rnd)) >> (LK_W_BITS - 5);
+                const int j2 = dp2a_hi_su(Wt, P, dp2a_hi_su(Wb, N, rnd)) >> (LK_W_BITS - 5);
+                const int d0 = j0 - tI[0], d1 = j1 - tI[1], d2 = j2 - tI[2];
+                sb1 = d0 * tIx[0] + d1 * tIx[1] + d2 * tIx[2];
+                sb2 = d0 * tIy[0] + d1 * tIy[1] + d2 * tIy[2];
             }
             sb1 = __reduce_add_sync(0xffffffffu, sb1);
             sb2 = __reduce_add_sync(0xffffffffu, sb2);
