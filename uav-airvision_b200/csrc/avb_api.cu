@@ -22,6 +22,7 @@ struct avb_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     uint8_t* h_in = nullptr;        // pinned: one input block (images + H)
     uint8_t* h_out = nullptr;       // pinned: S result blocks
+    bool zc_out = false;            // k_finish writes the result blocks straight into h_out (mapped): no D2H copy node
     size_t out_stride = 0;
     int parity = 1;                 // parity of the current frame; the first frame lands in parity 0
     bool first_frame = true;
@@ -228,11 +229,22 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
         CKC(dalloc(c, &d.r_bits, 2 * S * NM));
     }
     c->out_stride = out_stride_bytes(g.NMAX);
-    CKC(dalloc(c, &d.out, S * c->out_stride));
-    CKC(cudaHostAlloc((void**)&c->h_in, inb, cudaHostAllocDefault));
-    CKC(cudaHostAlloc((void**)&c->h_out, S * c->out_stride, cudaHostAllocDefault));
-    memset(c->h_in, 0, inb);
+    // A small result (one or a few streams) is written by k_finish directly into mapped pinned host memory: the posted
+    // PCIe writes overlap the kernel's tail and the D2H copy node (launch + completion latency of a DMA for ~19 kB)
+    // disappears from the frame.  Many streams: one bulk DMA of the device mirror is cheaper than scattered stores.
+    c->zc_out = S * c->out_stride <= (size_t)64 * 1024;
+    if (const char* e = getenv("AVB_ZC_OUT")) c->zc_out = atoi(e) != 0;
+    CKC(cudaHostAlloc((void**)&c->h_out, S * c->out_stride, cudaHostAllocMapped));
     memset(c->h_out, 0, S * c->out_stride);
+    if (c->zc_out) {
+        void* dp = nullptr;
+        CKC(cudaHostGetDevicePointer(&dp, c->h_out, 0));
+        d.out = static_cast<uint8_t*>(dp);
+    } else {
+        CKC(dalloc(c, &d.out, S * c->out_stride));
+    }
+    CKC(cudaHostAlloc((void**)&c->h_in, inb, cudaHostAllocDefault));
+    memset(c->h_in, 0, inb);
     avb_fill_rotations(c, c->h_in, nullptr, nullptr);      // identity until the caller provides rotations
 
     // dynamic shared memory of the bookkeeping kernels
@@ -399,7 +411,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     launch_finish(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[7], c->st));
     CK(cudaEventRecord(ev[8], c->st));
-    CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+    if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev[9], c->st));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
@@ -426,7 +438,7 @@ static int build_graphs(avb_ctx* c) {
             if (variant == 0)   // device variant: the block was placed by a D2D copy ordered before the launch
                 cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st);
             enqueue_chain(c, p, false);
-            cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
+            if (!c->zc_out) cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
             CK(cudaStreamEndCapture(c->st, &graph));
             cudaGraphExec_t exec = nullptr;
             CK(cudaGraphInstantiate(&exec, graph, 0));
@@ -489,7 +501,7 @@ static int run_frame(avb_ctx* c, int variant, bool wait) {
     } else {
         if (variant == 0) CK(cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st));
         enqueue_chain(c, p, c->first_frame);
-        CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+        if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev_t1, c->st));
