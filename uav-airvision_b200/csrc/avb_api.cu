@@ -425,7 +425,8 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
     // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
-    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0);
+    // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish
+    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + ((c->g.wpf == 1 && c->g.gmin < c->g.gmax) ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {

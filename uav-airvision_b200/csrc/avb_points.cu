@@ -56,19 +56,32 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_trac
 }
 
 // stereo_match of the new-feature candidates (feature_adder.py:79-80)
+// round < 0: every candidate in one launch (latency mode).  Throughput mode splits the work: the adder keeps only the
+// first `gmin` stereo inliers of a cell's list (feature_adder.py:102-108, B8), so round 0 matches list positions
+// < gmin and round 1 the rest, and only in cells where round 0 left a deficit (a position that failed or a list
+// shorter than it looks) -- typically a few percent of the cells.  Unmatched tail positions keep a stale c_ok, which
+// cannot matter: with gmin inliers ahead of them they rank >= gmin and are never adopted nor counted.
 template <int WPF>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_stereo_candidates(const __grid_constant__ Geom g,
-                                                                            const __grid_constant__ DevState d, int parity) {
+                                                                            const __grid_constant__ DevState d, int parity,
+                                                                            int round) {
     __shared__ LKShared sh;
     pdl_wait();
     pdl_launch_dependents();
     const int s = blockIdx.y;
-    const int wi = team_index<WPF>(blockIdx.x);
+    const int t = team_index<WPF>(blockIdx.x);              // teams are dealt densely over the positions of this round
     const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
-    if (wi >= g.NMAX) return;
-    const int cell = wi / g.gmax, j = wi - cell * g.gmax;
+    const int per_cell = round < 0 ? g.gmax : (round == 0 ? g.gmin : g.gmax - g.gmin);
+    if (t >= g.NC * per_cell) return;
+    const int cell = t / per_cell, j = t - cell * per_cell + (round == 1 ? g.gmin : 0);
     if (j >= d.c_count[s * g.NC + cell]) return;
+    const int wi = cell * g.gmax + j;
     const size_t idx = (size_t)s * g.NMAX + wi;
+    if (round == 1) {
+        int inl = 0;
+        for (int k = 0; k < g.gmin; ++k) inl += d.c_ok[idx - j + k];   // count > j >= gmin: all gmin positions were matched
+        if (inl == g.gmin) return;
+    }
     int resp, x, y;
     kp_decode(d.c_key[idx], g.W, resp, x, y);
     const ChainResult r = feature_chain<WPF>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, &sh);
@@ -171,10 +184,16 @@ void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st)
 }
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
-    if (g.wpf == 1)
-        launch_k(k_stereo_candidates<1>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
-    else
-        launch_k(k_stereo_candidates<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+    if (g.wpf == 1 && g.gmin < g.gmax) {
+        launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * g.gmin, 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0,
+                 g, d, parity, 0);
+        launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * (g.gmax - g.gmin), 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st,
+                 g_avb_pdl != 0, g, d, parity, 1);
+    } else if (g.wpf == 1) {
+        launch_k(k_stereo_candidates<1>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity, -1);
+    } else {
+        launch_k(k_stereo_candidates<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity, -1);
+    }
 }
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid((g.KPC + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.NC, g.S);
