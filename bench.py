@@ -415,6 +415,11 @@ def main():
         bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nfeat)
         chain_ms = dev_ms / K
         achieved = bpf / (chain_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None                 # measured DRAM bytes of one frame chain (ncu --set full capture)
+        tpath = os.path.join(ROOT, 'profiles', f'roofline_traffic_{args.workload}.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = float(tj['bytes_per_frame']), f"profiles/{os.path.basename(tpath)} ({tj.get('note', '')})"
         kernel_stages = {k_: v for k_, v in stage_ms.items() if k_ not in ('input_copy', 'result_copy')}
         dominant = max(kernel_stages, key=kernel_stages.get)
         line = {
@@ -439,7 +444,7 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': f'frame chain ({kernels_per_frame} kernels, one CUDA graph); '
                                                    f'dominant stage by time: {dominant}',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bpf,
                          'stage_ms_serialised': {k_: round(v, 4) for k_, v in stage_ms.items()},
                          'note': 'single stream = latency-bound dependent chain; see multi_stream for the '

@@ -29,5 +29,6 @@ if [[ $what == all || $what == ncu ]]; then
         -o $out/${tag}_s$S -f python tools/profile_target.py --streams $S --frames 5 > $out/${tag}_ncu_s$S.log 2>&1
     ncu -i $out/${tag}_s$S.ncu-rep --page raw --csv > $out/${tag}_s$S.raw.csv 2>/dev/null
   done
+  python tools/ncu_summary.py traffic $out/${tag}_s1.raw.csv > $out/${tag}_roofline_traffic_c2.json
 fi
 ls -la $out | tail -20

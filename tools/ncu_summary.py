@@ -85,5 +85,36 @@ def raw(path):
         print(f'| {k} | {len(rs)} | ' + ' | '.join(cells) + ' |')
 
 
+def traffic(path):
+    """DRAM bytes (read + write) of ONE steady-state frame chain from a --set full capture: every kernel name once
+    (k_pyr_down / k_stereo_candidates may launch more than once per frame: their launches inside one frame are summed
+    by dividing the capture's total by the number of frames it covers = launches of k_finish)."""
+    import json
+    with open(path, newline='') as f:
+        rd = csv.reader(f)
+        hdr = next(rd)
+        units = next(rd)
+        col = {h: i for i, h in enumerate(hdr)}
+        per = defaultdict(lambda: [0, 0.0])
+        for r in rd:
+            if len(r) != len(hdr):
+                continue
+            name = short(r[col['Kernel Name']])
+            tot = 0.0
+            for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                v = float(r[col[m]].replace(',', ''))
+                u = units[col[m]].lower()
+                tot += v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
+            per[name][0] += 1
+            per[name][1] += tot
+    frames = max(per.get('k_finish', [1])[0], 1)
+    out = {'frames_in_capture': frames, 'source': path,
+           'per_kernel_bytes_per_frame': {k: v[1] / frames for k, v in per.items() if not k.startswith('k_stereo_buckets')},
+           'note': 'ncu --set full replays every kernel with flushed caches: cold-cache DRAM traffic, an upper bound on the '
+                   'traffic of the warm chain'}
+    out['bytes_per_frame'] = sum(out['per_kernel_bytes_per_frame'].values())
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'raw': raw}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'raw': raw, 'traffic': traffic}[sys.argv[1]](sys.argv[2])
