@@ -150,7 +150,10 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     g.fast_thr = cfg->fast_threshold;
     // LK lane mapping: few features in flight (one or a handful of streams) -> 4 warps per feature to shorten the
     // dependent chain; many -> 1 warp per feature for throughput.  AVB_WPF=1|4 overrides (experiments).
-    g.wpf = ((long long)g.S * g.NMAX <= 4736) ? 4 : 1;      // 4736 = 148 SMs x 32 resident teams
+    // Both LK kernels are latency-bound per feature, so what counts is the number of WAVES: the 4-warp mapping keeps
+    // 148 SMs x 4 CTAs = 592 teams resident (111 registers), the 1-warp mapping 148 x 32 = 4736.  Measured at C3 (2000
+    // slots, one stream): k_track 228 us with 4 warps (3.4 waves) vs 150 us with 1 warp (one wave).
+    g.wpf = ((long long)g.S * g.NMAX <= 592) ? 4 : 1;
     if (const char* e = getenv("AVB_WPF")) g.wpf = (atoi(e) == 4) ? 4 : 1;
     if (const char* e = getenv("AVB_PDL")) g_avb_pdl = atoi(e) ? 1 : 0;
     g.max_iter = std::min(std::max(cfg->max_iteration, 0), 100);
@@ -426,7 +429,7 @@ extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
     // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
     // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish
-    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + ((c->g.wpf == 1 && c->g.gmin < c->g.gmax) ? 1 : 0);
+    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (avb_candidate_rounds(c->g) == 2 ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {

@@ -214,6 +214,7 @@ void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, co
                           cudaStream_t st);
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+int  avb_candidate_rounds(const Geom& g);    // 1: every candidate in one launch; 2: positions < gmin first, the rest on demand
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st);

@@ -182,9 +182,15 @@ void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st)
     else
         launch_k(k_track<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
 }
+// Two rounds save ~40 % of the matching work but cost a second chain of latency: worth it only when the candidates
+// fill the GPU several times over (throughput-bound), not when they fit in a wave or two.
+int avb_candidate_rounds(const Geom& g) {
+    return (g.wpf == 1 && g.gmin < g.gmax && (long long)g.S * g.NMAX > 2 * 4736) ? 2 : 1;
+}
+
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
-    if (g.wpf == 1 && g.gmin < g.gmax) {
+    if (avb_candidate_rounds(g) == 2) {
         launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * g.gmin, 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0,
                  g, d, parity, 0);
         launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * (g.gmax - g.gmin), 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st,
