@@ -198,7 +198,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=['c2', 'c3'])
-    ap.add_argument('--streams', type=int, default=64, help='streams per GPU of the extra multi-stream leg (0 = skip)')
+    ap.add_argument('--streams', type=int, default=64,
+                    help='total streams of the extra multi-stream leg (config C4), sharded over the GPUs (0 = skip)')
     ap.add_argument('--ms-steps', type=int, default=20)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
@@ -244,7 +245,9 @@ def main():
     skw = dict(skw, seed=skw['seed'] + rank)              # every rank owns its own stream
     W, K = args.warmup, args.steps
     n_prof = 12
-    n_extra = (2 * (args.streams - 1) + 4 + 1 + args.ms_steps + 2) if args.streams > 0 else 0
+    # multi-stream leg = BASELINE config C4: `--streams` (64) independent time-offset runs in total, sharded over the GPUs
+    S_ms = max(1, args.streams // world) if args.streams > 0 else 0
+    n_extra = (2 * (S_ms - 1) + 4 + 1 + args.ms_steps + 2) if S_ms > 0 else 0
     n = max(W + K + 1 + n_prof, n_extra)
     stream = make_sequence(skw, n)
     frames = [stream.frame(k) for k in range(n)]
@@ -346,8 +349,8 @@ def main():
 
     # ---- multi-stream leg: S time-offset runs of the same sequence per GPU (run.bat sweep shape) ---------------
     multi = None
-    if args.streams > 0:
-        S, KM, WM = args.streams, args.ms_steps, 4
+    if S_ms > 0:
+        S, KM, WM = S_ms, args.ms_steps, 4
         mctx = _native.Context(cfg, width, height, num_streams=S, device=local, use_graph=True)
         mbb = mctx.block_bytes
         rot_off = mctx.rot_offset
@@ -381,7 +384,8 @@ def main():
         mctx.close()
         bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nf / S)
         m_fps = world * S * KM / (m_ms * 1e-3)
-        multi = {'streams_per_gpu': S, 'steps': KM, 'value': m_fps, 'unit': UNIT, 'ms_per_step': m_ms / KM,
+        multi = {'config': f'C4: {S * world} independent time-offset runs sharded over {world} GPU(s)', 'streams_total': S * world,
+                 'streams_per_gpu': S, 'steps': KM, 'value': m_fps, 'unit': UNIT, 'ms_per_step': m_ms / KM,
                  'features_per_frame': nf / S, 'hbm_gbs': bpf * S * KM / (m_ms * 1e-3) / 1e9,
                  'stage_ms': {k_: round(v, 4) for k_, v in st.items()},
                  'note': 'S time-offset runs of the sequence (stream s starts 2*s frames in), lock-stepped in one '

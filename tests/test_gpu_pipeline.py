@@ -278,3 +278,65 @@ def test_both_lk_lane_mappings_match_reference_golden(wpf, golden_dir, monkeypat
     worst = _compare(frames, ref)
     print(f'AVB_WPF={wpf}: worst position deviation {worst:.3g} px')
     assert nid == int(g['next_feature_id'][0])
+
+
+def test_pipeline_vs_port_lossy_stream_30_frames():
+    """A stream that loses features on every frame (independently moving patches, heavy noise, fast drift + gyro): cells
+    empty and refill, pruning by lifetime kicks in, new ids are handed out every frame.  30 frames equal the port."""
+    cfg = FrontEndConfig(grid_row=6, grid_col=10)
+    kw = dict(n_frames=30, seed=5, sigma=2.0, drift=(2.2, -1.4), gyro=(0.02, 0.01, -0.03), noise=2.5,
+              movers=[(200, 150, 40, -3.0, 4.0), (520, 300, 50, 5.0, -2.5), (380, 240, 30, -6.0, -5.0)])
+    ref, ref_nid = _port_frames(cfg, SlidingTextureStream(**kw))
+    msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**kw))
+    worst = _compare(frames, ref)
+    lost = sum(f['counters'].get('after_tracking', 0) - f['counters'].get('after_matching', 0) for f in frames[1:])
+    print(f'lossy stream: 30 frames equal the port (worst {worst:.3g} px); {lost} features lost in stereo matching, '
+          f'{nid} ids handed out')
+    assert nid == ref_nid and lost > 0
+
+
+def test_maximum_capacity_context_matches_port():
+    """The largest table the library accepts: 16 x 16 cells x 32 slots = 8192 features per stream (AVB_MAX_CAP slots per
+    cell, NMAX limit), 1280x1024, RANSAC on: exercises the eight-CTA k_finish, the one-warp LK mapping on a single
+    stream and k_ransac's strided passes.  Three frames against the port."""
+    cfg = FrontEndConfig(grid_row=16, grid_col=16, grid_min=16, grid_max=32, pyramid_levels=4, width=1280, height=1024,
+                         two_point_ransac=True)
+    kw = dict(width=1280, height=1024, n_frames=3, seed=3, sigma=1.6, drift=(1.1, 0.8), movers=[(600, 500, 90, 4.0, 3.0)])
+    ref, ref_nid = _port_frames(cfg, SlidingTextureStream(**kw))
+    msgs, frames, nid = _run_gpu(cfg, SlidingTextureStream(**kw))
+    worst = _compare(frames, ref)
+    print(f'max capacity: features/frame {[len(f["ids"]) for f in frames]}, worst {worst:.3g} px')
+    assert nid == ref_nid
+    assert len(frames[-1]['ids']) > 3000
+
+
+def test_multi_stream_with_ransac_equals_single_pipelines():
+    """RANSAC draws are keyed by each stream's own frame index and both camera rotations travel per stream: S streams
+    in one context (process_frames, (2, S, 3, 3) rotations) publish what S separate pipelines publish."""
+    from image_processing import ImageProcessor
+    from multi_stream import MultiStreamFrontEnd, replay
+    cfg = FrontEndConfig(grid_row=5, grid_col=6, two_point_ransac=True, ransac_seed=11)
+    kws = [dict(n_frames=7, seed=40 + s, sigma=2.0 + 0.3 * s, drift=(1.2 + 0.3 * s, -0.6), gyro=(0.01 * s, -0.02, 0.02),
+                noise=0.5, movers=[(250 + 60 * s, 200, 40, 4.0, -3.0 + s)]) for s in range(3)]
+    singles, dropped = [], 0
+    for kw in kws:
+        ip = ImageProcessor(cfg)
+        out = []
+
+        def on_frame(k, msg, fm, ip=ip, out=out):
+            nonlocal dropped
+            out.append(fm)
+            if k:
+                dropped += ip.num_features['after_matching'] - ip.num_features['after_ransac']
+
+        run_stream(ip, SlidingTextureStream(**kw), on_frame=on_frame)
+        singles.append(out)
+        ip.context.close()
+    fe = MultiStreamFrontEnd(cfg, 752, 480, 3)
+    multi = replay(fe, [SlidingTextureStream(**kw) for kw in kws])
+    for s in range(3):
+        for a, b in zip(multi[s], singles[s]):
+            assert [(f.id, f.u0, f.v0, f.u1, f.v1) for f in a.features] == [(f.id, f.u0, f.v0, f.u1, f.v1) for f in b.features]
+    fe.close()
+    print(f'multi-stream + RANSAC: 3 streams x 7 frames identical to single pipelines; {dropped} features rejected by RANSAC')
+    assert dropped > 0
