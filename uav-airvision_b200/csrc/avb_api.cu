@@ -151,7 +151,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     // LK lane mapping: few features in flight (one or a handful of streams) -> 4 warps per feature to shorten the
     // dependent chain; many -> 1 warp per feature for throughput.  AVB_WPF=1|4 overrides (experiments).
     // Both LK kernels are latency-bound per feature, so what counts is the number of WAVES: the 4-warp mapping keeps
-    // 148 SMs x 4 CTAs = 592 teams resident (111 registers), the 1-warp mapping 148 x 32 = 4736.  Measured at C3 (2000
+    // 148 SMs x 4 CTAs = 592 teams resident (~120 registers), the 1-warp mapping 148 x 20 = 2960 (96 registers).  Measured at C3 (2000
     // slots, one stream): k_track 228 us with 4 warps (3.4 waves) vs 150 us with 1 warp (one wave).
     g.wpf = ((long long)g.S * g.NMAX <= 592) ? 4 : 1;
     if (const char* e = getenv("AVB_WPF")) g.wpf = (atoi(e) == 4) ? 4 : 1;

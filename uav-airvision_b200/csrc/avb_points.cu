@@ -4,6 +4,11 @@
 #include "avb_lk.cuh"
 
 #define WARPS_PER_BLOCK 4
+#ifndef AVB_WPF1_BLOCKS
+#define AVB_WPF1_BLOCKS 5            // resident CTAs per SM the 1-warp LK kernels are compiled for: 96 registers, no
+                                     // spills.  Measured at 64 streams (frames/s): 8 CTAs (64 regs, 244 B spilled)
+                                     // 50,981; 6 (80 regs) 52,243; 5 (96 regs) 53,253; 4 (127 regs) 52,544
+#endif
 
 // Team decomposition of a 128-thread block: WPF = 1 -> four features per block (one warp each), WPF = 4 -> one
 // feature per block.  Returns the feature index; `sh` points at the team's shared scratch.
@@ -15,7 +20,7 @@ __device__ __forceinline__ int team_index(int bx) {
 // FeatureTracker.track_features, steps 3-8 (feature_tracker.py:85-133) for every previous feature:
 // gyro prediction (K R K^-1) -> temporal LK -> image-bounds cull (> W-1 rule, B6) -> stereo match.
 template <int WPF>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_track(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOCKS : 4) k_track(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
                                                                 int parity) {
     __shared__ LKShared sh;
     pdl_wait();
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_trac
 // shorter than it looks) -- typically a few percent of the cells.  Unmatched tail positions keep a stale c_ok, which
 // cannot matter: with gmin inliers ahead of them they rank >= gmin and are never adopted nor counted.
 template <int WPF>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? 8 : 4) k_stereo_candidates(const __grid_constant__ Geom g,
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOCKS : 4) k_stereo_candidates(const __grid_constant__ Geom g,
                                                                             const __grid_constant__ DevState d, int parity,
                                                                             int round) {
     __shared__ LKShared sh;
@@ -185,7 +190,7 @@ void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st)
 // Two rounds save ~40 % of the matching work but cost a second chain of latency: worth it only when the candidates
 // fill the GPU several times over (throughput-bound), not when they fit in a wave or two.
 int avb_candidate_rounds(const Geom& g) {
-    return (g.wpf == 1 && g.gmin < g.gmax && (long long)g.S * g.NMAX > 2 * 4736) ? 2 : 1;
+    return (g.wpf == 1 && g.gmin < g.gmax && (long long)g.S * g.NMAX > 2 * 148 * AVB_WPF1_BLOCKS * WARPS_PER_BLOCK) ? 2 : 1;
 }
 
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
