@@ -2,6 +2,7 @@
 
   lib/libavb.so                         nvcc, sm_100a: CUDA kernels + the C-ABI of include/avb.h
   image_processing/_avbhost.*.so        gcc: CPython extension, the per-frame host driver (csrc/avb_host.c)
+  _msckfhost.*.so                       gcc: CPython extension, scalar inner loops of the host MSCKF (csrc/msckf_host.c)
 
     python uav-airvision_b200/build.py [--force] [--verbose]
 """
@@ -16,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libavb.so')
 HOST_EXT = os.path.join(HERE, 'image_processing', '_avbhost' + sysconfig.get_config_var('EXT_SUFFIX'))
+MSCKF_EXT = os.path.join(HERE, '_msckfhost' + sysconfig.get_config_var('EXT_SUFFIX'))
 SOURCES = ['avb_api.cu', 'avb_pyramid.cu', 'avb_fast.cu', 'avb_points.cu', 'avb_grid.cu', 'avb_ransac.cu']
 HEADERS = ['avb_common.cuh', 'avb_lk.cuh', os.path.join('..', '..', 'include', 'avb.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -32,7 +34,8 @@ def _stale(target, deps) -> bool:
 
 def needs_build() -> bool:
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return _stale(LIB, deps) or _stale(HOST_EXT, [os.path.join(CSRC, 'avb_host.c'), LIB, os.path.abspath(__file__)])
+    return (_stale(LIB, deps) or _stale(HOST_EXT, [os.path.join(CSRC, 'avb_host.c'), LIB, os.path.abspath(__file__)]) or
+            _stale(MSCKF_EXT, [os.path.join(CSRC, 'msckf_host.c'), os.path.abspath(__file__)]))
 
 
 def _run(cmd, verbose, what):
@@ -55,6 +58,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _run([os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-ffp-contract=off', '-Wall', '-I', inc,
               os.path.join(CSRC, 'avb_host.c'), '-o', HOST_EXT, '-L', os.path.dirname(LIB), '-lavb', '-lm',
               '-Wl,-rpath,$ORIGIN/../lib'], verbose, 'gcc (_avbhost)')
+    if force or _stale(MSCKF_EXT, [os.path.join(CSRC, 'msckf_host.c'), os.path.abspath(__file__)]):
+        inc = sysconfig.get_paths()['include']
+        _run([os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-ffp-contract=off', '-Wall', '-I', inc,
+              os.path.join(CSRC, 'msckf_host.c'), '-o', MSCKF_EXT, '-lm'], verbose, 'gcc (_msckfhost)')
     return LIB
 
 

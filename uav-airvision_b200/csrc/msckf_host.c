@@ -1,0 +1,409 @@
+/*
+ * _msckfhost -- the two scalar inner loops of the host MSCKF (uav-airvision_b200/msckf.py) in C:
+ *
+ *   propagate(...)    IMU batch between two images: per sample the closed-form transition matrix, RK4 state
+ *                     prediction, observability-constrained blocks and the 21x21 covariance update
+ *                     (reference behaviour: src/msckf.py:251-388); returns the accumulated transition matrix
+ *   triangulate(...)  Levenberg-Marquardt on inverse depth over all stereo observations of a feature
+ *                     (reference behaviour: src/feature/feature_position_initializer.py:31-70,
+ *                     feature_observation.py:4-39)
+ *
+ * Both are a few dozen 3x3 / 21x21 operations per call: numpy spends ~0.35 ms per IMU sample and ~0.5 ms per
+ * feature on call overhead, this spends microseconds.  msckf.py keeps the numpy statement of both (tests compare).
+ * Plain C, no BLAS; every argument is a C-contiguous float64 buffer.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <math.h>
+#include <string.h>
+
+#define N 21
+
+static void skew3(const double* v, double* S) {
+    S[0] = 0; S[1] = -v[2]; S[2] = v[1];
+    S[3] = v[2]; S[4] = 0; S[5] = -v[0];
+    S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
+}
+static void mat3_mul(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+static void mat3_mul_bt(const double* A, const double* B, double* C) { /* A B^T */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+static void mat3_vec(const double* A, const double* v, double* o) {
+    for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+static void mat3_tvec(const double* A, const double* v, double* o) { /* A^T v */
+    for (int i = 0; i < 3; ++i) o[i] = A[i] * v[0] + A[3 + i] * v[1] + A[6 + i] * v[2];
+}
+/* utils.py:12-23 */
+static void to_rotation(const double* q_in, double* R) {
+    const double n = sqrt(q_in[0] * q_in[0] + q_in[1] * q_in[1] + q_in[2] * q_in[2] + q_in[3] * q_in[3]);
+    const double q[4] = {q_in[0] / n, q_in[1] / n, q_in[2] / n, q_in[3] / n};
+    const double w = q[3], a = 2.0 * w * w - 1.0;
+    double S[9];
+    skew3(q, S);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = (i == j ? a : 0.0) - 2.0 * w * S[3 * i + j] + 2.0 * q[i] * q[j];
+}
+
+static void set_block(double* M, int r0, int c0, const double* B, double s) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[(r0 + i) * N + c0 + j] = s * B[3 * i + j];
+}
+
+/* msckf.py:340-388 */
+static void predict_new_state(double dt, const double* gyro, const double* acc, const double* g, double* q, double* v, double* p) {
+    const double gn = sqrt(gyro[0] * gyro[0] + gyro[1] * gyro[1] + gyro[2] * gyro[2]);
+    double Om[16] = {0};
+    double S[9];
+    skew3(gyro, S);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Om[4 * i + j] = -S[3 * i + j];
+        Om[4 * i + 3] = gyro[i];
+        Om[12 + i] = -gyro[i];
+    }
+    double dq[4], dq2[4];
+    for (int half = 0; half < 2; ++half) {
+        const double f = half ? 0.25 : 0.5;
+        double* out = half ? dq2 : dq;
+        double c, sOm;                        /* out = (c I + sOm Omega) q   (large rate) or c (I + sOm Omega) q (small) */
+        if (gn > 1e-5) {
+            c = cos(gn * dt * f);
+            sOm = sin(gn * dt * f) / gn;
+            for (int i = 0; i < 4; ++i) {
+                double acc_ = 0;
+                for (int j = 0; j < 4; ++j) acc_ += ((i == j ? c : 0.0) + sOm * Om[4 * i + j]) * q[j];
+                out[i] = acc_;
+            }
+        } else {
+            c = cos(gn * dt * f);
+            for (int i = 0; i < 4; ++i) {
+                double acc_ = 0;
+                for (int j = 0; j < 4; ++j) acc_ += (c * ((i == j ? 1.0 : 0.0) + Om[4 * i + j] * dt * f)) * q[j];
+                out[i] = acc_;
+            }
+        }
+    }
+    double R0[9], Rh[9], Rf[9];
+    to_rotation(q, R0);
+    to_rotation(dq2, Rh);
+    to_rotation(dq, Rf);
+    double k1[3], k2[3], k4[3], t[3];
+    mat3_tvec(R0, acc, t);
+    for (int i = 0; i < 3; ++i) k1[i] = t[i] + g[i];
+    mat3_tvec(Rh, acc, t);
+    for (int i = 0; i < 3; ++i) k2[i] = t[i] + g[i];           /* k3_v_dot == k2_v_dot */
+    mat3_tvec(Rf, acc, t);
+    for (int i = 0; i < 3; ++i) k4[i] = t[i] + g[i];
+    const double qn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2] + dq[3] * dq[3]);
+    for (int i = 0; i < 3; ++i) {
+        const double k1v = v[i] + k1[i] * dt / 2.0, k2v = v[i] + k2[i] * dt / 2, k3v = v[i] + k2[i] * dt;
+        p[i] = p[i] + (v[i] + 2 * k1v + 2 * k2v + k3v) * dt / 6.0;
+        v[i] = v[i] + (k1[i] + 2 * k2[i] + 2 * k2[i] + k4[i]) * dt / 6.0;
+    }
+    for (int i = 0; i < 4; ++i) q[i] = dq[i] / qn;
+}
+
+/* One IMU sample (msckf.py:274-338).  P: top-left 21x21 block of a matrix with row stride ldp. */
+static void process_model(double dt, const double* m_gyro, const double* m_acc, const double* g, const double* noise, double* q,
+                          double* p, double* v, const double* bg, const double* ba, double* qn, double* pn, double* vn, double* P,
+                          Py_ssize_t ldp, double* phi) {
+    double gyro[3], acc[3];
+    for (int i = 0; i < 3; ++i) {
+        gyro[i] = m_gyro[i] - bg[i];
+        acc[i] = m_acc[i] - ba[i];
+    }
+    double R[9], Rt[9];
+    to_rotation(q, R);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rt[3 * i + j] = R[3 * j + i];
+    double A[9], C[9], D[9], S[9], T[9], A2[9], A3[9], CA[9], CA2[9];
+    skew3(gyro, S);
+    for (int i = 0; i < 9; ++i) A[i] = -S[i] * dt;
+    skew3(acc, S);
+    mat3_mul(Rt, S, T);
+    for (int i = 0; i < 9; ++i) {
+        C[i] = -T[i] * dt;
+        D[i] = -Rt[i] * dt;
+    }
+    mat3_mul(A, A, A2);
+    mat3_mul(A2, A, A3);
+    mat3_mul(C, A, CA);
+    mat3_mul(CA, A, CA2);
+    memset(phi, 0, sizeof(double) * N * N);
+    for (int i = 0; i < N; ++i) phi[i * N + i] = 1.0;
+    double B[9], vth[9], pth[9];
+    for (int i = 0; i < 9; ++i) {
+        const double id = (i % 4 == 0) ? 1.0 : 0.0;
+        B[i] = -dt * (id + A[i] / 2.0 + A2[i] / 6.0);
+        vth[i] = C[i] + CA[i] / 2.0 + CA2[i] / 6.0;
+        pth[i] = dt * (C[i] / 2.0 + CA[i] / 6.0);
+    }
+    set_block(phi, 0, 3, B, 1.0);
+    for (int i = 0; i < 9; ++i) T[i] = -dt * (C[i] / 2.0 + CA[i] / 6.0);
+    set_block(phi, 6, 3, T, 1.0);
+    set_block(phi, 6, 9, D, 1.0);
+    for (int i = 0; i < 9; ++i) T[i] = -dt * dt * C[i] / 6.0;
+    set_block(phi, 12, 3, T, 1.0);
+    for (int i = 0; i < 3; ++i) phi[(12 + i) * N + 6 + i] = dt;
+    set_block(phi, 12, 9, D, dt / 2.0);
+
+    predict_new_state(dt, gyro, acc, g, q, v, p);
+
+    /* observability constraint (msckf.py:311-328) */
+    double Rk[9], Rn[9];
+    to_rotation(qn, Rk);
+    to_rotation(q, Rn);
+    mat3_mul_bt(Rn, Rk, T);
+    set_block(phi, 0, 0, T, 1.0);
+    double u[3], s[3], w[3], d[3], Au[3];
+    mat3_vec(Rk, g, u);
+    const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+    for (int i = 0; i < 3; ++i) s[i] = u[i] / uu;
+    for (int i = 0; i < 3; ++i) d[i] = vn[i] - v[i];
+    skew3(d, S);
+    mat3_vec(S, g, w);
+    mat3_vec(vth, u, Au);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) phi[(6 + i) * N + j] = vth[3 * i + j] - (Au[i] - w[i]) * s[j];
+    for (int i = 0; i < 3; ++i) d[i] = dt * vn[i] + pn[i] - p[i];
+    skew3(d, S);
+    mat3_vec(S, g, w);
+    mat3_vec(pth, u, Au);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) phi[(12 + i) * N + j] = pth[3 * i + j] - (Au[i] - w[i]) * s[j];
+
+    /* P_II <- Phi (P_II + G Qc G^T dt) Phi^T, symmetrised */
+    double M[N * N], X[N * N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) M[i * N + j] = P[i * ldp + j] + (i == j ? noise[i] * dt : 0.0);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double a = 0;
+            for (int k = 0; k < N; ++k) a += phi[i * N + k] * M[k * N + j];
+            X[i * N + j] = a;
+        }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double a = 0;
+            for (int k = 0; k < N; ++k) a += X[i * N + k] * phi[j * N + k];
+            M[i * N + j] = a;
+        }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) P[i * ldp + j] = (M[i * N + j] + M[j * N + i]) / 2.0;
+    memcpy(qn, q, 4 * sizeof(double));
+    memcpy(pn, p, 3 * sizeof(double));
+    memcpy(vn, v, 3 * sizeof(double));
+}
+
+static int get_buf(PyObject* o, Py_buffer* b, Py_ssize_t min_doubles, int writable, const char* name) {
+    if (PyObject_GetBuffer(o, b, (writable ? PyBUF_WRITABLE : 0) | PyBUF_C_CONTIGUOUS) < 0) return -1;
+    if (b->itemsize != 8 || b->len < min_doubles * 8) {
+        PyBuffer_Release(b);
+        PyErr_Format(PyExc_ValueError, "%s: need a C-contiguous float64 buffer of >= %zd elements", name, min_doubles);
+        return -1;
+    }
+    return 0;
+}
+
+/* propagate(q, p, v, bg, ba, q_null, p_null, v_null, P, n, noise, gravity, imu(k x 7), t_state, t_bound, phi_total)
+ *   -> (used, processed, t_state)   state arrays and P's 21x21 block updated in place; phi_total (21x21) = product of the
+ *   transition matrices of the processed samples (identity when none). */
+static PyObject* py_propagate(PyObject* self, PyObject* args) {
+    PyObject *oq, *op, *ov, *obg, *oba, *oqn, *opn, *ovn, *oP, *onoise, *og, *oimu, *ophi;
+    Py_ssize_t n;
+    double t_state, t_bound;
+    if (!PyArg_ParseTuple(args, "OOOOOOOOOnOOOddO", &oq, &op, &ov, &obg, &oba, &oqn, &opn, &ovn, &oP, &n, &onoise, &og, &oimu, &t_state,
+                          &t_bound, &ophi))
+        return NULL;
+    Py_buffer b[13];
+    PyObject* objs[13] = {oq, op, ov, obg, oba, oqn, opn, ovn, oP, onoise, og, oimu, ophi};
+    const Py_ssize_t mins[13] = {4, 3, 3, 3, 3, 4, 3, 3, n * n, N, 3, 0, N * N};
+    const int wr[13] = {1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1};
+    static const char* names[13] = {"q", "p", "v", "bg", "ba", "q_null", "p_null", "v_null", "P", "noise", "gravity", "imu", "phi_total"};
+    int got = 0;
+    for (; got < 13; ++got)
+        if (get_buf(objs[got], &b[got], mins[got], wr[got], names[got]) < 0) break;
+    if (got < 13 || n < N) {
+        for (int i = 0; i < got; ++i) PyBuffer_Release(&b[i]);
+        if (got == 13) PyErr_SetString(PyExc_ValueError, "covariance smaller than 21 x 21");
+        return NULL;
+    }
+    double *q = b[0].buf, *p = b[1].buf, *v = b[2].buf, *qn = b[5].buf, *pn = b[6].buf, *vn = b[7].buf, *P = b[8].buf;
+    const double *bg = b[3].buf, *ba = b[4].buf, *noise = b[9].buf, *g = b[10].buf, *imu = b[11].buf;
+    double* tot = b[12].buf;
+    const Py_ssize_t k = b[11].len / (7 * 8);
+    Py_ssize_t used = 0, processed = 0;
+    double phi[N * N], tmp[N * N];
+    memset(tot, 0, sizeof(double) * N * N);
+    for (int i = 0; i < N; ++i) tot[i * N + i] = 1.0;
+    for (Py_ssize_t i = 0; i < k; ++i) {
+        const double* m = imu + 7 * i;
+        if (m[0] < t_state) {
+            ++used;
+            continue;
+        }
+        if (m[0] > t_bound) break;
+        process_model(m[0] - t_state, m + 1, m + 4, g, noise, q, p, v, bg, ba, qn, pn, vn, P, n, phi);
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) {
+                double a = 0;
+                for (int j = 0; j < N; ++j) a += phi[r * N + j] * tot[j * N + c];
+                tmp[r * N + c] = a;
+            }
+        memcpy(tot, tmp, sizeof tmp);
+        ++used;
+        ++processed;
+        t_state = m[0];
+    }
+    for (int i = 0; i < 13; ++i) PyBuffer_Release(&b[i]);
+    return Py_BuildValue("(nnd)", used, processed, t_state);
+}
+
+static int solve3(const double* A_in, const double* b_in, double* x) {   /* partial pivoting */
+    double A[9], b[3];
+    memcpy(A, A_in, sizeof A);
+    memcpy(b, b_in, sizeof b);
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 3; ++r)
+            if (fabs(A[3 * r + c]) > fabs(A[3 * piv + c])) piv = r;
+        if (A[3 * piv + c] == 0.0) return -1;
+        if (piv != c) {
+            for (int j = 0; j < 3; ++j) {
+                const double t = A[3 * c + j];
+                A[3 * c + j] = A[3 * piv + j];
+                A[3 * piv + j] = t;
+            }
+            const double t = b[c];
+            b[c] = b[piv];
+            b[piv] = t;
+        }
+        for (int r = c + 1; r < 3; ++r) {
+            const double f = A[3 * r + c] / A[3 * c + c];
+            for (int j = c; j < 3; ++j) A[3 * r + j] -= f * A[3 * c + j];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = 2; r >= 0; --r) {
+        double a = b[r];
+        for (int j = r + 1; j < 3; ++j) a -= A[3 * r + j] * x[j];
+        x[r] = a / A[3 * r + r];
+    }
+    return 0;
+}
+
+static double lm_cost(const double* Rs, const double* ts, const double* zs, Py_ssize_t k, const double* x) {
+    double e = 0;
+    for (Py_ssize_t i = 0; i < k; ++i) {
+        const double* R = Rs + 9 * i;
+        const double* t = ts + 3 * i;
+        const double h1 = R[0] * x[0] + R[1] * x[1] + R[2] + x[2] * t[0];
+        const double h2 = R[3] * x[0] + R[4] * x[1] + R[5] + x[2] * t[1];
+        const double h3 = R[6] * x[0] + R[7] * x[1] + R[8] + x[2] * t[2];
+        const double a = h1 / h3 - zs[2 * i], b = h2 / h3 - zs[2 * i + 1];
+        e += a * a + b * b;
+    }
+    return e;
+}
+
+/* triangulate(Rs (k x 3 x 3), ts (k x 3), zs (k x 2), x0 (3), huber, precision, damping, outer_max, inner_max) -> (alpha, beta, rho)
+ * k camera poses relative to the first cam0 (x_ci = R x_c0 + t), their normalized measurements, initial (alpha, beta, rho). */
+static PyObject* py_triangulate(PyObject* self, PyObject* args) {
+    PyObject *oR, *ot, *oz, *ox;
+    double huber, precision, lambd;
+    int outer_max, inner_max;
+    if (!PyArg_ParseTuple(args, "OOOOdddii", &oR, &ot, &oz, &ox, &huber, &precision, &lambd, &outer_max, &inner_max)) return NULL;
+    Py_buffer bR, bt, bz, bx;
+    if (get_buf(oR, &bR, 9, 0, "Rs") < 0) return NULL;
+    const Py_ssize_t k = bR.len / 72;
+    if (get_buf(ot, &bt, 3 * k, 0, "ts") < 0) {
+        PyBuffer_Release(&bR);
+        return NULL;
+    }
+    if (get_buf(oz, &bz, 2 * k, 0, "zs") < 0) {
+        PyBuffer_Release(&bR);
+        PyBuffer_Release(&bt);
+        return NULL;
+    }
+    if (get_buf(ox, &bx, 3, 0, "x0") < 0) {
+        PyBuffer_Release(&bR);
+        PyBuffer_Release(&bt);
+        PyBuffer_Release(&bz);
+        return NULL;
+    }
+    const double *Rs = bR.buf, *ts = bt.buf, *zs = bz.buf;
+    double sol[3];
+    memcpy(sol, bx.buf, sizeof sol);
+    int outer = 0, inner = 0, singular = 0;
+    double delta_norm = INFINITY, total = lm_cost(Rs, ts, zs, k, sol);
+    while (outer < outer_max && delta_norm > precision && !singular) {
+        double A[9] = {0}, bb[3] = {0};
+        for (Py_ssize_t i = 0; i < k; ++i) {
+            const double* R = Rs + 9 * i;
+            const double* t = ts + 3 * i;
+            const double h1 = R[0] * sol[0] + R[1] * sol[1] + R[2] + sol[2] * t[0];
+            const double h2 = R[3] * sol[0] + R[4] * sol[1] + R[5] + sol[2] * t[1];
+            const double h3 = R[6] * sol[0] + R[7] * sol[1] + R[8] + sol[2] * t[2];
+            const double W[9] = {R[0], R[1], t[0], R[3], R[4], t[1], R[6], R[7], t[2]};
+            double J[6];
+            for (int j = 0; j < 3; ++j) {
+                J[j] = W[j] / h3 - W[6 + j] * h1 / (h3 * h3);
+                J[3 + j] = W[3 + j] / h3 - W[6 + j] * h2 / (h3 * h3);
+            }
+            const double r0 = h1 / h3 - zs[2 * i], r1 = h2 / h3 - zs[2 * i + 1];
+            const double e = sqrt(r0 * r0 + r1 * r1);
+            const double w2 = (e <= huber) ? 1.0 : (huber / (2 * e)) * (huber / (2 * e));
+            for (int a = 0; a < 3; ++a) {
+                for (int c = 0; c < 3; ++c) A[3 * a + c] += w2 * (J[a] * J[c] + J[3 + a] * J[3 + c]);
+                bb[a] += w2 * (J[a] * r0 + J[3 + a] * r1);
+            }
+        }
+        int reduced = 0;
+        while (inner < inner_max && !reduced) {
+            double Ad[9], delta[3], ns[3];
+            memcpy(Ad, A, sizeof Ad);
+            Ad[0] += lambd;
+            Ad[4] += lambd;
+            Ad[8] += lambd;
+            if (solve3(Ad, bb, delta) < 0) {
+                singular = 1;
+                break;
+            }
+            for (int j = 0; j < 3; ++j) ns[j] = sol[j] - delta[j];
+            delta_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+            const double nc = lm_cost(Rs, ts, zs, k, ns);
+            if (nc < total) {
+                reduced = 1;
+                memcpy(sol, ns, sizeof sol);
+                total = nc;
+                lambd = fmax(lambd / 10.0, 1e-10);
+            } else {
+                lambd = fmin(lambd * 10.0, 1e12);
+            }
+            ++inner;
+        }
+        ++outer;
+    }
+    PyBuffer_Release(&bR);
+    PyBuffer_Release(&bt);
+    PyBuffer_Release(&bz);
+    PyBuffer_Release(&bx);
+    if (singular) {
+        PyErr_SetString(PyExc_ArithmeticError, "singular normal equations in feature triangulation");
+        return NULL;
+    }
+    return Py_BuildValue("(ddd)", sol[0], sol[1], sol[2]);
+}
+
+static PyMethodDef methods[] = {
+    {"propagate", py_propagate, METH_VARARGS, "IMU batch propagation (msckf.py:251-388 of the reference)."},
+    {"triangulate", py_triangulate, METH_VARARGS, "Levenberg-Marquardt feature triangulation on inverse depth."},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_msckfhost", "Scalar inner loops of the host MSCKF.", -1, methods};
+
+PyMODINIT_FUNC PyInit__msckfhost(void) { return PyModule_Create(&moddef); }
