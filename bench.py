@@ -191,13 +191,141 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _render_sequence(job):
+    """Worker of the C5 leg: one rendered EuRoC-geometry sequence (images, IMU rows, ground truth) as arrays."""
+    q, n_frames = job
+    for p in (ROOT, os.path.join(ROOT, 'uav-airvision_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from frontend_config import config_c2
+    from synth_euroc import RoomSceneStream
+    st = RoomSceneStream(config_c2(), n_frames=n_frames, seed=100 + q, amp=0.7 + 0.08 * q, tex_size=1536)
+    fr = list(st.frames())
+    imu = np.array([[m.timestamp, *m.angular_velocity, *m.linear_acceleration] for m in st.imu()])
+    gt = list(st.groundtruth())
+    return {'q': q, 'ts': np.array([f.timestamp for f in fr]), 'img0': np.stack([f.cam0_image for f in fr]),
+            'img1': np.stack([f.cam1_image for f in fr]), 'imu': imu,
+            'gt_t': np.array([g.timestamp for g in gt]), 'gt_p': np.array([g.p for g in gt])}
+
+
+class _ArraySequence:
+    """Adapter: arrays of _render_sequence -> the frames()/imu()/groundtruth() shape CachedSequence reads."""
+
+    def __init__(self, d):
+        self.d, self.n = d, len(d['ts'])
+
+    def frames(self):
+        from synth_euroc import img_msg, stereo_msg
+        d = self.d
+        for k in range(self.n):
+            t = float(d['ts'][k])
+            yield stereo_msg(t, d['img0'][k], d['img1'][k], img_msg(t, d['img0'][k]), img_msg(t, d['img1'][k]))
+
+    def imu(self):
+        from synth_euroc import imu_msg
+        return (imu_msg(float(r[0]), r[1:4], r[4:7]) for r in self.d['imu'])
+
+    def groundtruth(self):
+        from synth_euroc import gt_msg
+        z = np.zeros(3)
+        return (gt_msg(float(t), p, None, z, z, z) for t, p in zip(self.d['gt_t'], self.d['gt_p']))
+
+
+def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_over_ranks, bound):
+    """BASELINE config C5: sequences x time offsets, full front end + host MSCKF, sharded over the GPUs by sequence.
+    Every rank renders its sequences (synthetic, EuRoC geometry), uploads each ONCE into an HBM frame store, and runs
+    all offset runs of its sequences in lock-step through one context; estimators run in worker processes."""
+    import multiprocessing as mp
+    from frontend_config import config_c2, with_filter_fields
+    from metrics import trajectory_metrics
+    from multi_stream import shard_streams
+    from sweep import CachedSequence, run_sweep
+    cfg = with_filter_fields(config_c2())
+    mine = shard_streams(args.c5_sequences, world, rank)
+    step_frames = 2                                           # offsets 0, 0.1 s, 0.2 s, ... (20 Hz frames)
+    offsets = [o * step_frames / 20.0 for o in range(args.c5_offsets)]
+    n_frames = args.c5_steps + step_frames * (args.c5_offsets - 1) + 1
+    cores = sorted(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    with mp.get_context('spawn').Pool(min(len(mine), max(1, len(cores)))) as pool:
+        rendered = pool.map(_render_sequence, [(q, n_frames) for q in mine])
+    render_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    seqs = [CachedSequence(_ArraySequence(d), device=local, name=f'room{d["q"]}') for d in rendered]
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t0
+    store_bytes = sum(q.store.nbytes for q in seqs)
+    workers = args.c5_workers if args.c5_workers > 0 else max(1, len(cores) - 1)
+    warm = 2
+    sampler = ClockSampler(local) if rank == 0 else None
+    # front end alone (what the GPU side of the sweep sustains from the HBM store, results as arrays on the host)
+    barrier()
+    fe_only = run_sweep(cfg, seqs, offsets, device=local, n_steps=args.c5_steps, warmup_steps=warm)
+    barrier()
+    t_a = time.perf_counter()
+    full = run_sweep(cfg, seqs, offsets, device=local, n_steps=args.c5_steps, estimator_workers=workers, warmup_steps=warm)
+    barrier()
+    t_b = time.perf_counter()
+    assert np.array_equal(fe_only['features'], full['features'])
+    S, timed = full['streams'], full['timed_steps']
+    wall = max_over_ranks(full['wall_s'])
+    fe_wall = max_over_ranks(fe_only['wall_s'])
+    frames_total = sum_over_ranks(S * timed)
+    feats_total = sum_over_ranks(float(full['features'][:, warm:].sum()))
+    published = sum_over_ranks(float(sum(len(t) for t in full['trajectories'])))
+    # accuracy of the offset-0 run of this rank's first sequence against its ground truth (sanity, not a parity gate)
+    ate = None
+    tr = full['trajectories'][0]
+    if len(tr) > 10 and seqs[0].groundtruth is not None:
+        m = trajectory_metrics(tr[:, 0], tr[:, 1:4], *seqs[0].groundtruth)
+        ate = {'ate_rmse_m': m['ate_rmse_m'], 'path_m': m['path_m'], 'poses': int(len(tr))}
+    for q in seqs:
+        q.close()
+    clocks = sampler.summary([(t_a, t_b)]) if sampler is not None else None
+    if rank == 0:
+        img_bytes = 2 * seqs[0].width * seqs[0].height
+        busy = full['estimator']['worker_busy_s']
+        line = {
+            'metric': METRIC, 'value': frames_total / wall, 'unit': UNIT, 'n_gpus': world, 'steps': timed, 'warmup': warm,
+            'ms_per_step': 1e3 * wall / timed, 'higher_is_better': True, 'scaling': 'weak' if world <= args.c5_sequences else 'strong',
+            'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (LK), f64 (undistort, MSCKF)', 'data': 'synthetic',
+            'config': {'workload': f'C5: {args.c5_sequences} EuRoC-geometry synthetic sequences x {args.c5_offsets} time offsets '
+                                   f'= {args.c5_sequences * args.c5_offsets} runs, full front end (C2 grid, 300 features) + host MSCKF, '
+                                   f'sharded by sequence over {world} GPU(s)',
+                       'runs_per_gpu': S, 'offset_spacing_s': step_frames / 20.0,
+                       'estimator_workers_per_gpu': workers, 'host_cores_per_rank': len(cores),
+                       'host_cpus_bound': sorted(bound) if bound else None,
+                       'frame_source': f'HBM frame store: each sequence uploaded once ({store_bytes / 1e6:.0f} MB on rank 0), '
+                                       f'every offset run gathers its frames on the device'},
+            'tracked_features_per_s': feats_total / wall,
+            'poses_published': int(published),
+            'front_end_only': {'value': frames_total / fe_wall, 'unit': UNIT, 'ms_per_step': 1e3 * fe_wall / timed,
+                               'note': 'same sweep without estimators: gather + frame chain + result arrays on the host'},
+            'estimator': {'worker_busy_s': [round(b, 3) for b in busy],
+                          'ms_per_frame': 1e3 * float(np.sum(busy)) / max(full['estimator']['frames'], 1),
+                          'note': 'host MSCKF (uav-airvision_b200/msckf.py) in worker processes; it bounds this leg'},
+            'e2e': {'value': frames_total / (wall + max_over_ranks(upload_s)), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(len(mine) * n_frames * img_bytes / args.c5_steps),
+                    'd2h_bytes_per_step': int(S * (48 + 300 * 40)),
+                    'note': 'includes the one-time upload of every sequence frame into the store (amortised over its offset runs); '
+                            'rendering the synthetic frames is excluded'},
+            'setup_s': {'render': round(render_s, 2), 'upload': round(upload_s, 3)},
+            'accuracy_run0': ate, 'gpu_launches': int(timed * full['kernels_per_step']), 'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3'])
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'])
+    ap.add_argument('--c5-sequences', type=int, default=8)
+    ap.add_argument('--c5-offsets', type=int, default=16)
+    ap.add_argument('--c5-steps', type=int, default=60)
+    ap.add_argument('--c5-workers', type=int, default=0, help='estimator processes per GPU (0 = host cores of the rank - 1)')
     ap.add_argument('--streams', type=int, default=64,
                     help='total streams of the extra multi-stream leg (config C4), sharded over the GPUs (0 = skip)')
     ap.add_argument('--ms-steps', type=int, default=20)
@@ -217,6 +345,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: libavb has no CPU fallback')
     torch.cuda.set_device(local)
+    # one process per GPU: stay on the host cores next to this GPU (pinned staging / mapped result block are first-touch)
+    from multi_stream import bind_to_gpu_numa
+    full_affinity = os.sched_getaffinity(0)
+    pr = torch.cuda.get_device_properties(local)
+    bound = bind_to_gpu_numa(f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0', local,
+                             int(os.environ.get('LOCAL_WORLD_SIZE', world)))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -239,6 +373,12 @@ def main():
         t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.workload == 'c5':
+        run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_over_ranks, bound)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     from image_processing import ImageProcessor, _native
     cfg, skw, wname = workload(args.workload)
@@ -395,6 +535,9 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)            # the CPU path may use every host core
+        import cv2
+        cv2.setNumThreads(-1)
         times, cfeats, threads, cvv = cpu_front_end(cfg, stream, min(n, W + 1 + K), budget_s=25.0)
         done = len(times)
         w_ = min(W + 1, max(done - 1, 1))
@@ -434,7 +577,8 @@ def main():
                        'l2_policy': f'{W + K + 1} distinct frames x {2 * img_bytes} B = '
                                     f'{(W + K + 1) * 2 * img_bytes / 1e6:.0f} MB device-resident sequence, each read once '
                                     f'(larger than the 126 MB L2 when steps >= 180)',
-                       'frame_graph': 'one CUDA-graph launch per frame'},
+                       'frame_graph': 'one CUDA-graph launch per frame',
+                       'host_cpus_bound': sorted(bound) if bound else None},
             'tracked_features_per_s': total_feats / (dev_ms * 1e-3),
             'e2e': {'value': world * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(bb),
                     'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': 1e3 * e2e_s / K,

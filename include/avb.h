@@ -27,6 +27,8 @@
  *                                  FeaturePublisher fused into one CUDA-graph launch per frame)
  *   avb_get_features              pipeline.prev_features (state read-back)  image_processing/pipeline.py:145-148
  *   avb_two_point_ransac          (none: all-ones stub)                 image_processing/feature_tracker.py:135-136
+ *   avb_store_* / avb_process_frame_gather
+ *                                 EuRoCDataset image readers of a run.bat sweep   streaming/dataset.py:101-117, 206-214
  */
 #ifndef AVB_H_
 #define AVB_H_
@@ -131,6 +133,27 @@ int  avb_process_frame_device(avb_ctx* ctx, const uint8_t* d_block);
  * context are ordered on its stream, so K enqueues + one sync time K dependent frames. */
 int  avb_enqueue_frame_device(avb_ctx* ctx, const uint8_t* d_block);
 int  avb_sync(avb_ctx* ctx);
+
+/* ---- HBM-resident sequence store (sweeps of time-offset runs) ---------------------------
+ * Replaces, for sweeps, the per-run image readers of the reference: every `python main.py --path <seq>
+ * --offset <s>` of run.bat:4-12 re-reads and re-decodes its frames (streaming/dataset.py:101-117, 206-214).
+ * Here a sequence is decoded and uploaded once; the S offset runs of a context take their current frames
+ * straight from device memory.  Frame k holds cam0 then cam1, width*height dense bytes each. */
+typedef struct avb_store avb_store;
+int  avb_store_create(int device, int width, int height, int n_frames, avb_store** out);
+void avb_store_destroy(avb_store* store);
+int  avb_store_num_frames(const avb_store* store);
+size_t avb_store_bytes(const avb_store* store);        /* device bytes held */
+/* Host images (uint8, row stride in bytes) -> frame k of the store.  Blocking; done once per sequence frame. */
+int  avb_store_upload(avb_store* store, int k, const uint8_t* img0, const uint8_t* img1, int stride);
+/* Device pointer of image `cam` of frame k (NULL when out of range). */
+const uint8_t* avb_store_image(const avb_store* store, int k, int cam);
+
+/* One stereo frame for every stream from images that already live in device memory: d_images[s*2 + cam] is a
+ * dense width*height uint8 image, 16-byte aligned (e.g. avb_store_image).  A gather kernel places them in the
+ * input block; rotations as in avb_process_frame.  Blocks until the results are in host memory. */
+int  avb_process_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, const double* R_p_c0,
+                              const double* R_p_c1);
 
 /* Results of the last frame for stream s (pointers into pinned host memory, valid until the
  * next avb_process_frame): ids[n], meas[n*4] = u0 v0 u1 v1 (normalized coords; u0,v0 carry the

@@ -340,3 +340,71 @@ def test_multi_stream_with_ransac_equals_single_pipelines():
     fe.close()
     print(f'multi-stream + RANSAC: 3 streams x 7 frames identical to single pipelines; {dropped} features rejected by RANSAC')
     assert dropped > 0
+
+
+def test_sweep_from_hbm_store_equals_single_pipelines():
+    """Sequence x offset sweep (run.bat shape): two sequences cached once in HBM, three time-offset runs each, all six in
+    lock-step through one context fed by the gather kernel.  Every run publishes exactly what a separate
+    ImageProcessor publishes when it replays the host frames of that run (frames and IMU samples older than the run's
+    start time dropped, dataset.py:206-214).  With estimator workers the sweep also returns one trajectory per run."""
+    from image_processing import ImageProcessor
+    from frontend_config import with_filter_fields
+    from sweep import CachedSequence, run_sweep
+    cfg = with_filter_fields(FrontEndConfig(grid_row=5, grid_col=6))
+    kws = [dict(n_frames=12, seed=60 + q, sigma=2.0 + 0.5 * q, drift=(1.3, -0.4 - 0.3 * q), gyro=(0.02, -0.01 * q, 0.03),
+                noise=0.5) for q in range(2)]
+    offsets = (0.0, 0.07, 0.21)                                    # frame period 0.05 s: runs start at frames 0, 2, 5
+    seqs = [CachedSequence(SlidingTextureStream(**kw)) for kw in kws]
+    assert seqs[0].store.nbytes >= 12 * 2 * 752 * 480
+    steps = 6
+    res = run_sweep(cfg, seqs, offsets, n_steps=steps, estimator_workers=2, warmup_steps=1)
+    assert res['streams'] == 6 and res['steps'] == steps and len(res['trajectories']) == 6
+    assert [r.first_frame for r in res['runs']] == [0, 2, 5, 0, 2, 5]
+    # the same runs, one pipeline each, host frames
+    want = []
+    for q, kw in enumerate(kws):
+        for off in offsets:
+            st = SlidingTextureStream(**kw)
+            frames = list(st.frames())
+            start = max(frames[0].timestamp, next(iter(st.imu())).timestamp) + off
+            ip = ImageProcessor(cfg)
+            out = []
+            for kind, m in st.events():
+                if m.timestamp < start:
+                    continue
+                if kind == 'imu':
+                    ip.imu_callback(m)
+                else:
+                    out.append(ip.stereo_callback(m))
+                    if len(out) == steps:
+                        break
+            ip.context.close()
+            want.append(out)
+    # replay the sweep once more without estimators, collecting what each run published
+    from multi_stream import MultiStreamFrontEnd
+    fe = MultiStreamFrontEnd(cfg, 752, 480, 6)
+    runs = res['runs']
+    pos = [r.first_imu for r in runs]
+    for k in range(steps):
+        refs, addrs = [], np.empty((6, 2), np.uint64)
+        for s, r in enumerate(runs):
+            seq = seqs[r.sequence]
+            idx = r.first_frame + k
+            j1 = int(np.searchsorted(seq.imu_rows[:, 0], seq.timestamps[idx], side='right'))
+            for m in seq.imu_msgs[pos[s]:j1]:
+                fe.imu_callback(s, m)
+            pos[s] = j1
+            refs.append(seq.frame_refs[idx])
+            addrs[s] = seq.store.addr[idx]
+        out = fe.step_from_store(addrs, refs)
+        for s, (ts, ids, meas) in enumerate(out):
+            fm = want[s][k]
+            assert ts == fm.timestamp
+            assert ids.tolist() == [f.id for f in fm.features]
+            assert meas.tolist() == [[float(f.u0), float(f.v0), float(f.u1), float(f.v1)] for f in fm.features]
+            assert res['features'][s, k] == len(ids)
+    fe.close()
+    for q in seqs:
+        q.close()
+    print(f'sweep: 6 offset runs x {steps} steps from the HBM store equal 6 single pipelines; '
+          f'{int(res["features"].sum())} features published')

@@ -61,3 +61,49 @@ def test_gloo_world2_gather_and_max_over_ranks():
     stats = got[0][1]
     assert [d['stream'] for d in stats] == list(range(7))
     assert all(d['frames'] == 3 and d['features'] == 3 * d['stream'] + 3 for d in stats)
+
+
+def _fake_sysfs(root, gpus, node_cpus):
+    """gpus: {pci id: numa node}; node_cpus: {node: cpulist text}."""
+    for pci, node in gpus.items():
+        d = root / 'bus' / 'pci' / 'devices' / pci
+        d.mkdir(parents=True)
+        (d / 'numa_node').write_text(f'{node}\n')
+        (d / 'vendor').write_text('0x10de\n')
+        (d / 'class').write_text('0x030200\n')
+    for node, cpus in node_cpus.items():
+        d = root / 'devices' / 'system' / 'node' / f'node{node}'
+        d.mkdir(parents=True)
+        (d / 'cpulist').write_text(cpus + '\n')
+
+
+def test_bind_to_gpu_numa_deals_the_node_cores_to_its_ranks(tmp_path):
+    """One process per GPU stays on the host cores of its GPU's NUMA node; unknown topology leaves the affinity alone."""
+    from multi_stream import _parse_cpulist, bind_to_gpu_numa
+    assert _parse_cpulist('0-3,8,10-11') == {0, 1, 2, 3, 8, 10, 11}
+    full = os.sched_getaffinity(0)
+    cpus = sorted(full)
+    try:
+        if len(cpus) >= 4:
+            half = len(cpus) // 2
+            lo, hi = cpus[:half], cpus[half:]
+            gpus = {f'0000:{0x10 + i:02x}:00.0': (0 if i < 2 else 1) for i in range(4)}
+            _fake_sysfs(tmp_path, gpus, {0: ','.join(map(str, lo)), 1: ','.join(map(str, hi))})
+            got = []
+            for r, pci in enumerate(sorted(gpus)):
+                os.sched_setaffinity(0, full)
+                got.append(bind_to_gpu_numa(pci, r, 4, sysfs=str(tmp_path)))
+                assert os.sched_getaffinity(0) == got[-1]
+            assert got[0] | got[1] <= set(lo) and got[2] | got[3] <= set(hi)
+            assert not (got[0] & got[1]) and not (got[2] & got[3])
+            os.sched_setaffinity(0, full)
+            # upper-case bus id as cudaDeviceGetPCIBusId prints it; single rank gets the whole node
+            assert bind_to_gpu_numa('0000:1A:00.0'.replace('1A', '10'), 0, 1, sysfs=str(tmp_path)) == set(lo)
+        os.sched_setaffinity(0, full)
+        assert bind_to_gpu_numa('0000:ff:00.0', 0, 1, sysfs=str(tmp_path)) is None      # no such device
+        (tmp_path / 'bus' / 'pci' / 'devices' / '0000:fe:00.0').mkdir(parents=True)
+        (tmp_path / 'bus' / 'pci' / 'devices' / '0000:fe:00.0' / 'numa_node').write_text('-1\n')
+        assert bind_to_gpu_numa('0000:fe:00.0', 0, 1, sysfs=str(tmp_path)) is None      # single-node box
+        assert os.sched_getaffinity(0) == full
+    finally:
+        os.sched_setaffinity(0, full)

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libavb.so')
 HOST_EXT = os.path.join(HERE, 'image_processing', '_avbhost' + sysconfig.get_config_var('EXT_SUFFIX'))
 MSCKF_EXT = os.path.join(HERE, '_msckfhost' + sysconfig.get_config_var('EXT_SUFFIX'))
-SOURCES = ['avb_api.cu', 'avb_pyramid.cu', 'avb_fast.cu', 'avb_points.cu', 'avb_grid.cu', 'avb_ransac.cu']
+SOURCES = ['avb_api.cu', 'avb_pyramid.cu', 'avb_fast.cu', 'avb_points.cu', 'avb_grid.cu', 'avb_ransac.cu', 'avb_store.cu']
 HEADERS = ['avb_common.cuh', 'avb_lk.cuh', os.path.join('..', '..', 'include', 'avb.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-fmad=false',            # cv2's float32/float64 arithmetic is not FMA-contracted; neither is ours

@@ -581,6 +581,34 @@ extern "C" int avb_enqueue_frame_device(avb_ctx* c, const uint8_t* d_block) {
     return run_frame(c, 1, false);
 }
 
+// Frames that already live in HBM (an avb_store, or any device buffers): one gather kernel places them in the input
+// block, the rotation section travels from the pinned staging on the side stream, then the device-input graph runs.
+cudaError_t launch_gather_frames(const Geom& g, uint8_t* d_in, const uint8_t* const* images, cudaStream_t st);
+
+static int gather_frame(avb_ctx* c, const uint8_t* const* d_images, const double* R_p_c0, const double* R_p_c1, bool wait) {
+    if (!c || !d_images) return AVB_E_INVALID;
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->cfg.device));
+    for (int i = 0; i < 2 * g.S; ++i)
+        if (!d_images[i] || (reinterpret_cast<uintptr_t>(d_images[i]) & 15))
+            return fail(c, AVB_E_INVALID, "image %d (stream %d cam %d): null or not 16-byte aligned", i, i / 2, i & 1);
+    const int p = c->parity ^ 1;
+    CK(cudaEventRecord(c->ev_t0, c->st));
+    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
+    const size_t ro = in_images_bytes(g);
+    CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));
+    CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
+    CK(cudaEventRecord(c->ev_join, c->st_side));
+    CK(launch_gather_frames(g, c->d.in[p], d_images, c->st));
+    CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    return run_frame(c, 2, wait);
+}
+
+extern "C" int avb_process_frame_gather(avb_ctx* c, const uint8_t* const* d_images, const double* R_p_c0,
+                                        const double* R_p_c1) {
+    return gather_frame(c, d_images, R_p_c0, R_p_c1, true);
+}
+
 extern "C" int avb_sync(avb_ctx* c) {
     if (!c) return AVB_E_INVALID;
     CK(cudaStreamSynchronize(c->st));

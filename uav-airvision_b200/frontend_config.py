@@ -58,6 +58,38 @@ class FrontEndConfig:
                 setattr(self, k, np.array([v[0] * sx, v[1] * sy, v[2] * sx, v[3] * sy]))
 
 
+class OptimizationConfig:
+    """Triangulation settings (reference config.py:7-17, OptimizationConfigEuRoC)."""
+    translation_threshold = -1.0
+    huber_epsilon = 0.01
+    estimation_precision = 5e-7
+    initial_damping = 1e-3
+    outer_loop_max_iteration = 5
+    inner_loop_max_iteration = 5
+
+
+def with_filter_fields(cfg):
+    """Adds the MSCKF fields of the reference's ConfigEuRoC (config.py:47-72, 93-122) to a front-end config, so one
+    object configures the front end and its consumer (msckf.MSCKF) the way ConfigEuRoC does."""
+    cfg.optimization_config = OptimizationConfig()
+    cfg.gravity = np.array([0.0, 0.0, -9.81])
+    cfg.max_cam_state_size = 20
+    cfg.position_std_threshold = 2.0
+    cfg.gyro_noise, cfg.acc_noise = 0.005 ** 2, 0.05 ** 2
+    cfg.gyro_bias_noise, cfg.acc_bias_noise = 0.001 ** 2, 0.01 ** 2
+    cfg.observation_noise = 0.035 ** 2
+    cfg.velocity = np.zeros(3)
+    cfg.velocity_cov, cfg.gyro_bias_cov, cfg.acc_bias_cov = 0.25, 0.01, 0.01
+    cfg.extrinsic_rotation_cov, cfg.extrinsic_translation_cov = 3.0462e-4, 2.5e-5
+    cfg.T_cn_cnm1 = np.array([
+        [0.999997256477881, 0.002312067192424, 0.000376008102415, -0.110073808127187],
+        [-0.002317135723281, 0.999898048506644, 0.014089835846648, 0.000399121547014],
+        [-0.000343393120525, -0.014090668452714, 0.999900662637729, -0.000853702503357],
+        [0, 0, 0, 1.0]])
+    cfg.T_imu_body = np.identity(4)
+    return cfg
+
+
 def config_default():            # the reference's shipped config: 4x5 cells, cap 100
     return FrontEndConfig()
 

@@ -19,6 +19,8 @@ EXPORTS = (
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
     'avb_undistort_points', 'avb_distort_points', 'avb_two_point_ransac', 'avb_last_frame_ms', 'avb_kernels_per_frame',
     'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device', 'avb_get_geometry',
+    'avb_store_create', 'avb_store_destroy', 'avb_store_num_frames', 'avb_store_bytes', 'avb_store_upload',
+    'avb_store_image', 'avb_process_frame_gather',
 )
 
 
@@ -101,6 +103,16 @@ def load():
     lib.avb_cuda_stream.restype = C.c_void_p
     lib.avb_time_pyramid.argtypes = [vp, ip, C.POINTER(C.c_float)]
     lib.avb_profile_frame_device.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    lib.avb_store_create.argtypes = [ip, ip, ip, ip, C.POINTER(vp)]
+    lib.avb_store_destroy.argtypes = [vp]
+    lib.avb_store_destroy.restype = None
+    lib.avb_store_num_frames.argtypes = [vp]
+    lib.avb_store_bytes.argtypes = [vp]
+    lib.avb_store_bytes.restype = C.c_size_t
+    lib.avb_store_upload.argtypes = [vp, ip, u8p, u8p, ip]
+    lib.avb_store_image.argtypes = [vp, ip, ip]
+    lib.avb_store_image.restype = C.c_void_p
+    lib.avb_process_frame_gather.argtypes = [vp, vp, f64p, f64p]
     if lib.avb_abi_version() != 2:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
@@ -122,6 +134,49 @@ def stereo_geometry(cfg):
     x, y, z = t01
     E = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]]) @ R01
     return R01, E
+
+
+class FrameStore:
+    """A decoded stereo sequence resident in HBM (avb_store_*): uploaded once, read by every time-offset run of the
+    sequence (reference: each `main.py --offset` run re-reads its PNGs, streaming/dataset.py:101-117, 206-214)."""
+
+    def __init__(self, width, height, n_frames, device=0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        rc = self._lib.avb_store_create(int(device), int(width), int(height), int(n_frames), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f'avb_store_create failed ({rc}): no CUDA device, bad geometry (width % 16) or out of memory')
+        self.width, self.height, self.n_frames, self.device = int(width), int(height), int(n_frames), int(device)
+        self.timestamps = [None] * self.n_frames
+        # device addresses [frame][cam], looked up once: the per-step pointer table is a numpy fancy index
+        self.addr = np.array([[self._lib.avb_store_image(self._h, k, cam) for cam in (0, 1)]
+                              for k in range(self.n_frames)], dtype=np.uint64)
+
+    @property
+    def nbytes(self):
+        return int(self._lib.avb_store_bytes(self._h))
+
+    def upload(self, k, img0, img1, timestamp=None):
+        for im in (img0, img1):
+            if im.dtype != np.uint8 or im.shape != (self.height, self.width) or im.strides[1] != 1:
+                raise ValueError(f'frames must be ({self.height}, {self.width}) uint8 with unit column stride')
+        if img0.strides[0] != img1.strides[0]:
+            img0, img1 = np.ascontiguousarray(img0), np.ascontiguousarray(img1)
+        rc = self._lib.avb_store_upload(self._h, int(k), _ptr(img0), _ptr(img1), int(img0.strides[0]))
+        if rc != 0:
+            raise RuntimeError(f'avb_store_upload failed ({rc})')
+        self.timestamps[k] = timestamp
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.avb_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -213,6 +268,15 @@ class Context:
             self.staging[s, 0] = imgs0[s]
             self.staging[s, 1] = imgs1[s]
         self.process_staged(R_p_c0, R_p_c1)
+
+    def process_gather(self, image_addrs, R_p_c0=None, R_p_c1=None):
+        """One frame from device-resident images: image_addrs = uint64[S, 2] device addresses (FrameStore.addr rows)."""
+        tab = np.ascontiguousarray(image_addrs, dtype=np.uint64).reshape(-1)
+        if tab.size != 2 * self.S:
+            raise ValueError(f'expected {2 * self.S} image addresses')
+        R = None if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
+        R1 = None if (R is None or R_p_c1 is None) else np.ascontiguousarray(R_p_c1, dtype=np.float64).reshape(-1)
+        self._ck(self._lib.avb_process_frame_gather(self._h, _ptr(tab), _ptr(R), _ptr(R1)))
 
     def fill_rotations(self, block, R_p_c0=None, R_p_c1=None):
         """Rotation section of an input block: cam0_R_p_c / cam1_R_p_c per stream (None: identity / conjugated)."""

@@ -13,6 +13,7 @@ sequences x time offsets with a batch file (run.bat:4-12).  Streams share nothin
 """
 from __future__ import annotations
 
+import os
 from collections import defaultdict, namedtuple
 
 import numpy as np
@@ -27,6 +28,52 @@ def shard_streams(n_streams: int, world: int, rank: int) -> list:
     if not (0 <= rank < world):
         raise ValueError('rank out of range')
     return list(range(rank, n_streams, world))
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(pci_bus_id: str, local_rank: int = 0, local_world: int = 1, sysfs: str = '/sys'):
+    """One process per GPU: keep the process (and with it the first-touch placement of its page-locked staging and
+    result blocks) on the host cores of the NUMA node the GPU hangs off, so the per-frame H2D copy and the result
+    block the last kernel writes into mapped host memory do not cross the socket interconnect.  Call it BEFORE the
+    context is created.  `pci_bus_id` is 'dddd:bb:dd.f' (cudaDeviceGetPCIBusId).  The node's allowed cores are dealt
+    to the ranks that share the node in contiguous slices.  Returns the cpu set bound to, or None when the topology
+    is unknown (no sysfs entry, node -1, no allowed core on the node): the affinity is then left untouched."""
+    try:
+        dev = os.path.join(sysfs, 'bus', 'pci', 'devices', pci_bus_id.lower())
+        node = int(open(os.path.join(dev, 'numa_node')).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(os.path.join(sysfs, 'devices', 'system', 'node', f'node{node}', 'cpulist')).read())
+        allowed = sorted(cpus & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        # ranks sharing this node: assume GPUs are spread evenly over the nodes that have any
+        nodes = set()
+        for d in os.listdir(os.path.join(sysfs, 'bus', 'pci', 'devices')):
+            try:
+                base = os.path.join(sysfs, 'bus', 'pci', 'devices', d)
+                if open(os.path.join(base, 'vendor')).read().strip() == '0x10de' and \
+                        open(os.path.join(base, 'class')).read().strip().startswith('0x0302'):
+                    nodes.add(int(open(os.path.join(base, 'numa_node')).read()))
+            except (OSError, ValueError):
+                continue
+        per_node = max(1, -(-local_world // max(1, len(nodes))))
+        slot = local_rank % per_node
+        share = max(1, len(allowed) // per_node)
+        mine = allowed[slot * share:(slot + 1) * share] or allowed
+        os.sched_setaffinity(0, mine)
+        return set(mine)
+    except (OSError, ValueError):
+        return None
 
 
 class MultiStreamFrontEnd:
@@ -72,6 +119,36 @@ class MultiStreamFrontEnd:
                     nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = hdr[3], hdr[4], hdr[5]
             self.prev_msg[s] = m.cam0_msg
             out.append(feature_msg(m.cam0_msg.timestamp, feats))
+        self.first_frame = False
+        return out
+
+    def step_from_store(self, image_addrs, cam0_msgs):
+        """One frame per stream from HBM-resident images (FrameStore.addr rows: uint64[S, 2]); cam0_msgs[s] carries the
+        frame's timestamp (the IMU window reads nothing else).  Returns per stream (timestamp, ids int64[n], meas
+        float64[n, 4]) -- copies of the result block, no per-feature Python objects: the form a sweep hands to its
+        estimator processes."""
+        if len(cam0_msgs) != self.S:
+            raise ValueError(f'expected {self.S} frames')
+        R0 = R1 = None
+        if not self.first_frame:
+            for s, m in enumerate(cam0_msgs):
+                imu = self.imu[s]
+                imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = self.prev_msg[s], m
+                self._R[0, s], self._R[1, s] = imu.integrate_imu_data()
+            R0, R1 = self._R[0], (self._R[1] if self.ctx.ransac else None)
+        self.ctx.process_gather(image_addrs, R0, R1)
+        out = []
+        for s, m in enumerate(cam0_msgs):
+            hdr, ids, meas = self.ctx.result(s)
+            self.next_feature_id[s] = int(hdr['next_feature_id'])
+            if not self.first_frame:
+                nf = self.num_features[s]
+                nf['before_tracking'] = int(hdr['before_tracking'])
+                if nf['before_tracking']:
+                    nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = \
+                        int(hdr['after_tracking']), int(hdr['after_matching']), int(hdr['after_ransac'])
+            self.prev_msg[s] = m
+            out.append((m.timestamp, ids.copy(), meas.copy()))
         self.first_frame = False
         return out
 
