@@ -154,6 +154,10 @@ const uint8_t* avb_store_image(const avb_store* store, int k, int cam);
  * input block; rotations as in avb_process_frame.  Blocks until the results are in host memory. */
 int  avb_process_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, const double* R_p_c0,
                               const double* R_p_c1);
+/* Enqueue-only variant (avb_sync waits): the caller prepares the next step (IMU windows of every stream) while
+ * this one runs.  One frame in flight per context: call avb_sync before the next enqueue or any result read. */
+int  avb_enqueue_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, const double* R_p_c0,
+                              const double* R_p_c1);
 
 /* Results of the last frame for stream s (pointers into pinned host memory, valid until the
  * next avb_process_frame): ids[n], meas[n*4] = u0 v0 u1 v1 (normalized coords; u0,v0 carry the

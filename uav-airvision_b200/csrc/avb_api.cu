@@ -609,6 +609,11 @@ extern "C" int avb_process_frame_gather(avb_ctx* c, const uint8_t* const* d_imag
     return gather_frame(c, d_images, R_p_c0, R_p_c1, true);
 }
 
+extern "C" int avb_enqueue_frame_gather(avb_ctx* c, const uint8_t* const* d_images, const double* R_p_c0,
+                                        const double* R_p_c1) {
+    return gather_frame(c, d_images, R_p_c0, R_p_c1, false);
+}
+
 extern "C" int avb_sync(avb_ctx* c) {
     if (!c) return AVB_E_INVALID;
     CK(cudaStreamSynchronize(c->st));

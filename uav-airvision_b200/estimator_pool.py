@@ -29,14 +29,14 @@ def feed(est, imu_rows, ts, ids, meas):
     return est.feature_callback(feature_msg(float(ts), feats))
 
 
-def _worker(conn, config, streams):
+def _worker(inbox, conn, config, streams):
     from msckf import MSCKF
     ests = {s: MSCKF(config, outfile=False) for s in streams}
     traj = {s: [] for s in streams}
     busy = 0.0
     frames = 0
     while True:
-        batch = conn.recv()
+        batch = inbox.get()
         if batch is None:
             break
         t0 = time.perf_counter()
@@ -54,31 +54,35 @@ def _worker(conn, config, streams):
 
 class EstimatorPool:
     """`n_streams` MSCKF instances spread over `n_workers` processes.  `push_step` queues one frame of every stream
-    and returns at once (the pipes give back-pressure when the workers fall behind); `finish` collects per stream the
-    published trajectory rows (t, x, y, z, qx, qy, qz, qw: the reference's output-file columns, msckf.py:152-160)."""
+    and returns at once: every worker has its own inbox `depth` steps deep (filter time per frame varies 3x around its
+    median, so workers must be allowed to drift apart; a full inbox blocks the producer, which is the back-pressure).
+    `finish` collects per stream the published trajectory rows (t, x, y, z, qx, qy, qz, qw: the reference's output-file
+    columns, msckf.py:152-160)."""
 
-    def __init__(self, config, n_streams, n_workers, method='spawn'):
+    def __init__(self, config, n_streams, n_workers, method='spawn', depth=64):
         self.S, self.P = int(n_streams), max(1, min(int(n_workers), int(n_streams)))
         ctx = mp.get_context(method)
-        self.conns, self.procs = [], []
+        self.conns, self.procs, self.inboxes = [], [], []
         for w in range(self.P):
-            parent, child = ctx.Pipe()
-            p = ctx.Process(target=_worker, args=(child, config, list(range(w, self.S, self.P))), daemon=True)
+            parent, child = ctx.Pipe(duplex=False)
+            inbox = ctx.Queue(maxsize=int(depth))
+            p = ctx.Process(target=_worker, args=(inbox, child, config, list(range(w, self.S, self.P))), daemon=True)
             p.start()
             child.close()
             self.conns.append(parent)
+            self.inboxes.append(inbox)
             self.procs.append(p)
 
     def push_step(self, items):
         """items[s] = (imu_rows float64[m, 7], timestamp, ids int64[n], meas float64[n, 4])."""
         if len(items) != self.S:
             raise ValueError(f'expected {self.S} items')
-        for w, conn in enumerate(self.conns):
-            conn.send([(s, *items[s]) for s in range(w, self.S, self.P)])
+        for w, inbox in enumerate(self.inboxes):
+            inbox.put([(s, *items[s]) for s in range(w, self.S, self.P)])
 
     def finish(self):
-        for conn in self.conns:
-            conn.send(None)
+        for inbox in self.inboxes:
+            inbox.put(None)
         traj, busy, frames = {}, [], 0
         for conn in self.conns:
             r = conn.recv()

@@ -20,7 +20,7 @@ EXPORTS = (
     'avb_undistort_points', 'avb_distort_points', 'avb_two_point_ransac', 'avb_last_frame_ms', 'avb_kernels_per_frame',
     'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device', 'avb_get_geometry',
     'avb_store_create', 'avb_store_destroy', 'avb_store_num_frames', 'avb_store_bytes', 'avb_store_upload',
-    'avb_store_image', 'avb_process_frame_gather',
+    'avb_store_image', 'avb_process_frame_gather', 'avb_enqueue_frame_gather',
 )
 
 
@@ -113,6 +113,7 @@ def load():
     lib.avb_store_image.argtypes = [vp, ip, ip]
     lib.avb_store_image.restype = C.c_void_p
     lib.avb_process_frame_gather.argtypes = [vp, vp, f64p, f64p]
+    lib.avb_enqueue_frame_gather.argtypes = [vp, vp, f64p, f64p]
     if lib.avb_abi_version() != 2:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
@@ -269,14 +270,16 @@ class Context:
             self.staging[s, 1] = imgs1[s]
         self.process_staged(R_p_c0, R_p_c1)
 
-    def process_gather(self, image_addrs, R_p_c0=None, R_p_c1=None):
-        """One frame from device-resident images: image_addrs = uint64[S, 2] device addresses (FrameStore.addr rows)."""
+    def process_gather(self, image_addrs, R_p_c0=None, R_p_c1=None, wait=True):
+        """One frame from device-resident images: image_addrs = uint64[S, 2] device addresses (FrameStore.addr rows).
+        wait=False only enqueues (sync() before reading results or enqueuing again)."""
         tab = np.ascontiguousarray(image_addrs, dtype=np.uint64).reshape(-1)
         if tab.size != 2 * self.S:
             raise ValueError(f'expected {2 * self.S} image addresses')
         R = None if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
         R1 = None if (R is None or R_p_c1 is None) else np.ascontiguousarray(R_p_c1, dtype=np.float64).reshape(-1)
-        self._ck(self._lib.avb_process_frame_gather(self._h, _ptr(tab), _ptr(R), _ptr(R1)))
+        fn = self._lib.avb_process_frame_gather if wait else self._lib.avb_enqueue_frame_gather
+        self._ck(fn(self._h, _ptr(tab), _ptr(R), _ptr(R1)))
 
     def fill_rotations(self, block, R_p_c0=None, R_p_c1=None):
         """Rotation section of an input block: cam0_R_p_c / cam1_R_p_c per stream (None: identity / conjugated)."""

@@ -89,6 +89,7 @@ class MultiStreamFrontEnd:
         self.next_feature_id = [0] * self.S
         self.num_features = [defaultdict(int) for _ in range(self.S)]
         self._R = np.empty((2, self.S, 3, 3))          # [cam][stream]; cam 1 is passed on only with RANSAC on
+        self._steps_prepared, self._prepared, self._in_flight = 0, None, None     # store-fed steps (sweep.py)
 
     def close(self):
         self.ctx.close()
@@ -126,19 +127,43 @@ class MultiStreamFrontEnd:
         """One frame per stream from HBM-resident images (FrameStore.addr rows: uint64[S, 2]); cam0_msgs[s] carries the
         frame's timestamp (the IMU window reads nothing else).  Returns per stream (timestamp, ids int64[n], meas
         float64[n, 4]) -- copies of the result block, no per-feature Python objects: the form a sweep hands to its
-        estimator processes."""
+        estimator processes.  = prepare_step + begin_step_from_store + end_step_from_store, which a driver may
+        interleave so that the host work of step k+1 runs while the GPU works on step k."""
+        self.prepare_step(cam0_msgs)
+        self.begin_step_from_store(image_addrs)
+        return self.end_step_from_store()
+
+    def prepare_step(self, cam0_msgs):
+        """Host half of a step: the IMU window of every stream (imu_processor.py:28-67) -> the camera rotations of the
+        step.  Touches host state only, so it may run while the previous step is still on the GPU."""
         if len(cam0_msgs) != self.S:
             raise ValueError(f'expected {self.S} frames')
-        R0 = R1 = None
-        if not self.first_frame:
+        R = None
+        if self._steps_prepared > 0:
+            R = np.empty((2, self.S, 3, 3))
             for s, m in enumerate(cam0_msgs):
                 imu = self.imu[s]
                 imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = self.prev_msg[s], m
-                self._R[0, s], self._R[1, s] = imu.integrate_imu_data()
-            R0, R1 = self._R[0], (self._R[1] if self.ctx.ransac else None)
-        self.ctx.process_gather(image_addrs, R0, R1)
-        out = []
+                R[0, s], R[1, s] = imu.integrate_imu_data()
         for s, m in enumerate(cam0_msgs):
+            self.prev_msg[s] = m
+        self._steps_prepared += 1
+        self._prepared = (list(cam0_msgs), R)
+
+    def begin_step_from_store(self, image_addrs):
+        """Enqueues gather + frame chain of the prepared step; returns at once."""
+        msgs, R = self._prepared
+        self._prepared = None
+        R0, R1 = (None, None) if R is None else (R[0], R[1] if self.ctx.ransac else None)
+        self.ctx.process_gather(image_addrs, R0, R1, wait=False)
+        self._in_flight = msgs
+
+    def end_step_from_store(self):
+        """Waits for the step begun last and returns its results (see step_from_store)."""
+        msgs, self._in_flight = self._in_flight, None
+        self.ctx.sync()
+        out = []
+        for s, m in enumerate(msgs):
             hdr, ids, meas = self.ctx.result(s)
             self.next_feature_id[s] = int(hdr['next_feature_id'])
             if not self.first_frame:
@@ -147,7 +172,6 @@ class MultiStreamFrontEnd:
                 if nf['before_tracking']:
                     nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = \
                         int(hdr['after_tracking']), int(hdr['after_matching']), int(hdr['after_ransac'])
-            self.prev_msg[s] = m
             out.append((m.timestamp, ids.copy(), meas.copy()))
         self.first_frame = False
         return out

@@ -107,34 +107,47 @@ def run_sweep(config, sequences, offsets_s, device=0, n_steps=None, estimator_wo
     launches = fe.ctx.kernels_per_frame() + (2 * S + 255) // 256       # frame chain + gather launches
     imu_pos = [r.first_imu for r in runs]
     n_feat = np.zeros((S, steps), dtype=np.int32)
-    addrs = np.empty((S, 2), dtype=np.uint64)
     t_mark = None
     fe_s = 0.0
+    def host_side(k):
+        """IMU messages up to frame k of every run -> the front end's buffers; the step's frame refs and addresses."""
+        refs, spans = [], []
+        a = np.empty((S, 2), dtype=np.uint64)
+        for s, r in enumerate(runs):
+            seq = sequences[r.sequence]
+            idx = r.first_frame + k
+            j0 = imu_pos[s]
+            j1 = int(np.searchsorted(seq.imu_rows[:, 0], seq.timestamps[idx], side='right'))
+            for m in seq.imu_msgs[j0:j1]:
+                fe.imu_callback(s, m)
+            imu_pos[s] = j1
+            spans.append((j0, j1))
+            refs.append(seq.frame_refs[idx])
+            a[s] = seq.store.addr[idx]
+        fe.prepare_step(refs)
+        return a, spans
+
     try:
+        # software pipeline: while the GPU runs step k, the host prepares step k+1 (IMU windows) and hands the results
+        # of step k-1 to the estimators
+        addrs, spans = host_side(0)
+        fe.begin_step_from_store(addrs)
         for k in range(steps):
             if k == warmup_steps:
                 t_mark = time.perf_counter()
-            refs, spans = [], []
-            for s, r in enumerate(runs):
-                seq = sequences[r.sequence]
-                idx = r.first_frame + k
-                ts = seq.timestamps[idx]
-                j0 = imu_pos[s]
-                j1 = int(np.searchsorted(seq.imu_rows[:, 0], ts, side='right'))
-                for m in seq.imu_msgs[j0:j1]:
-                    fe.imu_callback(s, m)
-                imu_pos[s] = j1
-                spans.append((j0, j1))
-                refs.append(seq.frame_refs[idx])
-                addrs[s] = seq.store.addr[idx]
+            nxt = host_side(k + 1) if k + 1 < steps else None
             t0 = time.perf_counter()
-            out = fe.step_from_store(addrs, refs)
+            out = fe.end_step_from_store()
             fe_s += time.perf_counter() - t0 if k >= warmup_steps else 0.0
+            if nxt is not None:
+                fe.begin_step_from_store(nxt[0])
             for s, (ts, ids, meas) in enumerate(out):
                 n_feat[s, k] = len(ids)
             if pool is not None:
                 pool.push_step([(sequences[r.sequence].imu_rows[j0:j1], ts, ids, meas)
                                 for r, (j0, j1), (ts, ids, meas) in zip(runs, spans, out)])
+            if nxt is not None:
+                spans = nxt[1]
         t_fe_done = time.perf_counter()
         traj, pstats = (None, None)
         if pool is not None:
@@ -148,6 +161,6 @@ def run_sweep(config, sequences, offsets_s, device=0, n_steps=None, estimator_wo
     wall = t_end - (t_mark if t_mark is not None else t_end)
     return {'runs': runs, 'steps': steps, 'timed_steps': timed, 'streams': S, 'features': n_feat,
             'trajectories': traj, 'estimator': pstats, 'kernels_per_step': launches,
-            'wall_s': wall, 'front_end_call_s': fe_s, 'front_end_done_s': t_fe_done - (t_mark or t_fe_done),
+            'wall_s': wall, 'front_end_wait_s': fe_s, 'front_end_done_s': t_fe_done - (t_mark or t_fe_done),
             'frames_per_s': S * timed / wall if wall > 0 and timed > 0 else 0.0,
             'features_per_s': float(n_feat[:, warmup_steps:].sum()) / wall if wall > 0 and timed > 0 else 0.0}
