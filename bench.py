@@ -255,7 +255,9 @@ def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_o
     torch.cuda.synchronize()
     upload_s = time.perf_counter() - t0
     store_bytes = sum(q.store.nbytes for q in seqs)
-    workers = args.c5_workers if args.c5_workers > 0 else max(1, len(cores) - 1)
+    # the ranks of a box share its cores unless each is bound to its own NUMA node
+    share = len(cores) if bound else len(cores) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+    workers = args.c5_workers if args.c5_workers > 0 else max(1, share - 1)
     warm = 2
     sampler = ClockSampler(local) if rank == 0 else None
     # front end alone (what the GPU side of the sweep sustains from the HBM store, results as arrays on the host)
@@ -273,6 +275,7 @@ def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_o
     frames_total = sum_over_ranks(S * timed)
     feats_total = sum_over_ranks(float(full['features'][:, warm:].sum()))
     published = sum_over_ranks(float(sum(len(t) for t in full['trajectories'])))
+    upload_max = max_over_ranks(upload_s)
     # accuracy of the offset-0 run of this rank's first sequence against its ground truth (sanity, not a parity gate)
     ate = None
     tr = full['trajectories'][0]
@@ -304,7 +307,7 @@ def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_o
             'estimator': {'worker_busy_s': [round(b, 3) for b in busy],
                           'ms_per_frame': 1e3 * float(np.sum(busy)) / max(full['estimator']['frames'], 1),
                           'note': 'host MSCKF (uav-airvision_b200/msckf.py) in worker processes; it bounds this leg'},
-            'e2e': {'value': frames_total / (wall + max_over_ranks(upload_s)), 'unit': UNIT,
+            'e2e': {'value': frames_total / (wall + upload_max), 'unit': UNIT,
                     'h2d_bytes_per_step': int(len(mine) * n_frames * img_bytes / args.c5_steps),
                     'd2h_bytes_per_step': int(S * (48 + 300 * 40)),
                     'note': 'includes the one-time upload of every sequence frame into the store (amortised over its offset runs); '

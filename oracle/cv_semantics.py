@@ -358,3 +358,77 @@ def distort_radtan(pts, intr, dist):
     xd = x * cdist + p1 * a1 + p2 * a2
     yd = y * cdist + p1 * a3 + p2 * a1
     return np.stack([xd * fx + cx, yd * fy + cy], axis=1).astype(out_dtype)
+
+
+# --------------------------------------------------------------------------------------
+# A.5b  equidistant (fisheye) undistort / distort -- camera_model.py:41-43, 69-70
+# --------------------------------------------------------------------------------------
+
+def undistort_equidistant(pts, intr, dist, R=None):
+    """cv2.fisheye.undistortPoints(pts, K, D, R, P=I) (OpenCV 4.13 calib3d/fisheye.cpp): theta_d = |(p - c) / f| clipped
+    to pi/2, Newton on theta (1 + k1 th^2 + k2 th^4 + k3 th^6 + k4 th^8) = theta_d, at most 10 steps, stop when a step is
+    smaller than 1e-8; scale = tan(theta) / theta_d; then R and the perspective divide.  A point that does not converge
+    or whose theta flips sign becomes (-1e6, -1e6).  f64 arithmetic, output dtype = input dtype."""
+    pts = np.asarray(pts)
+    out_dtype = pts.dtype if pts.dtype in (np.float32, np.float64) else np.float64
+    p = pts.astype(np.float64).reshape(-1, 2)
+    fx, fy, cx, cy = (float(v) for v in intr)
+    k = [float(v) for v in dist[:4]]
+    Rm = np.eye(3) if R is None else np.asarray(R, dtype=np.float64)
+    out = np.empty_like(p)
+    for i in range(len(p)):
+        wx, wy = (p[i, 0] - cx) / fx, (p[i, 1] - cy) / fy
+        theta_d = min(max(-np.pi / 2.0, float(np.sqrt(wx * wx + wy * wy))), np.pi / 2.0)
+        converged, theta, scale = False, theta_d, 0.0
+        if abs(theta_d) > 1e-8:
+            for _ in range(10):
+                t2 = theta * theta
+                t4 = t2 * t2
+                t6 = t4 * t2
+                t8 = t6 * t2
+                k0t2, k1t4, k2t6, k3t8 = k[0] * t2, k[1] * t4, k[2] * t6, k[3] * t8
+                fix = (theta * (1 + k0t2 + k1t4 + k2t6 + k3t8) - theta_d) / (1 + 3 * k0t2 + 5 * k1t4 + 7 * k2t6 + 9 * k3t8)
+                theta = theta - fix
+                if abs(fix) < 1e-8:
+                    converged = True
+                    break
+            scale = float(np.tan(theta)) / theta_d
+        else:
+            converged = True
+        flipped = (theta_d < 0 and theta > 0) or (theta_d > 0 and theta < 0)
+        if converged and not flipped:
+            ux, uy = wx * scale, wy * scale
+            X = Rm[0, 0] * ux + Rm[0, 1] * uy + Rm[0, 2]
+            Y = Rm[1, 0] * ux + Rm[1, 1] * uy + Rm[1, 2]
+            Wv = Rm[2, 0] * ux + Rm[2, 1] * uy + Rm[2, 2]
+            out[i] = (X / Wv, Y / Wv)
+        else:
+            out[i] = (-1000000.0, -1000000.0)
+    return out.astype(out_dtype)
+
+
+def distort_equidistant(pts, intr, dist):
+    """cv2.fisheye.distortPoints(pts, K, D): theta = atan(r), theta_d = theta (1 + k1 th^2 + ... + k4 th^8) evaluated
+    as theta + k1 th^3 + k2 th^5 + k3 th^7 + k4 th^9, scaled by 1/r (1 when r <= 1e-8)."""
+    pts = np.asarray(pts)
+    out_dtype = pts.dtype if pts.dtype in (np.float32, np.float64) else np.float64
+    p = pts.astype(np.float64).reshape(-1, 2)
+    fx, fy, cx, cy = (float(v) for v in intr)
+    k = [float(v) for v in dist[:4]]
+    out = np.empty_like(p)
+    for i in range(len(p)):
+        x, y = p[i]
+        r = float(np.sqrt(x * x + y * y))
+        theta = float(np.arctan(r))
+        t2 = theta * theta
+        t3 = t2 * theta
+        t4 = t2 * t2
+        t5 = t4 * theta
+        t6 = t3 * t3
+        t7 = t6 * theta
+        t8 = t4 * t4
+        t9 = t8 * theta
+        theta_d = theta + k[0] * t3 + k[1] * t5 + k[2] * t7 + k[3] * t9
+        cdist = theta_d / r if r > 1e-8 else 1.0
+        out[i] = (x * cdist * fx + cx, y * cdist * fy + cy)
+    return out.astype(out_dtype)

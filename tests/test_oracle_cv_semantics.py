@@ -170,3 +170,37 @@ def test_rodrigues_matches_cv2():
     g = np.random.default_rng(0)
     for v in list(g.normal(0, 0.05, (20, 3))) + [np.zeros(3), np.array([1e-20, 0, 0])]:
         assert np.abs(rodrigues(v) - cv2.Rodrigues(v)[0]).max() < 1e-15
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_equidistant_model_matches_cv2_fisheye(dtype):
+    """camera_model.py:41-43, 69-70 (cv2.fisheye.undistortPoints / distortPoints).  Groundwork only: the reference's
+    own distort_points raises under cv2 4.13 for this model (fisheye.distortPoints wants a 2-channel array and gets
+    (N, 2)), so its stereo matcher cannot run on an equidistant camera and libavb does not build the model."""
+    Ke = [461.6, 460.3, 362.7, 248.1]
+    De = np.array([-0.0091, 0.0666, -0.1028, 0.0612])
+    Km = np.array([[Ke[0], 0, Ke[2]], [0, Ke[1], Ke[3]], [0, 0, 1.0]])
+    g = np.random.default_rng(5)
+    pts = np.stack([g.uniform(-50, 800, 800), g.uniform(-50, 530, 800)], 1).astype(dtype)
+    pts[0] = (Ke[2], Ke[3])
+    R = cv2.Rodrigues(np.array([0.01, -0.02, 0.03]))[0]
+    tol = 0 if dtype == np.float32 else 4e-15
+    for rot in (None, R):
+        ref = cv2.fisheye.undistortPoints(pts.reshape(-1, 1, 2), Km, De, R=np.eye(3) if rot is None else rot,
+                                          P=np.eye(3)).reshape(-1, 2)
+        got = cs.undistort_equidistant(pts, Ke, De, rot)
+        assert got.dtype == ref.dtype == dtype and np.abs(ref - got).max() <= tol
+    und = cs.undistort_equidistant(pts, Ke, De)
+    ref = cv2.fisheye.distortPoints(und.reshape(-1, 1, 2), Km, De).reshape(-1, 2)
+    got = cs.distort_equidistant(und, Ke, De)
+    assert np.abs(ref - got).max() <= (0 if dtype == np.float32 else 1e-12)
+    assert np.abs(got.astype(np.float64) - pts).max() < (1e-3 if dtype == np.float32 else 1e-9)      # round trip
+    # points the Newton iteration cannot invert are flagged (-1e6, -1e6), exactly where cv2 flags them
+    hard = np.array([0.5, -2.0, 3.0, -4.0])
+    far = np.stack([g.uniform(-500, 1500, 300), g.uniform(-500, 1200, 300)], 1).astype(dtype)
+    ref = cv2.fisheye.undistortPoints(far.reshape(-1, 1, 2), Km, hard, R=np.eye(3), P=np.eye(3)).reshape(-1, 2)
+    got = cs.undistort_equidistant(far, Ke, hard)
+    assert np.array_equal(ref[:, 0] == -1e6, got[:, 0] == -1e6) and (got[:, 0] == -1e6).sum() > 100
+    assert np.abs(ref - got).max() <= tol
+    with pytest.raises(cv2.error):                            # the reference's call shape (camera_model.py:70)
+        cv2.fisheye.distortPoints(und, Km, De)

@@ -40,6 +40,8 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
     n = 60
     frames, j = [], 0
     for k in range(n):
+        if k == 30:                                           # a dropped frame: 2 x 10 + backlog IMU rows travel with frame 31
+            continue
         ts = float(z[f'f{k}_ts'][0])
         j1 = j
         while j1 < len(imu) and imu[j1, 0] <= ts:
@@ -54,7 +56,7 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
             want.append([r.timestamp, *r.pose.t, *est.imu_state.orientation])
     want = np.array(want)
     assert len(want) >= 30
-    pool = EstimatorPool(cfg, 3, 2)
+    pool = EstimatorPool(cfg, 3, 2, capacity=300, depth=4)
     try:
         for k, fr in enumerate(frames):
             # stream 2 lags one frame behind the others: streams are independent
@@ -62,7 +64,7 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
         traj, stats = pool.finish()
     finally:
         pool.close()
-    assert stats['frames'] == 3 * n and len(stats['worker_busy_s']) == 2
+    assert stats['frames'] == 3 * len(frames) and len(stats['worker_busy_s']) == 2
     assert np.array_equal(traj[0], want) and np.array_equal(traj[1], want)
     assert traj[2].shape[1] == 8 and len(traj[2]) >= len(want) - 2
     with pytest.raises(ValueError):
