@@ -40,8 +40,8 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
     n = 60
     frames, j = [], 0
     for k in range(n):
-        if k == 30:                                           # a dropped frame: 2 x 10 + backlog IMU rows travel with frame 31
-            continue
+        if 22 <= k < 38:                                      # 16 dropped frames: frame 38 arrives with 170 IMU rows, more
+            continue                                          # than a ring slot holds -> IMU-only slots travel ahead of it
         ts = float(z[f'f{k}_ts'][0])
         j1 = j
         while j1 < len(imu) and imu[j1, 0] <= ts:
@@ -55,7 +55,7 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
         if r is not None:
             want.append([r.timestamp, *r.pose.t, *est.imu_state.orientation])
     want = np.array(want)
-    assert len(want) >= 30
+    assert len(want) >= 20 and max(len(f[0]) for f in frames) > 128
     pool = EstimatorPool(cfg, 3, 2, capacity=300, depth=4)
     try:
         for k, fr in enumerate(frames):

@@ -29,6 +29,14 @@ if [[ $what == all || $what == ncu ]]; then
         -o $out/${tag}_s$S -f python tools/profile_target.py --streams $S --frames 5 > $out/${tag}_ncu_s$S.log 2>&1
     ncu -i $out/${tag}_s$S.ncu-rep --page raw --csv > $out/${tag}_s$S.raw.csv 2>/dev/null
   done
-  python tools/ncu_summary.py traffic $out/${tag}_s1.raw.csv > $out/${tag}_roofline_traffic_c2.json
+  python tools/ncu_summary.py traffic $out/${tag}_s1.raw.csv > $out/${tag}_traffic_cold_c2.json
+  # warm-cache DRAM traffic of the chain: counters only, caches left alone
+  for S in 1 64; do
+    timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum \
+        --launch-skip 24 -c 32 --csv --log-file $out/${tag}_warm_s$S.csv python tools/profile_target.py --streams $S --frames 7 \
+        > $out/${tag}_ncu_warm_s$S.log 2>&1
+  done
+  python tools/ncu_summary.py traffic_warm $out/${tag}_warm_s1.csv $out/${tag}_traffic_cold_c2.json > $out/${tag}_roofline_traffic_c2.json
+  python tools/ncu_summary.py traffic_warm $out/${tag}_warm_s64.csv > $out/${tag}_traffic_warm_s64.json
 fi
 ls -la $out | tail -20

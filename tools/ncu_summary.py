@@ -116,5 +116,36 @@ def traffic(path):
     print(json.dumps(out, indent=1))
 
 
+def traffic_warm(path, cold_json=None):
+    """DRAM bytes per steady-state frame chain from a `--cache-control none --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum` pass (one pass per kernel, caches NOT flushed between kernels: the traffic of the chain as it
+    runs, previous-frame pyramids and the just-copied input block still in L2).  With `cold_json` (output of `traffic`)
+    the result is merged into it."""
+    import json
+    per = defaultdict(lambda: [0, 0.0])
+    with open(path, newline='') as f:
+        lines = [l for l in f if l.startswith('"')]
+    ids = defaultdict(set)
+    for r in csv.DictReader(lines):
+        m = r.get('Metric Name')
+        if m not in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            continue
+        name = short(r['Kernel Name'])
+        v = float(r['Metric Value'].replace(',', ''))
+        v *= {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(r['Metric Unit'].lower(), 1)
+        per[name][1] += v
+        ids[name].add(r['ID'])
+    frames = max(len(ids.get('k_finish', [1])), 1)
+    # the capture window need not hold whole frames: average bytes per launch x that kernel's launches per frame
+    warm = {k: v[1] / len(ids[k]) * max(1, round(len(ids[k]) / frames)) for k, v in per.items()
+            if not k.startswith('k_stereo_buckets')}
+    out = json.load(open(cold_json)) if cold_json else {}
+    out['warm'] = {'frames_in_capture': frames, 'source': path, 'per_kernel_bytes_per_frame': warm,
+                   'bytes_per_frame': sum(warm.values()),
+                   'note': 'ncu --cache-control none, DRAM counters only (single pass, no replay): caches keep what the '
+                           'preceding copies and kernels left in them, as in the running chain'}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'raw': raw, 'traffic': traffic}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'raw': raw, 'traffic': traffic, 'traffic_warm': traffic_warm}[sys.argv[1]](*sys.argv[2:])
