@@ -71,6 +71,7 @@ def _worker(shm_name, depth, cap, filled, free, conn, config, streams):
         ests = [MSCKF(config, outfile=False) for _ in streams]
         traj = [[] for _ in streams]
         busy, frames, slot = 0.0, 0, 0
+        conn.send('ready')
         while True:
             filled.acquire()
             kind = int(ring.kind[slot])
@@ -124,6 +125,10 @@ class EstimatorPool:
             child.close()
             self.workers.append(dict(streams=streams, shm=shm, ring=ring, filled=filled, free=free, conn=parent, proc=p,
                                      slot=0))
+        for w in self.workers:          # interpreter start + imports + filter construction: ~1 s, all workers in parallel
+            if not w['conn'].poll(120) or w['conn'].recv() != 'ready':
+                self.close()
+                raise RuntimeError('estimator worker failed to start')
 
     def _post(self, w, kind, fill):
         w['free'].acquire()
@@ -166,15 +171,13 @@ class EstimatorPool:
     def finish(self):
         for w in self.workers:
             self._post(w, STOP, None)
+        self._stopped = True
         traj, busy, frames = {}, [], 0
         for w in self.workers:
             r = w['conn'].recv()
             traj.update(r['traj'])
             busy.append(r['busy_s'])
             frames += r['frames']
-        for w in self.workers:
-            w['proc'].join(timeout=10)
-        self._release()
         return [traj[s] for s in range(self.S)], {'worker_busy_s': busy, 'frames': frames}
 
     def _release(self):
@@ -189,7 +192,11 @@ class EstimatorPool:
                 w['shm'] = None
 
     def close(self):
+        """Joins the workers (they exit on their own after `finish`; anything still running after 5 s is terminated) and
+        frees the rings."""
         for w in self.workers:
+            if getattr(self, '_stopped', False):
+                w['proc'].join(timeout=5)
             if w['proc'].is_alive():
                 w['proc'].terminate()
                 w['proc'].join(timeout=5)
