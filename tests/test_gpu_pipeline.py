@@ -408,3 +408,41 @@ def test_sweep_from_hbm_store_equals_single_pipelines():
         q.close()
     print(f'sweep: 6 offset runs x {steps} steps from the HBM store equal 6 single pipelines; '
           f'{int(res["features"].sum())} features published')
+
+
+def test_live_front_end_plus_host_msckf_reproduces_the_reference_trajectory(golden_dir):
+    """The whole VIO on this box: rendered room sequence -> CUDA front end (stereo_callback) -> host MSCKF (msckf.py).
+    The front end must publish what the committed B200 dump holds (ids identical, coordinates to 1e-9: same kernels,
+    same arithmetic, any box), and the filter fed live must land on the trajectory the UNMODIFIED reference filter
+    produced from that dump (tests/golden/ref_msckf_traj.npz, tools/make_msckf_golden.py)."""
+    from frontend_config import with_filter_fields
+    from image_processing import ImageProcessor
+    from msckf import MSCKF
+    from tools.ate_parity import GRID, make_stream
+    n = 64
+    cfg = with_filter_fields(FrontEndConfig(**GRID))
+    z = np.load(os.path.join(golden_dir, 'ate_gpu_features.npz'))
+    want = np.load(os.path.join(golden_dir, 'ref_msckf_traj.npz'))['traj']
+    ip, est = ImageProcessor(cfg), MSCKF(cfg, outfile=False)
+    rows, k = [], 0
+    for kind, m in make_stream(n).events():
+        if kind == 'imu':
+            ip.imu_callback(m)
+            est.imu_callback(m)
+            continue
+        fm = ip.stereo_callback(m)
+        ids = np.array([f.id for f in fm.features], np.int64)
+        meas = np.array([[f.u0, f.v0, f.u1, f.v1] for f in fm.features], np.float64).reshape(-1, 4)
+        assert np.array_equal(ids, z[f'f{k}_ids']), f'frame {k}: ids differ from the committed B200 dump'
+        assert np.abs(meas - z[f'f{k}_meas']).max() < 1e-9
+        r = est.feature_callback(fm)
+        if r is not None:
+            rows.append([k, r.timestamp, *r.pose.t, *est.imu_state.orientation])
+        k += 1
+    ip.context.close()
+    got = np.array(rows)
+    ref = want[want[:, 0] < n]
+    assert len(got) == len(ref) > 30 and np.array_equal(got[:, 0], ref[:, 0])
+    dp, dq = np.abs(got[:, 2:5] - ref[:, 2:5]).max(), np.abs(got[:, 5:9] - ref[:, 5:9]).max()
+    print(f'live VIO on the GPU box: {len(got)} poses, max |dp| {dp:.3g} m, |dq| {dq:.3g} against the reference filter')
+    assert dp < 1e-6 and dq < 1e-6
