@@ -57,6 +57,18 @@ def workload(name):
     raise SystemExit(f'unknown workload {name}')
 
 
+def stage_bytes(w, h, max_level, S):
+    """Algorithmic HBM bytes of the image-scan stages for S streams: the input copy reads and writes
+    the block, every pyramid level l reads level l-1 and writes level l (both cameras), FAST reads cam0 once."""
+    px = [w * h]
+    lw, lh = w, h
+    for _ in range(max_level):
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+        px.append(lw * lh)
+    return {'input_copy': 2 * S * 2 * px[0], 'pyramid': 2 * S * sum(px[l - 1] + px[l] for l in range(1, max_level + 1)),
+            'clear+fast': S * px[0]}
+
+
 def algorithmic_bytes_per_frame(w, h, max_level, n_feat):
     """read both u8 inputs once + write pyramid levels 1..L once + 64 B per feature."""
     px, tot = w * h, 0
@@ -531,6 +543,8 @@ def main():
                  'streams_per_gpu': S, 'steps': KM, 'value': m_fps, 'unit': UNIT, 'ms_per_step': m_ms / KM,
                  'features_per_frame': nf / S, 'hbm_gbs': bpf * S * KM / (m_ms * 1e-3) / 1e9,
                  'stage_ms': {k_: round(v, 4) for k_, v in st.items()},
+                 'stage_hbm_gbs': {k_: round(b / (st[k_] * 1e-3) / 1e9, 1)
+                                   for k_, b in stage_bytes(width, height, cfg.pyramid_levels, S).items() if st.get(k_, 0) > 0},
                  'note': 'S time-offset runs of the sequence (stream s starts 2*s frames in), lock-stepped in one '
                          'context: every kernel launch covers all S streams; inputs resident in HBM'}
         del mblocks

@@ -31,11 +31,13 @@ if [[ $what == all || $what == ncu ]]; then
   done
   python tools/ncu_summary.py traffic $out/${tag}_s1.raw.csv > $out/${tag}_traffic_cold_c2.json
   # warm-cache DRAM traffic of the chain: counters only, caches left alone
-  for S in 1 64; do
-    timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum \
-        --launch-skip 24 -c 32 --csv --log-file $out/${tag}_warm_s$S.csv python tools/profile_target.py --streams $S --frames 7 \
-        > $out/${tag}_ncu_warm_s$S.log 2>&1
-  done
+  # S=1: 200 distinct frames (144 MB > L2, like bench.py), counters taken from frame 191 on; S=64: 7 steps of 46 MB
+  timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum \
+      --launch-skip 1527 -c 32 --csv --log-file $out/${tag}_warm_s1.csv python tools/profile_target.py --streams 1 --frames 200 \
+      > $out/${tag}_ncu_warm_s1.log 2>&1
+  timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum \
+      --launch-skip 24 -c 40 --csv --log-file $out/${tag}_warm_s64.csv python tools/profile_target.py --streams 64 --frames 7 \
+      > $out/${tag}_ncu_warm_s64.log 2>&1
   python tools/ncu_summary.py traffic_warm $out/${tag}_warm_s1.csv $out/${tag}_traffic_cold_c2.json > $out/${tag}_roofline_traffic_c2.json
   python tools/ncu_summary.py traffic_warm $out/${tag}_warm_s64.csv > $out/${tag}_traffic_warm_s64.json
 fi

@@ -19,7 +19,7 @@
 #define PB_W 160                    // box width: 16 left halo (alignment) + 2*PT_W + 16, multiple of 16 bytes
 #define PB_X 16                     // columns between the box start and the tile's first source column
 #define PB_H 36                     // box height (2*PT_H + 4)
-#define HB_PITCH 66                 // u16 pitch of the horizontal-pass buffer (bank spread)
+#define HB_PITCH 68                 // u16 pitch of the horizontal-pass buffer: rows 8-byte aligned for 64-bit accesses
 
 #define QT_W 16                     // pair kernel: tile of level l+1
 #define QT_H 8
@@ -55,6 +55,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {      // sum of 4 unsigned byte products + c
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Geom g,
                                                   const __grid_constant__ DevState d, int level /*dst*/, int parity) {
     __shared__ __align__(128) uint8_t tile[PB_H][PB_W];
@@ -81,40 +87,58 @@ __global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ CUtens
     }
     mbar_wait(&bar, 0);
 
-    // horizontal pass at the even source columns of this tile
+    // BORDER_REFLECT_101 in x: the two columns left of column 0 / right of column w-1 that the 5 taps can touch arrive
+    // as zeros from the TMA copy; tiles on the image border write the mirrored pixels there, so that the horizontal
+    // pass below needs no per-tap index arithmetic anywhere.
     const int dx0 = PT_W * blockIdx.x, dy0 = PT_H * blockIdx.y;
-    const bool inner_x = (2 * dx0 - 2 >= 0) && (2 * (dx0 + PT_W - 1) + 2 < ls.w);
-    for (int i = tid; i < PB_H * PT_W; i += 256) {
-        const int r = i / PT_W, x = i % PT_W;
-        const int sx = 2 * (dx0 + x);
-        int v = 0;
-        const uint8_t* row = tile[r];
-        if (inner_x) {
-            const uint8_t* q = row + (sx - x0);
-            v = q[-2] + 4 * q[-1] + 6 * q[0] + 4 * q[1] + q[2];
-        } else if (dx0 + x < ld.w) {
-            const int c0 = refl101(sx - 2, ls.w) - x0, c1 = refl101(sx - 1, ls.w) - x0, c2 = sx - x0;
-            const int c3 = refl101(sx + 1, ls.w) - x0, c4 = refl101(sx + 2, ls.w) - x0;
-            v = row[c0] + 4 * row[c1] + 6 * row[c2] + 4 * row[c3] + row[c4];
+    const bool left = blockIdx.x == 0, right = 2 * (dx0 + PT_W - 1) + 2 >= ls.w;
+    if (left || right) {
+        if (tid < PB_H * 4) {
+            const int r = tid >> 2, j = tid & 3;            // j: 0,1 left columns -2,-1; 2,3 right columns w, w+1
+            uint8_t* row = tile[r];
+            if (j < 2) {
+                if (left) row[PB_X - 2 + j] = row[PB_X + 2 - j];
+            } else if (right) {
+                const int c = ls.w + (j - 2);               // source column to fabricate: w or w+1 -> w-2 or w-3
+                if (c - x0 < PB_W) row[c - x0] = row[2 * ls.w - 2 - c - x0];
+            }
         }
-        hbuf[r][x] = (unsigned short)v;
+        __syncthreads();
+    }
+
+    // horizontal pass: a thread makes 4 adjacent outputs of one box row from 16 source bytes (aligned 32-bit shared
+    // loads, the [1 4 6 4 1] taps as byte dot products): out_k = sum_i w_i b[2k - 2 + i]
+    for (int i = tid; i < PB_H * (PT_W / 4); i += 256) {
+        const int r = i >> 4, x = (i & 15) * 4;
+        const unsigned* q = reinterpret_cast<const unsigned*>(&tile[r][2 * x + PB_X - 4]);      // bytes c-4 .. c+11, c = 2x + PB_X
+        const unsigned w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+        int o0 = dp4a_uu(w0, 0x04010000u, dp4a_uu(w1, 0x00010406u, 0));      // b[c-2] + 4 b[c-1] | 6 b[c] + 4 b[c+1] + b[c+2]
+        int o1 = dp4a_uu(w1, 0x04060401u, (int)(w2 & 0xffu));                // b[c] .. b[c+3] | b[c+4]
+        int o2 = dp4a_uu(w1, 0x04010000u, dp4a_uu(w2, 0x00010406u, 0));
+        int o3 = dp4a_uu(w2, 0x04060401u, (int)(w3 & 0xffu));
+        const int lim = ld.w - (dx0 + x);                   // outputs at and beyond the level's width stay zero
+        o0 = lim > 0 ? o0 : 0;
+        o1 = lim > 1 ? o1 : 0;
+        o2 = lim > 2 ? o2 : 0;
+        o3 = lim > 3 ? o3 : 0;
+        *reinterpret_cast<uint2*>(&hbuf[r][x]) = make_uint2((unsigned)o0 | ((unsigned)o1 << 16), (unsigned)o2 | ((unsigned)o3 << 16));
     }
     __syncthreads();
 
-    // vertical pass: thread -> 4 consecutive destination pixels of one row
+    // vertical pass: thread -> 4 consecutive destination pixels of one row, two per register: a column sum is at most
+    // 16 * 16 * 255 + 128 < 2^16, so the packed halves never carry into each other
     const int ry = tid >> 4, cx = (tid & 15) * 4;
     const int dy = dy0 + ry, dx = dx0 + cx;
     if (dy < ld.h && dx < ld.pitch) {
         const int sy = 2 * dy;
         const int r0 = refl101(sy - 2, ls.h) - y0, r1 = refl101(sy - 1, ls.h) - y0, r2 = sy - y0;
         const int r3 = refl101(sy + 1, ls.h) - y0, r4 = refl101(sy + 2, ls.h) - y0;
-        unsigned w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = cx + k;
-            const int v = hbuf[r0][x] + 4 * hbuf[r1][x] + 6 * hbuf[r2][x] + 4 * hbuf[r3][x] + hbuf[r4][x];
-            w |= (unsigned)((v + 128) >> 8) << (8 * k);
-        }
+        const uint2 a0 = *reinterpret_cast<const uint2*>(&hbuf[r0][cx]), a1 = *reinterpret_cast<const uint2*>(&hbuf[r1][cx]);
+        const uint2 a2 = *reinterpret_cast<const uint2*>(&hbuf[r2][cx]), a3 = *reinterpret_cast<const uint2*>(&hbuf[r3][cx]);
+        const uint2 a4 = *reinterpret_cast<const uint2*>(&hbuf[r4][cx]);
+        const unsigned lo = ((a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + 0x00800080u) >> 8) & 0x00ff00ffu;
+        const unsigned hi = ((a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + 0x00800080u) >> 8) & 0x00ff00ffu;
+        const unsigned w = __byte_perm(lo, hi, 0x6420);     // bytes lo.0, lo.2, hi.0, hi.2
         uint8_t* dst = pyr_slot(d, g, s, slot) + ld.off + (size_t)dy * ld.pitch + dx;
         *reinterpret_cast<unsigned*>(dst) = w;
     }
@@ -210,9 +234,20 @@ __global__ void __launch_bounds__(256) k_pyr_pair(const __grid_constant__ CUtens
     }
 }
 
+// The pair kernel trades redundant halo work for one launch less: right for a few streams (launch-latency bound), wrong
+// when the one-level kernel already fills the GPU at the pair's first level (many streams: it ran at 6 % of the HBM
+// rate there).
+static int pyramid_pair_level(const Geom& g) {
+    const int built = g.nlev - 1;                       // levels 1..built
+    if (built < 2) return 0;
+    const int l = built - 1;
+    const long ctas = (long)((g.lv[l].w + PT_W - 1) / PT_W) * ((g.lv[l].h + PT_H - 1) / PT_H) * 2 * g.S;
+    return ctas >= 148 * 4 ? 0 : l;
+}
+
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st) {
     const int built = g.nlev - 1;                       // levels 1..built
-    const int pair_at = built >= 2 ? built - 1 : 0;     // the pair kernel builds levels pair_at and pair_at + 1
+    const int pair_at = pyramid_pair_level(g);          // the pair kernel builds levels pair_at and pair_at + 1 (0: not used)
     for (int l = 1; l <= built; ++l) {
         if (l == pair_at) {
             dim3 grid((g.lv[l + 1].w + QT_W - 1) / QT_W, (g.lv[l + 1].h + QT_H - 1) / QT_H, 2 * g.S);
@@ -226,5 +261,5 @@ void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int p
 
 int avb_pyramid_launches(const Geom& g) {
     const int built = g.nlev - 1;
-    return built >= 2 ? built - 1 : built;
+    return pyramid_pair_level(g) ? built - 1 : built;
 }
