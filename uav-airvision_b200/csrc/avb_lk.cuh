@@ -124,9 +124,49 @@ __device__ __forceinline__ void lk_template(const uint8_t* __restrict__ img, int
                                             short (&tIx)[NPX], short (&tIy)[NPX], int& sA11, int& sA12, int& sA22) {
     const int y = ipy + L.row, x = ipx + L.c0;          // absolute position of this lane's first sample
     int up[NPX + 3], mid[NPX + 3], dn[NPX + 3];          // rows y-1, y, y+1; columns x-1 .. x+NPX+1
-    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y - 1, up);
-    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y, mid);
-    load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y + 1, dn);
+    if (LPR == 2 && NPX == 8 && ipx >= 1 && ipx + 18 <= cols && ipy >= 1 && ipy + 17 <= rows) {
+        // Warp-uniform: the 18 x 18 footprint lies inside the level.  A lane fetches only ITS row, as aligned 32-bit
+        // words (11 bytes from column x-1: at most 4 words), and takes the rows above and below from lanes -2 / +2;
+        // the first and the last row of lanes fetch the one row nobody owns.  A warp-wide byte load of 16 rows costs 16
+        // L1 wavefronts; this is 4 + 2 loads per template instead of 33 (the L1 data pipe was the busiest unit of the
+        // 64-stream LK kernels, and 3/4 of its wavefronts came from here).
+        const uint8_t* a = img + (size_t)y * pitch + (x - 1);
+        const unsigned o = (unsigned)(size_t)a & 3u, sh = o * 8u;
+        const unsigned* aw = reinterpret_cast<const unsigned*>((size_t)a & ~(size_t)3);
+        unsigned M[3], U[3], D[3];
+        {
+            const unsigned W0 = __ldg(aw), W1 = __ldg(aw + 1), W2 = __ldg(aw + 2), W3 = o >= 2 ? __ldg(aw + 3) : 0u;
+            M[0] = __funnelshift_r(W0, W1, sh);
+            M[1] = __funnelshift_r(W1, W2, sh);
+            M[2] = __funnelshift_r(W2, W3, sh);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            U[i] = __shfl_up_sync(0xffffffffu, M[i], LPR);
+            D[i] = __shfl_down_sync(0xffffffffu, M[i], LPR);
+        }
+        if (L.row == 0 || L.row == 15) {                 // rows ipy-1 and ipy+16: aligned like the lane's own row
+            const unsigned* ew = reinterpret_cast<const unsigned*>(
+                reinterpret_cast<const uint8_t*>(aw) + (L.row == 0 ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch));
+            const unsigned W0 = __ldg(ew), W1 = __ldg(ew + 1), W2 = __ldg(ew + 2), W3 = o >= 2 ? __ldg(ew + 3) : 0u;
+            const unsigned E0 = __funnelshift_r(W0, W1, sh), E1 = __funnelshift_r(W1, W2, sh), E2 = __funnelshift_r(W2, W3, sh);
+            if (L.row == 0) {
+                U[0] = E0, U[1] = E1, U[2] = E2;
+            } else {
+                D[0] = E0, D[1] = E1, D[2] = E2;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NPX + 3; ++k) {
+            up[k] = (int)((U[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            mid[k] = (int)((M[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            dn[k] = (int)((D[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        }
+    } else {
+        load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y - 1, up);
+        load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y, mid);
+        load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y + 1, dn);
+    }
     // Scharr derivative at (y, x+k), k = 0..NPX; zero outside the level
     unsigned dcur[NPX + 1], dnxt[NPX + 1];
     const bool yin = (y >= 0) && (y < rows);
