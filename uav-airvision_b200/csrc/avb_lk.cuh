@@ -124,7 +124,8 @@ __device__ __forceinline__ void lk_template(const uint8_t* __restrict__ img, int
                                             short (&tIx)[NPX], short (&tIy)[NPX], int& sA11, int& sA12, int& sA22) {
     const int y = ipy + L.row, x = ipx + L.c0;          // absolute position of this lane's first sample
     int up[NPX + 3], mid[NPX + 3], dn[NPX + 3];          // rows y-1, y, y+1; columns x-1 .. x+NPX+1
-    if (LPR == 2 && NPX == 8 && ipx >= 1 && ipx + 18 <= cols && ipy >= 1 && ipy + 17 <= rows) {
+    const bool inside = LPR == 2 && NPX == 8 && ipx >= 1 && ipx + 18 <= cols && ipy >= 1 && ipy + 17 <= rows;
+    if (inside) {
         // Warp-uniform: the 18 x 18 footprint lies inside the level.  A lane fetches only ITS row, as aligned 32-bit
         // words (11 bytes from column x-1: at most 4 words), and takes the rows above and below from lanes -2 / +2;
         // the first and the last row of lanes fetch the one row nobody owns.  A warp-wide byte load of 16 rows costs 16
@@ -167,34 +168,49 @@ __device__ __forceinline__ void lk_template(const uint8_t* __restrict__ img, int
         load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y, mid);
         load_row<NPX + 3>(img, cols, rows, pitch, x - 1, y + 1, dn);
     }
-    // Scharr derivative at (y, x+k), k = 0..NPX; zero outside the level
-    unsigned dcur[NPX + 1], dnxt[NPX + 1];
-    const bool yin = (y >= 0) && (y < rows);
+    // Scharr derivative at (y, x+k), k = 0..NPX, separably: dx = [3 10 3]^T (x) [-1 0 1], dy = [-1 0 1]^T (x) [3 10 3]
+    int sv[NPX + 3], tv[NPX + 3];
+#pragma unroll
+    for (int j = 0; j < NPX + 3; ++j) {
+        sv[j] = 3 * (up[j] + dn[j]) + 10 * mid[j];
+        tv[j] = dn[j] - up[j];
+    }
+    int dxc[NPX + 1], dyc[NPX + 1], dxn[NPX + 1], dyn[NPX + 1];
 #pragma unroll
     for (int k = 0; k <= NPX; ++k) {
-        int dx = 3 * (up[k + 2] - up[k]) + 10 * (mid[k + 2] - mid[k]) + 3 * (dn[k + 2] - dn[k]);
-        int dy = 3 * (dn[k] - up[k]) + 10 * (dn[k + 1] - up[k + 1]) + 3 * (dn[k + 2] - up[k + 2]);
-        const bool in = yin && (x + k >= 0) && (x + k < cols);
-        dx = in ? dx : 0;
-        dy = in ? dy : 0;
-        dcur[k] = ((unsigned)dx & 0xffffu) | ((unsigned)dy << 16);
+        dxc[k] = sv[k + 2] - sv[k];
+        dyc[k] = 3 * (tv[k] + tv[k + 2]) + 10 * tv[k + 1];
+    }
+    if (!inside) {                                       // zero outside the level (cv2's derivative image has no border)
+        const bool yin = (y >= 0) && (y < rows);
+#pragma unroll
+        for (int k = 0; k <= NPX; ++k) {
+            const bool in = yin && (x + k >= 0) && (x + k < cols);
+            dxc[k] = in ? dxc[k] : 0;
+            dyc[k] = in ? dyc[k] : 0;
+        }
     }
 #pragma unroll
-    for (int k = 0; k <= NPX; ++k) dnxt[k] = __shfl_down_sync(0xffffffffu, dcur[k], LPR);
+    for (int k = 0; k <= NPX; ++k) {                     // the row below, from lane + LPR
+        dxn[k] = __shfl_down_sync(0xffffffffu, dxc[k], LPR);
+        dyn[k] = __shfl_down_sync(0xffffffffu, dyc[k], LPR);
+    }
+    // lanes that only supply a row (npx == 0) interpolate their derivatives with zero weights: Ix = Iy = 0, which is what
+    // the iteration sums need from an inactive slot; the same for the one slot past a 7-pixel lane
+    const bool lane_on = L.npx > 0;
+    const int v00 = lane_on ? w00 : 0, v01 = lane_on ? w01 : 0, v10 = lane_on ? w10 : 0, v11 = lane_on ? w11 : 0;
     sA11 = sA12 = sA22 = 0;
 #pragma unroll
     for (int k = 0; k < NPX; ++k) {
         const int iv = (mid[k + 1] * w00 + mid[k + 2] * w01 + dn[k + 1] * w10 + dn[k + 2] * w11 + (1 << (LK_W_BITS - 6))) >>
                        (LK_W_BITS - 5);
-        const int dx00 = (short)(dcur[k] & 0xffff), dy00 = (int)dcur[k] >> 16;
-        const int dx01 = (short)(dcur[k + 1] & 0xffff), dy01 = (int)dcur[k + 1] >> 16;
-        const int dx10 = (short)(dnxt[k] & 0xffff), dy10 = (int)dnxt[k] >> 16;
-        const int dx11 = (short)(dnxt[k + 1] & 0xffff), dy11 = (int)dnxt[k + 1] >> 16;
-        int ixv = (dx00 * w00 + dx01 * w01 + dx10 * w10 + dx11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
-        int iyv = (dy00 * w00 + dy01 * w01 + dy10 * w10 + dy11 * w11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
-        const bool act = k < L.npx;
-        ixv = act ? ixv : 0;
-        iyv = act ? iyv : 0;
+        int ixv = (dxc[k] * v00 + dxc[k + 1] * v01 + dxn[k] * v10 + dxn[k + 1] * v11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+        int iyv = (dyc[k] * v00 + dyc[k + 1] * v01 + dyn[k] * v10 + dyn[k + 1] * v11 + (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+        if (k == NPX - 1) {
+            const bool act = L.npx == NPX || !lane_on;   // (inactive lanes are already zero)
+            ixv = act ? ixv : 0;
+            iyv = act ? iyv : 0;
+        }
         tI[k] = (short)iv;
         tIx[k] = (short)ixv;
         tIy[k] = (short)iyv;
