@@ -160,6 +160,8 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     g.min_eig = cfg->min_eig_threshold;
     const double eps = std::min(std::max(cfg->track_precision, 0.0), 10.0);
     g.eps2 = eps * eps;
+    g.eps2_lo = (float)(g.eps2 * 0.99999);      // formed here: in the kernels the compiler re-did this FP64 product every iteration
+    g.eps2_hi = (float)(g.eps2 * 1.00001);
     g.cam0 = {cfg->cam0_intrinsics[0], cfg->cam0_intrinsics[1], cfg->cam0_intrinsics[2], cfg->cam0_intrinsics[3],
               cfg->cam0_distortion[0], cfg->cam0_distortion[1], cfg->cam0_distortion[2], cfg->cam0_distortion[3]};
     g.cam1 = {cfg->cam1_intrinsics[0], cfg->cam1_intrinsics[1], cfg->cam1_intrinsics[2], cfg->cam1_intrinsics[3],

@@ -51,6 +51,7 @@ struct Geom {
     int max_iter;
     double min_eig;
     double eps2;                   // (track_precision)^2 in double, like criteria.epsilon
+    float eps2_lo, eps2_hi;        // (float)(eps2 * (1 -+ 1e-5)): band outside which the float estimate of |delta|^2 decides
     CamModel cam0, cam1;
     double R01[9];                 // R_cam0_to_cam1
     double E[9];                   // essential

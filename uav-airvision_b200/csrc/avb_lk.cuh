@@ -633,8 +633,8 @@ __device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevSta
     prm.max_iter = g.max_iter;
     prm.min_eig = g.min_eig;
     prm.eps2 = g.eps2;
-    prm.eps2_lo = (float)(g.eps2 * 0.99999);
-    prm.eps2_hi = (float)(g.eps2 * 1.00001);
+    prm.eps2_lo = g.eps2_lo;
+    prm.eps2_hi = g.eps2_hi;
     ChainResult r;
     r.tracked = true;
     r.matched = false;

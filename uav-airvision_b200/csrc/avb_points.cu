@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_klt_points(const __gri
     prm.max_iter = g.max_iter;
     prm.min_eig = g.min_eig;
     prm.eps2 = g.eps2;
-    prm.eps2_lo = (float)(g.eps2 * 0.99999);
-    prm.eps2_hi = (float)(g.eps2 * 1.00001);
+    prm.eps2_lo = g.eps2_lo;
+    prm.eps2_hi = g.eps2_hi;
     const PyrView A = pyr_view(d, g, s, slot_from), B = pyr_view(d, g, s, slot_to);
     float ox, oy;
     int flip = 0;
