@@ -608,9 +608,12 @@ def main():
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if 'warm' in tj:            # the chain as it runs (caches left alone); the cold-cache replay figure beside it
-                traffic = float(tj['warm']['bytes_per_frame'])
-                traffic_src = (f"profiles/{os.path.basename(tpath)} warm: {tj['warm'].get('note', '')}; cold-cache replay "
-                               f"(--set full, caches flushed before every kernel): {float(tj['bytes_per_frame']):.0f} B")
+                traffic = float(tj['warm']['bytes_per_frame']) + float(bb)
+                traffic_src = (f"profiles/{os.path.basename(tpath)}: {float(tj['warm']['bytes_per_frame']):.0f} B by the kernels "
+                               f"(ncu --cache-control none, DRAM counters of the running chain, 200 distinct frames: the kernels "
+                               f"find the just-copied input block and both pyramids in L2) + {int(bb)} B read by the copy engine "
+                               f"that places the frame's input block; cold-cache replay of the same kernels (--set full, caches "
+                               f"flushed before every kernel): {float(tj['bytes_per_frame']):.0f} B")
             else:
                 traffic, traffic_src = float(tj['bytes_per_frame']), f"profiles/{os.path.basename(tpath)} ({tj.get('note', '')})"
         kernel_stages = {k_: v for k_, v in stage_ms.items() if k_ not in ('input_copy', 'result_copy')}

@@ -37,6 +37,11 @@ struct avb_ctx {
     int s_cap = 0;
     std::string err;
     float last_ms = 0.f;
+    static constexpr int PIN_CACHE = 8;   // is_page_locked: recently seen caller buffers
+    uintptr_t pin_base[PIN_CACHE] = {};
+    size_t pin_len[PIN_CACHE] = {};
+    bool pin_yes[PIN_CACHE] = {};
+    unsigned pin_next = 0;
 };
 
 static int fail(avb_ctx* c, int code, const char* fmt, ...) {
@@ -398,6 +403,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     cudaEvent_t ev[10];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(c->st));
+    CK(cudaEventRecord(c->ev_t0, c->st));
     CK(cudaEventRecord(ev[0], c->st));
     CK(cudaMemcpyAsync(c->d.in[p], d_block, in_block_bytes(g), cudaMemcpyDeviceToDevice, c->st));
     CK(cudaEventRecord(ev[1], c->st));
@@ -418,10 +424,10 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     CK(cudaEventRecord(ev[8], c->st));
     if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev[9], c->st));
+    CK(cudaEventRecord(c->ev_t1, c->st));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
     for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
-    cudaEventElapsedTime(&c->last_ms, ev[0], ev[9]);
     for (auto& e : ev) cudaEventDestroy(e);
     c->parity = p;
     return AVB_OK;
@@ -514,20 +520,50 @@ static int run_frame(avb_ctx* c, int variant, bool wait) {
     c->parity = p;
     c->first_frame = false;
     c->have_frame = true;
-    if (wait) {
-        CK(cudaStreamSynchronize(c->st));
-        cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1);
-    }
+    if (wait) CK(cudaStreamSynchronize(c->st));       // device time of the frame: on demand, avb_last_frame_ms
     return AVB_OK;
 }
 
-static bool is_page_locked(const void* p) {
+// Is [p, p + n) page-locked host memory?  The driver query costs about a microsecond per image, and callers keep their
+// frames in a few large page-locked allocations (or recycle buffers), so the last few answers are remembered per
+// context as address ranges (the whole allocation when the driver reports it).  A stale "yes" (buffer freed and
+// reallocated pageable) is harmless: cudaMemcpyAsync accepts pageable memory, it merely stages the copy itself.
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+static bool is_page_locked(avb_ctx* c, const void* p, size_t n) {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(p);
+    for (int i = 0; i < avb_ctx::PIN_CACHE; ++i)
+        if (c->pin_len[i] && a0 >= c->pin_base[i] && a0 + n <= c->pin_base[i] + c->pin_len[i]) return c->pin_yes[i];
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    bool yes = false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
         cudaGetLastError();
-        return false;
+    else
+        yes = a.type == cudaMemoryTypeHost;
+    uintptr_t base = a0;
+    size_t len = n;
+    if (yes) {
+        static GetAddressRangeFn range_fn = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess) {
+                cudaGetLastError();
+                fn = nullptr;
+            }
+            return reinterpret_cast<GetAddressRangeFn>(fn);
+        }();
+        CUdeviceptr b = 0;
+        size_t sz = 0;
+        if (range_fn && range_fn(&b, &sz, (CUdeviceptr)a0) == CUDA_SUCCESS && b <= a0 && a0 + n <= b + sz) {
+            base = (uintptr_t)b;
+            len = sz;
+        }
     }
-    return a.type == cudaMemoryTypeHost;
+    const int slot = c->pin_next++ % avb_ctx::PIN_CACHE;
+    c->pin_base[slot] = base;
+    c->pin_len[slot] = len;
+    c->pin_yes[slot] = yes;
+    return yes;
 }
 
 extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
@@ -543,32 +579,36 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
     // Pipelined intake: each image is staged into pinned memory (or, when the caller's buffer is itself page-locked
     // and dense, taken from where it lies) and its H2D copy is enqueued before the next image is touched, so the PCIe
     // transfer of one image overlaps the host copy of the next.  The kernels then run from the graph variant that has
-    // no H2D node.
+    // no H2D node.  Order of submission: the first image copy goes out before anything else (the GPU is idle until it
+    // arrives; every host call ahead of it is on the frame's critical path), then the 216-byte rotation section on the
+    // side stream (a copy this small is all latency; in line it would add ~2.5 us), then the remaining images.
     const int p = c->parity ^ 1;
     const size_t ib = (size_t)g.W * g.H;
-    CK(cudaEventRecord(c->ev_t0, c->st));
-    // the 216-byte rotation section travels on the side stream while the images cross PCIe on the main one (a copy
-    // this small is all latency; in line it would add ~2.5 us to every frame)
-    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     const size_t ro = in_images_bytes(g);
-    CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));          // not before the previous frame is done with d.in[p]
-    CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
-    CK(cudaEventRecord(c->ev_join, c->st_side));
+    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
+    CK(cudaEventRecord(c->ev_t0, c->st));
+    bool rot_sent = false;
     for (int s = 0; s < g.S; ++s) {
         for (int cam = 0; cam < 2; ++cam) {
             const uint8_t* src = cam ? img1[s] : img0[s];
             if (!src) return fail(c, AVB_E_INVALID, "null image pointer (stream %d cam %d)", s, cam);
             const size_t off = ((size_t)s * 2 + cam) * ib;
-            if (stride == g.W && is_page_locked(src)) {
+            if (stride == g.W && is_page_locked(c, src, ib)) {
                 CK(cudaMemcpyAsync(c->d.in[p] + off, src, ib, cudaMemcpyHostToDevice, c->st));
-                continue;
+            } else {
+                uint8_t* dst = c->h_in + off;
+                if (stride == g.W)
+                    memcpy(dst, src, ib);
+                else
+                    for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
+                CK(cudaMemcpyAsync(c->d.in[p] + off, dst, ib, cudaMemcpyHostToDevice, c->st));
             }
-            uint8_t* dst = c->h_in + off;
-            if (stride == g.W)
-                memcpy(dst, src, ib);
-            else
-                for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
-            CK(cudaMemcpyAsync(c->d.in[p] + off, dst, ib, cudaMemcpyHostToDevice, c->st));
+            if (!rot_sent) {
+                CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));      // not before the previous frame is done with d.in[p]
+                CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
+                CK(cudaEventRecord(c->ev_join, c->st_side));
+                rot_sent = true;
+            }
         }
     }
     CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
@@ -619,7 +659,6 @@ extern "C" int avb_enqueue_frame_gather(avb_ctx* c, const uint8_t* const* d_imag
 extern "C" int avb_sync(avb_ctx* c) {
     if (!c) return AVB_E_INVALID;
     CK(cudaStreamSynchronize(c->st));
-    cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1);
     return AVB_OK;
 }
 
@@ -631,6 +670,10 @@ extern "C" int avb_process_frame_device(avb_ctx* c, const uint8_t* d_block) {
 
 extern "C" int avb_last_frame_ms(avb_ctx* c, float* ms) {
     if (!c || !ms) return AVB_E_INVALID;
+    if (c->have_frame) {
+        CK(cudaEventSynchronize(c->ev_t1));
+        CK(cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
+    }
     *ms = c->last_ms;
     return AVB_OK;
 }

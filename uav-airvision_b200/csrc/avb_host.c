@@ -66,8 +66,26 @@ static PyObject* FM_repr(FMObject* self) {
     return PyUnicode_FromString(buf);
 }
 
+/* A frame publishes a few hundred of these and the consumer drops them a frame later: freed objects of the exact type
+ * wait on a free list (as CPython does for its own small types) instead of going back to the allocator. */
+#ifndef FM_FREELIST_MAX
+#define FM_FREELIST_MAX 16384
+#endif
+static PyTypeObject FMType;
+static FMObject* fm_free[FM_FREELIST_MAX + 1];
+static int fm_nfree = 0;
+
+static void FM_dealloc(FMObject* self) {
+    if (Py_IS_TYPE((PyObject*)self, &FMType) && fm_nfree < FM_FREELIST_MAX) {       /* subclasses go the normal way */
+        fm_free[fm_nfree++] = self;
+        return;
+    }
+    Py_TYPE(self)->tp_free((PyObject*)self);
+}
+
 static PyTypeObject FMType = {
     PyVarObject_HEAD_INIT(NULL, 0).tp_name = "image_processing.FeatureMeasurement",
+    .tp_dealloc = (destructor)FM_dealloc,
     .tp_basicsize = sizeof(FMObject),
     .tp_flags = Py_TPFLAGS_DEFAULT | Py_TPFLAGS_BASETYPE,
     .tp_doc = "Stereo measurement of one feature in normalized coordinates: id, u0, v0, u1, v1.",
@@ -82,8 +100,14 @@ static PyObject* g_names[5];
 
 static PyObject* make_feature(PyTypeObject* tp, long long id, const double* m) {
     if (tp == &FMType) {
-        FMObject* o = (FMObject*)FMType.tp_alloc(&FMType, 0);
-        if (!o) return NULL;
+        FMObject* o;
+        if (fm_nfree) {
+            o = fm_free[--fm_nfree];
+            _Py_NewReference((PyObject*)o);
+        } else {
+            o = (FMObject*)FMType.tp_alloc(&FMType, 0);
+            if (!o) return NULL;
+        }
         o->id = id;
         o->u0 = m[0];
         o->v0 = m[1];
@@ -359,6 +383,27 @@ static PyObject* py_features_from_result(PyObject* self, PyObject* args) {
     return out;
 }
 
+/* features_from_arrays(ids: int64[n], meas: float64[n, 4], fm_type) -> list: the list construction alone, from caller
+ * arrays (what a sweep's estimator side holds, estimator_pool.py). */
+static PyObject* py_features_from_arrays(PyObject* self, PyObject* args) {
+    Py_buffer bi, bm;
+    PyObject* tpobj;
+    if (!PyArg_ParseTuple(args, "y*y*O", &bi, &bm, &tpobj)) return NULL;
+    PyObject* out = NULL;
+    const Py_ssize_t n = bi.len / 8;
+    if (!PyType_Check(tpobj) || bi.len % 8 || bm.len != n * 32) {
+        PyErr_SetString(PyExc_ValueError, "features_from_arrays(ids int64[n], meas float64[n, 4] (both C-contiguous), type)");
+    } else {
+        avb_frame_header h;
+        memset(&h, 0, sizeof h);
+        h.n_features = n;
+        out = build_list((PyTypeObject*)tpobj, &h, (const int64_t*)bi.buf, (const double*)bm.buf);
+    }
+    PyBuffer_Release(&bi);
+    PyBuffer_Release(&bm);
+    return out;
+}
+
 /* ---- gyro integration ---------------------------------------------------------------------------------- */
 
 static PyObject *s_timestamp, *s_angular_velocity;
@@ -554,6 +599,7 @@ static PyMethodDef methods[] = {
     {"process_frame", py_process_frame, METH_VARARGS, "One stereo frame: host images in, (FeatureMeasurement list, header) out."},
     {"process_frames", py_process_frames, METH_VARARGS, "One stereo frame for every stream of a multi-stream context."},
     {"features_from_result", py_features_from_result, METH_VARARGS, "FeatureMeasurement list of stream s from the last frame."},
+    {"features_from_arrays", py_features_from_arrays, METH_VARARGS, "FeatureMeasurement list from ids / measurement arrays."},
     {"png_unfilter", py_png_unfilter, METH_VARARGS, "Undo PNG row filters into a caller buffer."},
     {"integrate_imu", py_integrate_imu, METH_VARARGS, "Gyro window integration (imu_processor.py:28-67)."},
     {NULL, NULL, 0, NULL}};

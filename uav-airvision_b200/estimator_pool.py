@@ -10,8 +10,8 @@ Transport: one shared-memory ring per worker (`depth` slots; a slot = one step o
 timestamp, ids, normalized stereo measurements as plain arrays) guarded by two semaphores.  The producer copies arrays
 into the slot and posts; nothing is pickled and no feeder thread competes for the producer's GIL (with pickling queues
 the producer of a 128-run sweep spent 37 ms per step handing 1.6 MB to 23 feeder threads).  A worker rebuilds the
-`feature_msg` the filter expects.  Nothing here touches CUDA, and the module imports neither torch nor libavb: workers
-start in well under a second with the `spawn` method.
+`feature_msg` the filter expects.  Nothing here touches CUDA (the host driver extension is imported for its list builder only, no context is created)
+and torch is never imported: workers start in about a second with the `spawn` method.
 """
 from __future__ import annotations
 
@@ -30,11 +30,20 @@ MAX_IMU = 64                # IMU rows per stream and slot; longer runs of IMU s
 STOP, IMU_ONLY, FRAME = -1, 0, 1
 
 
+try:                                    # the C list builder of the front end's host driver (3 us for 300 measurements)
+    from image_processing import FeatureMeasurement as _FM, _avbhost as _host
+except Exception:                       # pragma: no cover - e.g. the filter used without the front end's extension built
+    _host = None
+
+
 def feed(est, imu_rows, ts, ids, meas):
     """One frame into an estimator: IMU rows (t, gyro xyz, acc xyz) in order, then the feature message."""
     for row in imu_rows:
         est.imu_callback(imu_msg(float(row[0]), row[1:4].copy(), row[4:7].copy()))
-    feats = [Meas(int(i), *r) for i, r in zip(ids.tolist(), meas.tolist())]
+    if _host is not None and ids.flags.c_contiguous and meas.flags.c_contiguous and ids.dtype == np.int64 and meas.dtype == np.float64:
+        feats = _host.features_from_arrays(ids, meas, _FM)
+    else:
+        feats = [Meas(int(i), *r) for i, r in zip(ids.tolist(), meas.tolist())]
     return est.feature_callback(feature_msg(float(ts), feats))
 
 
