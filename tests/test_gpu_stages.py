@@ -42,7 +42,8 @@ def test_pyramid_bit_exact(ctx752, frames752):
             assert np.array_equal(got, ref[lvl]), f'slot {slot} level {lvl}'
 
 
-@pytest.mark.parametrize('w,h,levels', [(1280, 1024, 4), (640, 512, 4), (80 * 16, 400, 3), (96, 96, 1), (752, 481, 3)])
+@pytest.mark.parametrize('w,h,levels', [(1280, 1024, 4), (640, 512, 4), (80 * 16, 400, 3), (96, 96, 1), (752, 481, 3),
+                                        (752, 480, 5), (144, 113, 5)])      # last two: level 5 is built from an odd-width level
 def test_pyramid_other_sizes(w, h, levels):
     from image_processing import _native
     cfg = FrontEndConfig(pyramid_levels=levels, width=w, height=h)
@@ -242,3 +243,40 @@ def test_camera_model_class_matches_reference_signature(ctx752):
     assert cm.undistort_points([], cm.intrinsics, 'radtan', cm.distortion_coeffs) == []
     with pytest.raises(RuntimeError):
         cm.undistort_points(pts, cm.intrinsics, 'equidistant', cm.distortion_coeffs)
+
+
+def test_gather_from_frame_store_places_every_image():
+    """avb_store_* + avb_process_frame_gather with more images than one gather launch carries (2 x 130 > 256 pointers):
+    level 0 of every stream and camera equals the frame the table pointed at, and the levels built from it equal the
+    oracle pyramid."""
+    from image_processing import _native
+    w, h, S, n = 160, 128, 130, 7
+    cfg = FrontEndConfig(grid_row=2, grid_col=2, pyramid_levels=2, width=w, height=h)
+    g = np.random.default_rng(9)
+    frames = g.integers(0, 256, (n, 2, h, w)).astype(np.uint8)
+    store = _native.FrameStore(w, h, n)
+    ctx = _native.Context(cfg, w, h, num_streams=S, use_graph=False)
+    try:
+        assert store.nbytes >= n * 2 * w * h and store.addr.shape == (n, 2)
+        for k in range(n):
+            store.upload(k, frames[k, 0], frames[k, 1][:, :], timestamp=float(k))
+        with pytest.raises(RuntimeError):                       # frame index out of range
+            store.upload(n, frames[0, 0], frames[0, 1])
+        with pytest.raises(ValueError):                         # wrong shape
+            store.upload(0, frames[0, 0][:, :-16], frames[0, 1])
+        pick = g.integers(0, n, S)
+        ctx.process_gather(store.addr[pick])
+        for s in (0, 1, 63, 127, 128, 129):
+            for cam in (0, 1):
+                assert np.array_equal(ctx.download_level(cam, 0, s=s), frames[pick[s], cam]), (s, cam)
+            ref = cs.build_pyramid(frames[pick[s], 1], 2)
+            assert np.array_equal(ctx.download_level(1, 2, s=s), ref[2])
+        with pytest.raises(ValueError):
+            ctx.process_gather(store.addr[pick[:3]])
+        bad = store.addr[pick].copy()
+        bad[5, 1] += 1                                          # not 16-byte aligned
+        with pytest.raises(RuntimeError, match='aligned'):
+            ctx.process_gather(bad)
+    finally:
+        ctx.close()
+        store.close()
