@@ -210,3 +210,40 @@ def test_host_side_stage_logic_without_gpu():
         exp.append([h[0] / h[2], h[1] / h[2]])
     assert got.dtype == np.float32 and np.array_equal(got, np.array(exp, np.float32))
     assert tr.get_grid_size(np.zeros((480, 752), np.uint8)) == (120, 151)
+
+
+def test_feature_measurement_objects_and_list_builder():
+    """FeatureMeasurement (C type, feature_measurment.py:1-9 attribute set): constructor, attributes, subclassing; the
+    list builder used by the hot path and the estimator workers; freed objects are recycled without leaking state."""
+    from image_processing import FeatureMeasurement, _avbhost
+    f = FeatureMeasurement(7, 0.1, 0.2, 0.3, 0.4)
+    assert (f.id, f.u0, f.v0, f.u1, f.v1) == (7, 0.1, 0.2, 0.3, 0.4) and 'id=7' in repr(f)
+    g = FeatureMeasurement()
+    g.id, g.u0 = 3, -1.5
+    assert g.id == 3 and g.u0 == -1.5 and g.v1 == 0.0
+
+    class Sub(FeatureMeasurement):
+        pass
+    s = Sub(1, 2.0, 3.0, 4.0, 5.0)
+    s.extra = 'x'
+    assert s.v1 == 5.0 and s.extra == 'x'
+    del s
+    ids = np.arange(100, 400, dtype=np.int64)
+    meas = np.random.default_rng(0).normal(size=(300, 4))
+    a = _avbhost.features_from_arrays(ids, meas, FeatureMeasurement)
+    assert len(a) == 300 and [x.id for x in a] == ids.tolist()
+    assert np.array_equal(np.array([[x.u0, x.v0, x.u1, x.v1] for x in a]), meas)
+    keep = a[5]
+    del a                                                     # 299 objects go to the free list, one stays alive
+    b = _avbhost.features_from_arrays(ids[:50] + 1000, meas[:50] * 2, FeatureMeasurement)
+    assert keep.id == 105 and keep.u0 == meas[5, 0]           # not recycled while referenced
+    assert [x.id for x in b] == (ids[:50] + 1000).tolist() and b[7].v0 == 2 * meas[7, 1]
+    assert all(x is not keep for x in b)
+    # any class with the five attributes can be requested instead (generic path)
+    class Plain:
+        pass
+    c = _avbhost.features_from_arrays(ids[:3], meas[:3], Plain)
+    assert [type(x) for x in c] == [Plain] * 3 and c[2].id == 102 and c[2].u1 == meas[2, 2]
+    assert _avbhost.features_from_arrays(ids[:0], meas[:0], FeatureMeasurement) == []
+    with pytest.raises(ValueError):
+        _avbhost.features_from_arrays(ids, meas[:10], FeatureMeasurement)

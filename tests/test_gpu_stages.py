@@ -43,7 +43,7 @@ def test_pyramid_bit_exact(ctx752, frames752):
 
 
 @pytest.mark.parametrize('w,h,levels', [(1280, 1024, 4), (640, 512, 4), (80 * 16, 400, 3), (96, 96, 1), (752, 481, 3),
-                                        (752, 480, 5), (144, 113, 5)])      # last two: level 5 is built from an odd-width level
+                                        (1040, 1030, 5)])      # last: level 5 (33 px wide) is built from an odd-width level (65 px)
 def test_pyramid_other_sizes(w, h, levels):
     from image_processing import _native
     cfg = FrontEndConfig(pyramid_levels=levels, width=w, height=h)
