@@ -1,26 +1,10 @@
-"""ORACLE (test infrastructure).  Deterministic synchronous replay driver.
+"""ORACLE (test infrastructure).  The deterministic synchronous replay driver lives in the package
+(uav-airvision_b200/replay.py, plain host logic); re-exported here for the oracle's callers."""
+import os
+import sys
 
-Replaces the reference's wall-clock paced DataPublisher + VIO threads
-(/root/reference/src/streaming/publisher.py:32-53, src/modules/vio.py:26-53) for testing:
-before each stereo frame every IMU message with timestamp <= the frame's is delivered, in
-order, to `imu_callback`; then `stereo_callback` runs inline.  The same driver feeds the
-real reference (tools/make_golden.py), the oracle port and the CUDA front end."""
-from __future__ import annotations
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'uav-airvision_b200')
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
 
-
-def run_stream(front_end, stream, on_frame=None, msckf=None):
-    """Returns the list of feature_msg (one per stereo frame)."""
-    out = []
-    for kind, msg in stream.events():
-        if kind == 'imu':
-            front_end.imu_callback(msg)
-            if msckf is not None:
-                msckf.imu_callback(msg)
-        else:
-            fm = front_end.stereo_callback(msg)
-            out.append(fm)
-            if on_frame is not None:
-                on_frame(len(out) - 1, msg, fm)
-            if msckf is not None:
-                msckf.feature_callback(fm)
-    return out
+from replay import run_stream  # noqa: E402,F401

@@ -33,15 +33,15 @@ GRID = dict(grid_row=6, grid_col=10, grid_min=3, grid_max=5)        # C2: 300 fe
 
 
 def make_stream(n_frames):
-    from oracle.configs import FrontEndConfig
+    from frontend_config import FrontEndConfig
     from synth_euroc import RoomSceneStream
     return RoomSceneStream(FrontEndConfig(**GRID), n_frames=n_frames, **SEQ)
 
 
 def dump(args):
     from image_processing import ImageProcessor
-    from oracle.configs import FrontEndConfig
-    from oracle.driver import run_stream
+    from frontend_config import FrontEndConfig
+    from replay import run_stream
     cfg = FrontEndConfig(**GRID)
     ip = ImageProcessor(cfg)
     rec = {}
@@ -82,7 +82,7 @@ def run_vio(front_end, stream, tag, workdir):
     """Deterministic driver: reference MSCKF consuming `front_end`'s messages.  Returns (t, positions) of the filter."""
     from msckf import MSCKF                                   # reference, unmodified
     from config import ConfigEuRoC
-    from oracle.driver import run_stream
+    from replay import run_stream
     os.environ['DATASET_NAME'], os.environ['TIME_OFFSET'] = tag, '0'
     cwd = os.getcwd()
     os.chdir(workdir)

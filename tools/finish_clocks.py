@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, 'uav-airvision_b200')):
     sys.path.insert(0, p)
 from bench import make_sequence, workload
 from image_processing import ImageProcessor
-from oracle.driver import run_stream
+from replay import run_stream
 cfg, skw, _ = workload(sys.argv[1] if len(sys.argv) > 1 else 'c2')
 ip = ImageProcessor(cfg)
 rows = []

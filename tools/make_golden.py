@@ -14,9 +14,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.dont_write_bytecode = True
-sys.path.insert(0, '/root/reference/src')
-sys.path.insert(0, ROOT)
+# the reference's src/ FIRST: `image_processing`, `config` must resolve to the UNMODIFIED reference; the package
+# directory is only there for synth_euroc / replay / frontend_config (it also holds the drop-in `image_processing`)
 sys.path.insert(0, os.path.join(ROOT, 'uav-airvision_b200'))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference/src')
 
 CASES = {
     # name: (grid_row, grid_col, grid_min, grid_max, stream kwargs)
@@ -32,7 +34,7 @@ def dump_case(name, spec):
     from config import ConfigEuRoC                      # reference config, unmodified
     from image_processing import ImageProcessor        # reference front end, unmodified
     from synth_euroc import SlidingTextureStream
-    from oracle.driver import run_stream
+    from replay import run_stream
 
     gr, gc, gmin, gmax, skw = spec
     cfg = ConfigEuRoC()
@@ -69,7 +71,9 @@ def dump_case(name, spec):
     rec['n_frames'] = np.asarray([stream.n])
     rec['next_feature_id'] = np.asarray([ip.next_feature_id])
     rec['spec'] = np.asarray([gr, gc, gmin, gmax])
-    path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+    import image_processing
+    assert image_processing.__file__.startswith('/root/reference/'), image_processing.__file__
+    path = os.path.join(os.environ.get('GOLDEN_OUT', os.path.join(ROOT, 'tests', 'golden')), name + '.npz')
     np.savez_compressed(path, **rec)
     print(name, 'frames', stream.n, 'features/frame',
           [len(rec[f'f{k}_ids']) for k in range(stream.n)], '->', os.path.getsize(path), 'B')
