@@ -5,13 +5,86 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "avb_common.cuh"
 
 static thread_local std::string g_create_error;
 int g_avb_pdl = 1;
+
+// Host helper thread for pageable caller images: the two images of a stereo frame are staged into pinned memory by two
+// cores at once (a 361 kB memcpy from cold memory takes 25-35 us).  Polls for about a millisecond after a job, then
+// sleeps on a condition variable; the poster spins on an atomic for the few microseconds it may have to wait.
+struct CopyWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    const uint8_t* src = nullptr;
+    uint8_t* dst = nullptr;
+    int W = 0, H = 0, stride = 0;
+    std::atomic<int> state{0};      // 0 idle, 1 job posted, 2 job done
+    bool quit = false;
+
+    static void copy(uint8_t* dst, const uint8_t* src, int W, int H, int stride) {
+        if (stride == W)
+            memcpy(dst, src, (size_t)W * H);
+        else
+            for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * W, src + (size_t)y * stride, W);
+    }
+    void run() {
+        for (;;) {
+            // a stream of frames posts every few hundred microseconds: poll that long before going to sleep (waking a
+            // sleeping thread costs more than the copy it is there to hide)
+            bool have = false;
+            for (int spin = 0; spin < 40000 && !have; ++spin) {
+                have = state.load(std::memory_order_acquire) == 1;
+#if defined(__x86_64__)
+                if (!have) __builtin_ia32_pause();
+#endif
+            }
+            if (!have) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return quit || state.load(std::memory_order_acquire) == 1; });
+                if (quit) return;
+            }
+            copy(dst, src, W, H, stride);
+            state.store(2, std::memory_order_release);
+        }
+    }
+    void post(uint8_t* d, const uint8_t* s, int w, int h, int st) {
+        if (!th.joinable()) th = std::thread([this] { run(); });
+        if (state.load(std::memory_order_acquire) != 0) wait();        // a job left behind by an error return
+        {
+            std::lock_guard<std::mutex> lk(m);
+            dst = d, src = s, W = w, H = h, stride = st;
+            state.store(1, std::memory_order_release);
+        }
+        cv.notify_one();
+    }
+    void wait() {
+        while (state.load(std::memory_order_acquire) != 2) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        state.store(0, std::memory_order_relaxed);
+    }
+    ~CopyWorker() {
+        if (th.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(m);
+                quit = true;
+            }
+            cv.notify_one();
+            th.join();
+        }
+    }
+};
 
 struct avb_ctx {
     avb_config cfg;
@@ -42,6 +115,7 @@ struct avb_ctx {
     size_t pin_len[PIN_CACHE] = {};
     bool pin_yes[PIN_CACHE] = {};
     unsigned pin_next = 0;
+    CopyWorker copier;
 };
 
 static int fail(avb_ctx* c, int code, const char* fmt, ...) {
@@ -588,27 +662,38 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
     avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     CK(cudaEventRecord(c->ev_t0, c->st));
     bool rot_sent = false;
+    auto send_rotations = [&]() -> int {
+        CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));      // not before the previous frame is done with d.in[p]
+        CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
+        CK(cudaEventRecord(c->ev_join, c->st_side));
+        rot_sent = true;
+        return AVB_OK;
+    };
     for (int s = 0; s < g.S; ++s) {
-        for (int cam = 0; cam < 2; ++cam) {
-            const uint8_t* src = cam ? img1[s] : img0[s];
-            if (!src) return fail(c, AVB_E_INVALID, "null image pointer (stream %d cam %d)", s, cam);
-            const size_t off = ((size_t)s * 2 + cam) * ib;
-            if (stride == g.W && is_page_locked(c, src, ib)) {
-                CK(cudaMemcpyAsync(c->d.in[p] + off, src, ib, cudaMemcpyHostToDevice, c->st));
-            } else {
-                uint8_t* dst = c->h_in + off;
-                if (stride == g.W)
-                    memcpy(dst, src, ib);
-                else
-                    for (int y = 0; y < g.H; ++y) memcpy(dst + (size_t)y * g.W, src + (size_t)y * stride, g.W);
-                CK(cudaMemcpyAsync(c->d.in[p] + off, dst, ib, cudaMemcpyHostToDevice, c->st));
+        const uint8_t* src0 = img0[s];
+        const uint8_t* src1 = img1[s];
+        if (!src0 || !src1) return fail(c, AVB_E_INVALID, "null image pointer (stream %d)", s);
+        const size_t off0 = ((size_t)s * 2) * ib, off1 = off0 + ib;
+        const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
+        if (!pin1) c->copier.post(c->h_in + off1, src1, g.W, g.H, stride);     // the helper stages cam1 meanwhile
+        if (pin0) {
+            CK(cudaMemcpyAsync(c->d.in[p] + off0, src0, ib, cudaMemcpyHostToDevice, c->st));
+        } else {
+            CopyWorker::copy(c->h_in + off0, src0, g.W, g.H, stride);
+            CK(cudaMemcpyAsync(c->d.in[p] + off0, c->h_in + off0, ib, cudaMemcpyHostToDevice, c->st));
+        }
+        if (!rot_sent) {
+            const int r = send_rotations();
+            if (r != AVB_OK) {
+                if (!pin1) c->copier.wait();
+                return r;
             }
-            if (!rot_sent) {
-                CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));      // not before the previous frame is done with d.in[p]
-                CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
-                CK(cudaEventRecord(c->ev_join, c->st_side));
-                rot_sent = true;
-            }
+        }
+        if (pin1) {
+            CK(cudaMemcpyAsync(c->d.in[p] + off1, src1, ib, cudaMemcpyHostToDevice, c->st));
+        } else {
+            c->copier.wait();
+            CK(cudaMemcpyAsync(c->d.in[p] + off1, c->h_in + off1, ib, cudaMemcpyHostToDevice, c->st));
         }
     }
     CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
