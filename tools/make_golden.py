@@ -14,11 +14,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.dont_write_bytecode = True
-# the reference's src/ FIRST: `image_processing`, `config` must resolve to the UNMODIFIED reference; the package
-# directory is only there for synth_euroc / replay / frontend_config (it also holds the drop-in `image_processing`)
-sys.path.insert(0, os.path.join(ROOT, 'uav-airvision_b200'))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, '/root/reference/src')
+
+
+def _reference_first():
+    """Only when run as a script (tests import CASES from this module and must keep their own sys.path): the
+    reference's src/ FIRST, so that `image_processing` and `config` resolve to the UNMODIFIED reference; the package
+    directory stays on the path for synth_euroc / replay / frontend_config (it also holds the drop-in `image_processing`)."""
+    for p in (os.path.join(ROOT, 'uav-airvision_b200'), ROOT, '/root/reference/src'):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+
 
 CASES = {
     # name: (grid_row, grid_col, grid_min, grid_max, stream kwargs)
@@ -80,6 +86,7 @@ def dump_case(name, spec):
 
 
 if __name__ == '__main__':
+    _reference_first()
     import cv2
     print('reference run with cv2', cv2.__version__, 'numpy', np.__version__)
     for name, spec in CASES.items():
