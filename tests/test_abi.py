@@ -70,6 +70,11 @@ def test_no_cpu_fallback_without_device():
     ip = ImageProcessor(config_default())
     with pytest.raises(RuntimeError):
         ip.stereo_callback(SlidingTextureStream(n_frames=1).frame(0))
+    with pytest.raises(RuntimeError, match='avb_store_create'):      # the HBM frame store has no host stand-in either
+        _native.FrameStore(752, 480, 4)
+    lib = _native.load()
+    assert lib.avb_store_num_frames(None) == 0 and lib.avb_store_image(None, 0, 0) is None
+    assert lib.avb_process_frame_gather(None, None, None, None) == -1   # AVB_E_INVALID
 
 
 def test_product_package_does_not_import_oracle():
