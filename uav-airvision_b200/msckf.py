@@ -682,32 +682,31 @@ class MSCKF:
                 out[i] = (H[k], r[k], slots[k], bool(ok[k]))
         return out
 
-    def measurement_update(self, H, r):
-        """msckf.py:542-603."""
-        if len(H) == 0 or len(r) == 0:
+    def measurement_update(self, Hc, r, cols):
+        """msckf.py:542-603.  The stacked Jacobian arrives compact: `Hc` holds only the columns `cols` (sorted state
+        indices) of H -- H is zero everywhere else (the 21 IMU columns always; in the pruning update everything but the
+        two camera states that leave: 12 of up to 120 columns)."""
+        if len(Hc) == 0 or len(r) == 0:
             return
-        if H.shape[0] > H.shape[1]:
-            # Thin QR as in the reference (msckf.py:548-554), without its two avoidable costs: the 21 IMU columns of H
-            # are identically zero (only camera-state blocks are filled), so the factorisation runs on the other columns,
-            # and Q is never formed -- Q^T r comes from the Householder reflectors (dgeqrf + dormqr).  The rows of
-            # [0 | R] span the same space as the reference's R; K and (I - K H) P are the same.
+        nc = len(cols)
+        if Hc.shape[0] > nc:
+            # Thin QR as in the reference (msckf.py:548-554), on the non-zero columns alone, and without forming Q: Q^T r
+            # comes from the Householder reflectors (dgeqrf + dormqr).  R scattered into `cols` and the reference's R have
+            # the same Gram matrix H^T H and the same H^T r, which is all K r and (I - K H) P depend on.
             from scipy.linalg import get_lapack_funcs
-            Hc = np.asfortranarray(H[:, 21:])
-            geqrf, ormqr = get_lapack_funcs(('geqrf', 'ormqr'), (Hc,))
-            qr_, tau, _, info = geqrf(Hc, overwrite_a=True)
+            Hf = np.asfortranarray(Hc)
+            geqrf, ormqr = get_lapack_funcs(('geqrf', 'ormqr'), (Hf,))
+            qr_, tau, _, info = geqrf(Hf, overwrite_a=True)
             c = np.asfortranarray(r.reshape(-1, 1))
             cq, _, info2 = ormqr('L', 'T', qr_, tau, c, max(64 * c.shape[0], 1), overwrite_c=True)
             if info != 0 or info2 != 0:
                 raise np.linalg.LinAlgError('QR of the stacked measurement Jacobian failed')
-            nc = Hc.shape[1]
-            H_thin = np.zeros((nc, H.shape[1]))
-            H_thin[:, 21:] = np.triu(qr_[:nc])
-            r_thin = cq[:nc, 0]
+            H_thin, r_thin = np.triu(qr_[:nc]), cq[:nc, 0]
         else:
-            H_thin, r_thin = H, r
+            H_thin, r_thin = Hc, r
         P = self.state_cov
-        HP = H_thin @ P
-        S = HP @ H_thin.T
+        HP = H_thin @ P[cols]                                         # H P with H's zero columns skipped
+        S = HP[:, cols] @ H_thin.T
         S[np.diag_indices(len(S))] += self.config.observation_noise
         Kt = np.linalg.solve(S, HP)
         delta = Kt.T @ r_thin
@@ -759,10 +758,15 @@ class MSCKF:
         Pn = P - Kt.T @ HP                                            # (I - K H) P
         self.state_cov = (Pn + Pn.T) / 2.0
 
-    def _stack(self, blocks, width):
-        """Dense stacked Jacobian / residual from (H, r, slots) blocks: one scatter per group of equal block shape."""
+    def _stack(self, blocks):
+        """Stacked Jacobian / residual from (H, r, slots) blocks, compact in the columns: only the camera states that
+        occur in some block get columns (one scatter per group of equal block shape).  Returns Hc, r and the state indices
+        `cols` of Hc's columns."""
         rows = sum(len(b[1]) for b in blocks)
-        H = np.zeros((rows, width))
+        used = sorted({int(v) for b in blocks for v in b[2]})
+        pos = np.full(max(used) + 1, -1, dtype=np.int64) if used else np.zeros(0, np.int64)
+        pos[used] = np.arange(len(used))
+        H = np.zeros((rows, 6 * len(used)))
         r = np.empty(rows)
         groups, at = {}, 0
         for Hb, rb, slots in blocks:
@@ -771,12 +775,13 @@ class MSCKF:
         for (a, c), items in groups.items():
             starts = np.array([it[0] for it in items])
             Hs = np.stack([it[1] for it in items])                                  # (F, a, 6m)
-            sl = np.stack([it[3] for it in items])                                  # (F, m)
+            sl = pos[np.stack([it[3] for it in items])]                             # (F, m) -> compact column blocks
             ri = starts[:, None] + np.arange(a)                                     # (F, a)
-            ci = ((21 + 6 * sl)[:, :, None] + np.arange(6)).reshape(len(items), c)  # (F, 6m)
+            ci = ((6 * sl)[:, :, None] + np.arange(6)).reshape(len(items), c)       # (F, 6m)
             H[ri[:, :, None], ci[:, None, :]] = Hs
             r[ri] = np.stack([it[2] for it in items])
-        return H, r
+        cols = (21 + 6 * np.array(used, dtype=np.int64)[:, None] + np.arange(6)).reshape(-1)
+        return H, r, cols
 
     def remove_lost_features(self):
         """msckf.py:614-676: features that lost tracking are used for an update and leave the map."""
@@ -804,8 +809,8 @@ class MSCKF:
                 rows += len(r)
             if rows > 1500:
                 break
-        H, r = self._stack(blocks, self.state_cov.shape[0])
-        self.measurement_update(H, r)
+        H, r, cols = self._stack(blocks)
+        self.measurement_update(H, r, cols)
         for feat in processed:
             del self.map_server[feat.id]
 
@@ -857,8 +862,8 @@ class MSCKF:
         for feat, involved in todo:
             for c in involved:
                 del feat.observations[c]
-        H, r = self._stack(blocks, self.state_cov.shape[0])
-        self.measurement_update(H, r)
+        H, r, cols = self._stack(blocks)
+        self.measurement_update(H, r, cols)
         for cam_id in rm:
             i = self.cams.remove(cam_id)
             keep = np.r_[0:21 + 6 * i, 27 + 6 * i:self.state_cov.shape[0]]
