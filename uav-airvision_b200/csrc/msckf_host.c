@@ -399,7 +399,94 @@ static PyObject* py_triangulate(PyObject* self, PyObject* args) {
     return Py_BuildValue("(ddd)", sol[0], sol[1], sol[2]);
 }
 
+/* ---- stereo measurement Jacobians of F features x m camera states (msckf.py:443-502 of the reference) ------------------
+ * jacobians(R0 (F,m,3,3), pcam (F,m,3), Rn (F,m,3,3), pn (F,m,3), pw (F,3), Z (F,m,4), R01 (3,3), t01 (3), g (3),
+ *           Hx out (F,m,4,6), Hf out (F,4m,3), r out (F,4m))
+ * Per observation: p_c0 = R0 (p_w - p_cam), p_c1 = R01 p_c0 + t01; H_x = [d(proj)/dp * skew(p_c0) | -d(proj)/dp * R0] for
+ * both cameras; the observability constraint removes the component of H_x along u = [R_null g; (p_w - p_null) x g];
+ * H_f = -H_x[:, 3:6]; r = z - proj.  About sixty small numpy calls per group of features otherwise. */
+static PyObject* py_jacobians(PyObject* self, PyObject* args) {
+    PyObject* o[12];
+    if (!PyArg_ParseTuple(args, "OOOOOOOOOOOO", &o[0], &o[1], &o[2], &o[3], &o[4], &o[5], &o[6], &o[7], &o[8], &o[9], &o[10], &o[11]))
+        return NULL;
+    static const char* names[12] = {"R0", "pcam", "Rn", "pn", "pw", "Z", "R01", "t01", "g", "Hx", "Hf", "r"};
+    Py_buffer b[12];
+    int got = 0;
+    for (; got < 12; ++got)
+        if (get_buf(o[got], &b[got], 1, got >= 9, names[got]) < 0) break;
+    PyObject* ret = NULL;
+    if (got == 12) {
+        const Py_ssize_t F = b[4].len / 24, fm = b[1].len / 24;
+        const Py_ssize_t m = F > 0 ? fm / F : 0;
+        if (F <= 0 || m <= 0 || fm != F * m || b[0].len != fm * 72 || b[2].len != fm * 72 || b[3].len != fm * 24 ||
+            b[5].len != fm * 32 || b[6].len != 72 || b[7].len != 24 || b[8].len != 24 || b[9].len != fm * 192 ||
+            b[10].len != fm * 96 || b[11].len != fm * 32) {
+            PyErr_SetString(PyExc_ValueError, "jacobians: inconsistent array sizes");
+        } else {
+            const double *R0a = b[0].buf, *pca = b[1].buf, *Rna = b[2].buf, *pna = b[3].buf, *pwa = b[4].buf, *Za = b[5].buf;
+            const double *R01 = b[6].buf, *t01 = b[7].buf, *g = b[8].buf;
+            double *Hxa = b[9].buf, *Hfa = b[10].buf, *ra = b[11].buf;
+            for (Py_ssize_t f = 0; f < F; ++f) {
+                const double* pw = pwa + 3 * f;
+                for (Py_ssize_t k = 0; k < m; ++k) {
+                    const Py_ssize_t i = f * m + k;
+                    const double *R0 = R0a + 9 * i, *pc = pca + 3 * i, *Rn = Rna + 9 * i, *pn = pna + 3 * i, *z = Za + 4 * i;
+                    double* Hx = Hxa + 24 * i;
+                    const double d[3] = {pw[0] - pc[0], pw[1] - pc[1], pw[2] - pc[2]};
+                    double p0[3], p1[3], sk[9], R01sk[9], R01R0[9];
+                    mat3_vec(R0, d, p0);
+                    mat3_vec(R01, p0, p1);
+                    p1[0] += t01[0];
+                    p1[1] += t01[1];
+                    p1[2] += t01[2];
+                    skew3(p0, sk);
+                    mat3_mul(R01, sk, R01sk);
+                    mat3_mul(R01, R0, R01R0);
+                    const double iz0 = 1.0 / p0[2], iz1 = 1.0 / p1[2];
+                    const double J0[6] = {iz0, 0.0, -p0[0] * iz0 * iz0, 0.0, iz0, -p0[1] * iz0 * iz0};
+                    const double J1[6] = {iz1, 0.0, -p1[0] * iz1 * iz1, 0.0, iz1, -p1[1] * iz1 * iz1};
+                    for (int a = 0; a < 2; ++a)
+                        for (int c = 0; c < 3; ++c) {
+                            Hx[6 * a + c] = J0[3 * a] * sk[c] + J0[3 * a + 1] * sk[3 + c] + J0[3 * a + 2] * sk[6 + c];
+                            Hx[6 * a + 3 + c] = -(J0[3 * a] * R0[c] + J0[3 * a + 1] * R0[3 + c] + J0[3 * a + 2] * R0[6 + c]);
+                            Hx[6 * (a + 2) + c] = J1[3 * a] * R01sk[c] + J1[3 * a + 1] * R01sk[3 + c] + J1[3 * a + 2] * R01sk[6 + c];
+                            Hx[6 * (a + 2) + 3 + c] =
+                                -(J1[3 * a] * R01R0[c] + J1[3 * a + 1] * R01R0[3 + c] + J1[3 * a + 2] * R01R0[6 + c]);
+                        }
+                    double u[6];
+                    mat3_vec(Rn, g, u);
+                    const double dn[3] = {pw[0] - pn[0], pw[1] - pn[1], pw[2] - pn[2]};
+                    u[3] = dn[1] * g[2] - dn[2] * g[1];
+                    u[4] = dn[2] * g[0] - dn[0] * g[2];
+                    u[5] = dn[0] * g[1] - dn[1] * g[0];
+                    double uu = 0.0;
+                    for (int c = 0; c < 6; ++c) uu += u[c] * u[c];
+                    for (int a = 0; a < 4; ++a) {
+                        double Au = 0.0;
+                        for (int c = 0; c < 6; ++c) Au += Hx[6 * a + c] * u[c];
+                        for (int c = 0; c < 6; ++c) Hx[6 * a + c] -= Au * (u[c] / uu);
+                        double* hf = Hfa + 3 * (4 * i + a);
+                        hf[0] = -Hx[6 * a + 3];
+                        hf[1] = -Hx[6 * a + 4];
+                        hf[2] = -Hx[6 * a + 5];
+                    }
+                    double* r = ra + 4 * i;
+                    r[0] = z[0] - p0[0] / p0[2];
+                    r[1] = z[1] - p0[1] / p0[2];
+                    r[2] = z[2] - p1[0] / p1[2];
+                    r[3] = z[3] - p1[1] / p1[2];
+                }
+            }
+            ret = Py_None;
+            Py_INCREF(ret);
+        }
+    }
+    for (int i = 0; i < got; ++i) PyBuffer_Release(&b[i]);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"jacobians", py_jacobians, METH_VARARGS, "Stereo measurement Jacobians of F features x m camera states."},
     {"propagate", py_propagate, METH_VARARGS, "IMU batch propagation (msckf.py:251-388 of the reference)."},
     {"triangulate", py_triangulate, METH_VARARGS, "Levenberg-Marquardt feature triangulation on inverse depth."},
     {NULL, NULL, 0, NULL}};

@@ -603,18 +603,12 @@ class MSCKF:
         return sol
 
     # -- measurement model ------------------------------------------------------------------------------------------------
-    def _jacobians(self, feats, cam_ids):
-        """Measurement Jacobians of F features that are each observed in m camera states (cam_ids[f] lists them), projected
-        onto the left null space of the feature Jacobian (msckf.py:443-540), all features at once.
-        Returns H (F, 4m - 3, 6m), r (F, 4m - 3), slots (F, m): column block k of H[f] belongs to window slot slots[f, k]."""
-        cams = self.cams
-        F, m = len(feats), len(cam_ids[0])
-        slots = np.array([[cams.index[c] for c in ids] for ids in cam_ids])         # (F, m)
-        Z = np.array([[f.observations[c] for c in ids] for f, ids in zip(feats, cam_ids)])    # (F, m, 4)
-        p_w = np.array([f.position for f in feats])                                 # (F, 3)
+    def _jacobian_blocks(self, R0, p_cam, R_null, p_null, p_w, Z):
+        """numpy statement of _msckfhost.jacobians (msckf.py:443-502): H_x (F, m, 4, 6) with the observability
+        constraint applied, H_f (F, 4m, 3), r (F, 4m)."""
+        F, m = Z.shape[:2]
         R01, t01, g = self.R_cam0_cam1, self.t_cam0_cam1, self.gravity
-        R0 = cams.R[slots]                                                          # (F, m, 3, 3) world -> cam0
-        d = p_w[:, None, :] - cams.p[slots]
+        d = p_w[:, None, :] - p_cam
         pc0 = np.einsum('fmij,fmj->fmi', R0, d)
         # t_c1_w = t_c0_w - R_w_c1^T t_cam0_cam1  ->  p_c1 = R_cam0_cam1 p_c0 + t_cam0_cam1
         pc1 = pc0 @ R01.T + t01
@@ -640,8 +634,8 @@ class MSCKF:
         Hx[..., 2:, 3:] = -(J1 @ (R01 @ R0))
         # observability constraint (msckf.py:496-502)
         u = np.empty((F, m, 6))
-        u[..., :3] = cams.R_null[slots] @ g
-        dn = p_w[:, None, :] - cams.p_null[slots]
+        u[..., :3] = R_null @ g
+        dn = p_w[:, None, :] - p_null
         u[..., 3] = dn[..., 1] * g[2] - dn[..., 2] * g[1]
         u[..., 4] = dn[..., 2] * g[0] - dn[..., 0] * g[2]
         u[..., 5] = dn[..., 0] * g[1] - dn[..., 1] * g[0]
@@ -652,6 +646,26 @@ class MSCKF:
         r[..., :2] = Z[..., :2] - pc0[..., :2] / pc0[..., 2:3]
         r[..., 2:] = Z[..., 2:] - pc1[..., :2] / pc1[..., 2:3]
         r = r.reshape(F, 4 * m)
+        return Hx, Hf, r
+
+    def _jacobians(self, feats, cam_ids):
+        """Measurement Jacobians of F features that are each observed in m camera states (cam_ids[f] lists them), projected
+        onto the left null space of the feature Jacobian (msckf.py:443-540), all features at once.
+        Returns H (F, 4m - 3, 6m), r (F, 4m - 3), slots (F, m): column block k of H[f] belongs to window slot slots[f, k]."""
+        cams = self.cams
+        F, m = len(feats), len(cam_ids[0])
+        slots = np.array([[cams.index[c] for c in ids] for ids in cam_ids])         # (F, m)
+        Z = np.array([[f.observations[c] for c in ids] for f, ids in zip(feats, cam_ids)])    # (F, m, 4)
+        p_w = np.array([f.position for f in feats])                                 # (F, 3)
+        R01, t01, g = self.R_cam0_cam1, self.t_cam0_cam1, self.gravity
+        R0 = cams.R[slots]                                                          # (F, m, 3, 3) world -> cam0
+        if self.use_c:
+            Hx, Hf, r = np.empty((F, m, 4, 6)), np.empty((F, 4 * m, 3)), np.empty((F, 4 * m))
+            _C.jacobians(R0, cams.p[slots], cams.R_null[slots], cams.p_null[slots], np.ascontiguousarray(p_w),
+                         np.ascontiguousarray(Z), np.ascontiguousarray(R01), np.ascontiguousarray(t01),
+                         np.ascontiguousarray(g), Hx, Hf, r)
+        else:
+            Hx, Hf, r = self._jacobian_blocks(R0, cams.p[slots], cams.R_null[slots], cams.p_null[slots], p_w, Z)
         # left null space of H_f: the last 4m - 3 columns of its complete QR
         Q, _ = np.linalg.qr(Hf, mode='complete')
         At = Q[:, :, 3:].transpose(0, 2, 1)                                         # (F, 4m - 3, 4m)
@@ -668,19 +682,35 @@ class MSCKF:
         gamma = np.einsum('fa,fa->f', r, np.linalg.solve(S, r[:, :, None])[:, :, 0])
         return gamma < self.chi_squared_test_table[dof]
 
-    def _evaluate(self, feats, cam_ids, dof_offset):
+    def _evaluate(self, feats, cam_ids, dof_offset, max_rows=None):
         """Jacobians + gate for a list of features, grouped by their number of camera states so that every group is one
-        vectorised pass.  Returns per feature (H, r, slots, accepted) in the order given."""
-        out = [None] * len(feats)
+        vectorised pass.  Returns the accepted features as blocks (H (n, a, 6m), r (n, a), slots (n, m)), one per group.
+        `max_rows`: the reference stops stacking once more than this many rows are in (msckf.py:665-667): features are
+        taken in the order given up to and including the one that crosses the limit."""
         groups = {}
         for i, ids in enumerate(cam_ids):
             groups.setdefault(len(ids), []).append(i)
+        res = []
+        ok_all = np.zeros(len(feats), dtype=bool)
+        rows_all = np.zeros(len(feats), dtype=np.int64)
         for m, idx in groups.items():
             H, r, slots = self._jacobians([feats[i] for i in idx], [cam_ids[i] for i in idx])
             ok = self._gates(H, r, slots, m + dof_offset)
-            for k, i in enumerate(idx):
-                out[i] = (H[k], r[k], slots[k], bool(ok[k]))
-        return out
+            idx = np.asarray(idx)
+            ok_all[idx] = ok
+            rows_all[idx] = H.shape[1]
+            res.append((idx, H, r, slots, ok))
+        last = len(feats)
+        if max_rows is not None:
+            over = np.flatnonzero(np.cumsum(rows_all * ok_all) > max_rows)
+            if len(over):
+                last = int(over[0]) + 1
+        blocks = []
+        for idx, H, r, slots, ok in res:
+            keep = ok & (idx < last)
+            if keep.any():
+                blocks.append((H[keep], r[keep], slots[keep]))
+        return blocks
 
     def measurement_update(self, Hc, r, cols):
         """msckf.py:542-603.  The stacked Jacobian arrives compact: `Hc` holds only the columns `cols` (sorted state
@@ -759,28 +789,27 @@ class MSCKF:
         self.state_cov = (Pn + Pn.T) / 2.0
 
     def _stack(self, blocks):
-        """Stacked Jacobian / residual from (H, r, slots) blocks, compact in the columns: only the camera states that
-        occur in some block get columns (one scatter per group of equal block shape).  Returns Hc, r and the state indices
+        """Stacked Jacobian / residual from blocks (H (n, a, 6m), r (n, a), slots (n, m)), compact in the columns: only the
+        camera states that occur in some block get columns (one scatter per block).  Returns Hc, r and the state indices
         `cols` of Hc's columns."""
-        rows = sum(len(b[1]) for b in blocks)
-        used = sorted({int(v) for b in blocks for v in b[2]})
-        pos = np.full(max(used) + 1, -1, dtype=np.int64) if used else np.zeros(0, np.int64)
+        rows = sum(b[1].size for b in blocks)
+        used = np.unique(np.concatenate([b[2].reshape(-1) for b in blocks])) if blocks else np.zeros(0, np.int64)
+        pos = np.full(int(used.max()) + 1 if len(used) else 0, -1, dtype=np.int64)
         pos[used] = np.arange(len(used))
         H = np.zeros((rows, 6 * len(used)))
         r = np.empty(rows)
-        groups, at = {}, 0
-        for Hb, rb, slots in blocks:
-            groups.setdefault(Hb.shape, []).append((at, Hb, rb, slots))
-            at += len(rb)
-        for (a, c), items in groups.items():
-            starts = np.array([it[0] for it in items])
-            Hs = np.stack([it[1] for it in items])                                  # (F, a, 6m)
-            sl = pos[np.stack([it[3] for it in items])]                             # (F, m) -> compact column blocks
-            ri = starts[:, None] + np.arange(a)                                     # (F, a)
-            ci = ((6 * sl)[:, :, None] + np.arange(6)).reshape(len(items), c)       # (F, 6m)
-            H[ri[:, :, None], ci[:, None, :]] = Hs
-            r[ri] = np.stack([it[2] for it in items])
-        cols = (21 + 6 * np.array(used, dtype=np.int64)[:, None] + np.arange(6)).reshape(-1)
+        at = 0
+        for Hs, rs, sl in blocks:
+            n, a, c = Hs.shape
+            if len(used) * 6 == c and n and (sl == sl[0]).all() and (np.diff(sl[0]) > 0).all():
+                H[at:at + n * a] = Hs.reshape(n * a, c)                             # every feature on the same states,
+            else:                                                                   # in column order: already compact
+                ri = (at + a * np.arange(n))[:, None] + np.arange(a)                # (n, a)
+                ci = ((6 * pos[sl])[:, :, None] + np.arange(6)).reshape(n, c)       # (n, 6m)
+                H[ri[:, :, None], ci[:, None, :]] = Hs
+            r[at:at + n * a] = rs.reshape(-1)
+            at += n * a
+        cols = (21 + 6 * used[:, None] + np.arange(6)).reshape(-1)
         return H, r, cols
 
     def remove_lost_features(self):
@@ -802,13 +831,8 @@ class MSCKF:
             del self.map_server[fid]
         if not processed:
             return
-        blocks, rows = [], 0
-        for H, r, slots, ok in self._evaluate(processed, [list(f.observations) for f in processed], -1):
-            if ok:                                                    # gate dof = observations - 1 (msckf.py:661)
-                blocks.append((H, r, slots))
-                rows += len(r)
-            if rows > 1500:
-                break
+        # gate dof = observations - 1 (msckf.py:661); stacking stops after the feature that takes it past 1500 rows
+        blocks = self._evaluate(processed, [list(f.observations) for f in processed], -1, max_rows=1500)
         H, r, cols = self._stack(blocks)
         self.measurement_update(H, r, cols)
         for feat in processed:
@@ -854,11 +878,8 @@ class MSCKF:
                         del obs[c]
                     continue
             todo.append((feat, involved))
-        blocks = []
-        if todo:
-            for H, r, slots, ok in self._evaluate([t[0] for t in todo], [t[1] for t in todo], 0):
-                if ok:                                                # gate dof = involved states (msckf.py:763)
-                    blocks.append((H, r, slots))
+        # gate dof = involved states (msckf.py:763)
+        blocks = self._evaluate([t[0] for t in todo], [t[1] for t in todo], 0) if todo else []
         for feat, involved in todo:
             for c in involved:
                 del feat.observations[c]
