@@ -15,9 +15,10 @@ work is laid out, not what is computed:
   * the camera-state window lives in arrays (quaternions, positions, cached rotation matrices), not in per-state objects;
   * the transition matrix is assembled from its 3x3 blocks in closed form instead of three dense 21x21 products, the
     cross-covariance is propagated once per image with the accumulated transition matrix of the IMU batch;
-  * the measurement Jacobians of ALL observations of a feature are formed in one vectorised pass, the null-space basis
-    comes from a complete QR of the 4m x 3 feature Jacobian (the update and the gate are invariant to the choice of
-    orthonormal basis), and the projected rows are scattered straight into the stacked matrix;
+  * the measurement Jacobians of ALL observations of all features with the same number of camera states are formed in one
+    pass (per-observation blocks in C), the null-space basis comes from a complete QR of the 4m x 3 feature Jacobian (the
+    update and the gate are invariant to the choice of orthonormal basis), accepted features stay batched up to the
+    stacked matrix, which is kept compact in its non-zero columns (the thin QR and the update run on those alone);
   * no printing (the reference prints ~15 lines per frame), no per-frame file open unless an output file is asked for.
 Results agree with the reference to rounding (tests/test_msckf_host.py replays a 400-frame feature dump against the
 reference filter's committed trajectory).
