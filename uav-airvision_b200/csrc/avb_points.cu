@@ -7,7 +7,9 @@
 #ifndef AVB_WPF1_BLOCKS
 #define AVB_WPF1_BLOCKS 5            // resident CTAs per SM the 1-warp LK kernels are compiled for: 96 registers, no
                                      // spills.  Measured at 64 streams (frames/s): 8 CTAs (64 regs, 244 B spilled)
-                                     // 50,981; 6 (80 regs) 52,243; 5 (96 regs) 53,253; 4 (127 regs) 52,544
+                                     // 50,981; 6 (80 regs) 52,243; 5 (96 regs) 53,253; 4 (127 regs) 52,544.  Again
+                                     // after the template rewrite (r01h): 8 -> 58,182; 6 -> 59,130; 5 -> 61,541;
+                                     // 4 -> 59,260 (build variants with -DAVB_WPF1_BLOCKS=n via AVB_EXTRA_NVCC)
 #endif
 
 // Team decomposition of a 128-thread block: WPF = 1 -> four features per block (one warp each), WPF = 4 -> one
