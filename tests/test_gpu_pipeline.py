@@ -446,3 +446,30 @@ def test_live_front_end_plus_host_msckf_reproduces_the_reference_trajectory(gold
     dp, dq = np.abs(got[:, 2:5] - ref[:, 2:5]).max(), np.abs(got[:, 5:9] - ref[:, 5:9]).max()
     print(f'live VIO on the GPU box: {len(got)} poses, max |dp| {dp:.3g} m, |dq| {dq:.3g} against the reference filter')
     assert dp < 1e-6 and dq < 1e-6
+
+
+def test_run_sweep_cli_on_euroc_directories(tmp_path):
+    """run_sweep.py (the reference's run.bat as one job): two rendered sequences written in the EuRoC layout, two time
+    offsets each; every run leaves the reference's trajectory file (msckf.py:152-160) and a row of the metrics summary."""
+    import csv
+    from euroc import write_euroc
+    from run_sweep import COLUMNS, main
+    from synth_euroc import RoomSceneStream
+    paths = []
+    for q in range(2):
+        st = RoomSceneStream(FrontEndConfig(), n_frames=34, seed=20 + q, tex_size=512, amp=0.8 + 0.2 * q)
+        p = tmp_path / f'SEQ_{q:02d}'
+        write_euroc(str(p), st)
+        paths.append(str(p))
+    out = tmp_path / 'results'
+    assert main(['--path', *paths, '--offsets', '0', '0.3', '--workers', '2', '--out', str(out)]) == 0
+    rows = list(csv.DictReader(open(out / 'metrics_summary.csv')))
+    assert [r['dataset'] for r in rows] == ['SEQ_00', 'SEQ_00', 'SEQ_01', 'SEQ_01'] and list(rows[0]) == COLUMNS
+    assert [r['offset'] for r in rows] == ['0', '0.3', '0', '0.3']
+    for r in rows:
+        lines = open(out / 'txts' / f"output_{r['dataset']}_offset{r['offset']}.txt").read().strip().splitlines()
+        assert len(lines) == int(r['poses'])
+        if r['offset'] == '0':                                   # 28 frames per run: the filter publishes from frame 20 on
+            assert int(r['frames']) == 28 and len(lines) >= 5 and float(r['ate_rmse_m']) < 0.05
+            cols = lines[0].split()
+            assert len(cols) == 8 and abs(sum(float(c) ** 2 for c in cols[4:]) - 1.0) < 1e-6

@@ -31,7 +31,7 @@ def test_offset_start_equals_the_dataset_reader(tmp_path):
 
 def test_estimator_pool_equals_in_process_filter(golden_dir):
     """3 streams over 2 worker processes: every stream's trajectory equals the filter fed directly."""
-    from estimator_pool import EstimatorPool, feed
+    from estimator_pool import EstimatorPool, feed, state_row
     from frontend_config import FrontEndConfig, with_filter_fields
     from msckf import MSCKF
     cfg = with_filter_fields(FrontEndConfig())
@@ -53,7 +53,7 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
     for fr in frames:
         r = feed(est, *fr)
         if r is not None:
-            want.append([r.timestamp, *r.pose.t, *est.imu_state.orientation])
+            want.append(state_row(est))
     want = np.array(want)
     assert len(want) >= 20 and max(len(f[0]) for f in frames) > 128
     pool = EstimatorPool(cfg, 3, 2, capacity=300, depth=4)

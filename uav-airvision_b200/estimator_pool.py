@@ -47,6 +47,13 @@ def feed(est, imu_rows, ts, ids, meas):
     return est.feature_callback(feature_msg(float(ts), feats))
 
 
+def state_row(est):
+    """The columns the reference appends to its output file per published state (msckf.py:152-160):
+    IMU-state timestamp, position, JPL orientation quaternion (x, y, z, w)."""
+    st = est.imu_state
+    return [st.timestamp, *st.position, *st.orientation]
+
+
 class _Ring:
     """Views into one worker's shared-memory ring: [slot][stream] arrays."""
 
@@ -96,7 +103,7 @@ def _worker(shm_name, depth, cap, filled, free, conn, config, streams):
                 r = feed(est, ring.imu[slot, i, :n_imu], ring.ts[slot, i], ring.ids[slot, i, :n_feat], ring.meas[slot, i, :n_feat])
                 frames += 1
                 if r is not None:
-                    traj[i].append([r.timestamp, *r.pose.t, *est.imu_state.orientation])
+                    traj[i].append(state_row(est))
             busy += time.perf_counter() - t0
             free.release()
             slot = (slot + 1) % depth
