@@ -84,6 +84,11 @@ def test_write_then_read_round_trip_and_offset(tmp_path):
     assert len(list(ds.stereo)) == sum(1 for f in frames if f.timestamp >= ds.starttime + 0.22)
     kinds = [k for k, _ in ds.events()]
     assert kinds[-1] == 'stereo' and kinds.count('stereo') == len(list(ds.stereo))
+    # threaded decode-ahead (what fills a sweep's frame store): same messages, same order, start time honoured
+    pre = list(ds.stereo.prefetch(threads=3, depth=4))
+    assert [m.timestamp for m in pre] == [m.timestamp for m in ds.stereo]
+    assert all(np.array_equal(a.cam0_image, b.cam0_image) and np.array_equal(a.cam1_msg.image, b.cam1_image)
+               for a, b in zip(pre, ds.stereo))
     t_last_imu = None
     for k, m in ds.events():                                 # every IMU message precedes the first frame stamped after it
         if k == 'imu':

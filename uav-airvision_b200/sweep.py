@@ -40,7 +40,10 @@ class CachedSequence:
 
     def __init__(self, source, device=0, max_frames=None, name=None):
         self.name = name or getattr(source, 'path', type(source).__name__)
-        frames = source.frames() if hasattr(source, 'frames') else iter(source.stereo)
+        if hasattr(source, 'frames'):
+            frames = source.frames()
+        else:                                           # EuRoCDataset: decode ahead on several threads
+            frames = source.stereo.prefetch() if hasattr(source.stereo, 'prefetch') else iter(source.stereo)
         first = next(frames)
         h, w = first.cam0_image.shape
         n = max_frames if max_frames is not None else getattr(source, 'n', None)
