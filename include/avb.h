@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define AVB_ABI_VERSION 2
+#define AVB_ABI_VERSION 3   /* 3: + avb_store_*, avb_process_frame_gather, avb_enqueue_frame_gather (structs unchanged since 2) */
 
 #define AVB_OK              0
 #define AVB_E_INVALID      -1   /* bad argument / unsupported configuration */

@@ -114,7 +114,7 @@ def load():
     lib.avb_store_image.restype = C.c_void_p
     lib.avb_process_frame_gather.argtypes = [vp, vp, f64p, f64p]
     lib.avb_enqueue_frame_gather.argtypes = [vp, vp, f64p, f64p]
-    if lib.avb_abi_version() != 2:
+    if lib.avb_abi_version() != 3:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
     return lib
