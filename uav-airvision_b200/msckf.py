@@ -675,9 +675,13 @@ class MSCKF:
 
     def _gates(self, H, r, slots, dof):
         """msckf.py:605-612 for a batch: H by its non-zero column blocks.  Returns the boolean decisions."""
-        cols = (21 + 6 * slots)[:, :, None] + np.arange(6)                          # (F, m, 6)
-        cols = cols.reshape(len(H), -1)
-        P = self.state_cov[cols[:, :, None], cols[:, None, :]]                      # (F, 6m, 6m)
+        if (slots == slots[0]).all():                                               # the usual case: one set of states
+            c0 = ((21 + 6 * slots[0])[:, None] + np.arange(6)).reshape(-1)
+            P = self.state_cov[np.ix_(c0, c0)]                                      # (6m, 6m), broadcast over the features
+        else:
+            cols = (21 + 6 * slots)[:, :, None] + np.arange(6)                      # (F, m, 6)
+            cols = cols.reshape(len(H), -1)
+            P = self.state_cov[cols[:, :, None], cols[:, None, :]]                  # (F, 6m, 6m)
         S = H @ P @ H.transpose(0, 2, 1)
         S[:, np.arange(S.shape[1]), np.arange(S.shape[1])] += self.config.observation_noise
         gamma = np.einsum('fa,fa->f', r, np.linalg.solve(S, r[:, :, None])[:, :, 0])
