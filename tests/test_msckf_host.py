@@ -45,13 +45,13 @@ def _msckf_config():
     return cfg
 
 
-def _replay(golden_dir, n_frames=None):
+def _replay(golden_dir, n_frames=None, **kw):
     from msckf import MSCKF
     z = np.load(os.path.join(golden_dir, 'ate_gpu_features.npz'))
     g = np.load(os.path.join(golden_dir, 'ref_msckf_traj.npz'))
     imu = g['imu']
     n = int(z['n_frames'][0]) if n_frames is None else n_frames
-    est = MSCKF(_msckf_config(), outfile=False)
+    est = MSCKF(_msckf_config(), outfile=False, **kw)
     rows, secs, j = [], [], 0
     for k in range(n):
         ts = float(z[f'f{k}_ts'][0])
@@ -82,6 +82,15 @@ def test_trajectory_equals_reference_filter(golden_dir):
           f'{1e3 * np.median(secs[20:]):.2f} ms/frame here vs {ref_ms:.2f} ms/frame for the reference when the fixture was made')
     assert dp < 1e-6 and dq < 1e-6 and dv < 1e-5
     assert est.large_update_count == 0
+
+
+def test_c_inner_loops_equal_their_numpy_statement(golden_dir):
+    """_msckfhost (propagation, triangulation, Jacobian blocks, null-space projection) against the numpy statements kept
+    in msckf.py: the same 120 frames through both."""
+    a = _replay(golden_dir, 120, use_c=True)[0]
+    b = _replay(golden_dir, 120, use_c=False)[0]
+    assert a.shape == b.shape and len(a) == 100 and np.array_equal(a[:, 12:], b[:, 12:])
+    assert np.abs(a[:, 2:12] - b[:, 2:12]).max() < 1e-9
 
 
 def test_returns_none_until_gravity_is_initialised_and_reset(golden_dir):

@@ -485,7 +485,92 @@ static PyObject* py_jacobians(PyObject* self, PyObject* args) {
     return ret;
 }
 
+/* ---- projection onto the left null space of the feature Jacobian (msckf.py:504-540 of the reference) -------------------
+ * null_project(Hx (F,m,4,6), Hf (F,4m,3), r (F,4m), H out (F,4m-3,6m), rp out (F,4m-3))
+ * Per feature: three Householder reflectors triangularise H_f (the QR numpy's `qr(..., mode='complete')` does through
+ * LAPACK); applied to the block-sparse H_x (observation k fills rows 4k..4k+3, columns 6k..6k+5) and to r, the rows
+ * below the third are Q[:, 3:]^T H_x and Q[:, 3:]^T r.  Any orthonormal basis of the null space gives the same gate and
+ * the same update. */
+static PyObject* py_null_project(PyObject* self, PyObject* args) {
+    PyObject* o[5];
+    if (!PyArg_ParseTuple(args, "OOOOO", &o[0], &o[1], &o[2], &o[3], &o[4])) return NULL;
+    static const char* names[5] = {"Hx", "Hf", "r", "H", "rp"};
+    Py_buffer b[5];
+    int got = 0;
+    for (; got < 5; ++got)
+        if (get_buf(o[got], &b[got], 1, got >= 3, names[got]) < 0) break;
+    PyObject* ret = NULL;
+    if (got == 5) {
+        const Py_ssize_t fm = b[0].len / 192;                    /* F * m */
+        Py_ssize_t F = 0, m = 0;
+        /* F from r and rp: r has 4m per feature, rp 4m - 3:  len(r) - len(rp) = 3 F doubles */
+        if (b[2].len >= b[4].len) F = (b[2].len - b[4].len) / 24;
+        if (F > 0) m = fm / F;
+        const Py_ssize_t rows = 4 * m, cols = 6 * m;
+        if (F <= 0 || m <= 0 || fm != F * m || rows < 4 || b[0].len != fm * 192 || b[1].len != F * rows * 24 ||
+            b[2].len != F * rows * 8 || b[3].len != F * (rows - 3) * cols * 8 || b[4].len != F * (rows - 3) * 8) {
+            PyErr_SetString(PyExc_ValueError, "null_project: inconsistent array sizes");
+        } else {
+            const double *Hxa = b[0].buf, *Hfa = b[1].buf, *ra = b[2].buf;
+            double *Ha = b[3].buf, *rpa = b[4].buf;
+            double* W = PyMem_Malloc(sizeof(double) * (size_t)(rows * cols + rows * 3 + rows));
+            if (!W) {
+                PyErr_NoMemory();
+            } else {
+                double *D = W, *A = W + rows * cols, *rr = A + rows * 3;
+                for (Py_ssize_t f = 0; f < F; ++f) {
+                    memset(D, 0, sizeof(double) * (size_t)(rows * cols));
+                    for (Py_ssize_t k = 0; k < m; ++k)
+                        for (int a = 0; a < 4; ++a)
+                            memcpy(D + (4 * k + a) * cols + 6 * k, Hxa + ((f * m + k) * 4 + a) * 6, 6 * sizeof(double));
+                    memcpy(A, Hfa + f * rows * 3, sizeof(double) * (size_t)(rows * 3));
+                    memcpy(rr, ra + f * rows, sizeof(double) * (size_t)rows);
+                    for (int j = 0; j < 3; ++j) {
+                        double xn2 = 0.0;
+                        for (Py_ssize_t i = j + 1; i < rows; ++i) xn2 += A[i * 3 + j] * A[i * 3 + j];
+                        if (xn2 == 0.0) continue;                 /* already triangular in this column: H = I */
+                        const double alpha = A[j * 3 + j];
+                        const double beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                        const double tau = (beta - alpha) / beta, sc = 1.0 / (alpha - beta);
+                        /* v = (1, A[j+1:, j] * sc); apply I - tau v v^T to the later columns of A, to D and to r */
+                        for (int c = j + 1; c < 3; ++c) {
+                            double w = A[j * 3 + c];
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) w += A[i * 3 + j] * sc * A[i * 3 + c];
+                            w *= tau;
+                            A[j * 3 + c] -= w;
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) A[i * 3 + c] -= A[i * 3 + j] * sc * w;
+                        }
+                        for (Py_ssize_t c = 0; c < cols; ++c) {
+                            double w = D[j * cols + c];
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) w += A[i * 3 + j] * sc * D[i * cols + c];
+                            if (w == 0.0) continue;
+                            w *= tau;
+                            D[j * cols + c] -= w;
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) D[i * cols + c] -= A[i * 3 + j] * sc * w;
+                        }
+                        {
+                            double w = rr[j];
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) w += A[i * 3 + j] * sc * rr[i];
+                            w *= tau;
+                            rr[j] -= w;
+                            for (Py_ssize_t i = j + 1; i < rows; ++i) rr[i] -= A[i * 3 + j] * sc * w;
+                        }
+                    }
+                    memcpy(Ha + f * (rows - 3) * cols, D + 3 * cols, sizeof(double) * (size_t)((rows - 3) * cols));
+                    memcpy(rpa + f * (rows - 3), rr + 3, sizeof(double) * (size_t)(rows - 3));
+                }
+                PyMem_Free(W);
+                ret = Py_None;
+                Py_INCREF(ret);
+            }
+        }
+    }
+    for (int i = 0; i < got; ++i) PyBuffer_Release(&b[i]);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"null_project", py_null_project, METH_VARARGS, "Projection of H_x and r onto the left null space of H_f."},
     {"jacobians", py_jacobians, METH_VARARGS, "Stereo measurement Jacobians of F features x m camera states."},
     {"propagate", py_propagate, METH_VARARGS, "IMU batch propagation (msckf.py:251-388 of the reference)."},
     {"triangulate", py_triangulate, METH_VARARGS, "Levenberg-Marquardt feature triangulation on inverse depth."},

@@ -668,6 +668,10 @@ class MSCKF:
         else:
             Hx, Hf, r = self._jacobian_blocks(R0, cams.p[slots], cams.R_null[slots], cams.p_null[slots], p_w, Z)
         # left null space of H_f: the last 4m - 3 columns of its complete QR
+        if self.use_c:
+            H, rp = np.empty((F, 4 * m - 3, 6 * m)), np.empty((F, 4 * m - 3))
+            _C.null_project(Hx, Hf, r, H, rp)
+            return H, rp, slots
         Q, _ = np.linalg.qr(Hf, mode='complete')
         At = Q[:, :, 3:].transpose(0, 2, 1)                                         # (F, 4m - 3, 4m)
         H = np.einsum('fakr,fkrc->fakc', At.reshape(F, 4 * m - 3, m, 4), Hx).reshape(F, 4 * m - 3, 6 * m)
