@@ -312,32 +312,10 @@ static double lm_cost(const double* Rs, const double* ts, const double* zs, Py_s
 
 /* triangulate(Rs (k x 3 x 3), ts (k x 3), zs (k x 2), x0 (3), huber, precision, damping, outer_max, inner_max) -> (alpha, beta, rho)
  * k camera poses relative to the first cam0 (x_ci = R x_c0 + t), their normalized measurements, initial (alpha, beta, rho). */
-static PyObject* py_triangulate(PyObject* self, PyObject* args) {
-    PyObject *oR, *ot, *oz, *ox;
-    double huber, precision, lambd;
-    int outer_max, inner_max;
-    if (!PyArg_ParseTuple(args, "OOOOdddii", &oR, &ot, &oz, &ox, &huber, &precision, &lambd, &outer_max, &inner_max)) return NULL;
-    Py_buffer bR, bt, bz, bx;
-    if (get_buf(oR, &bR, 9, 0, "Rs") < 0) return NULL;
-    const Py_ssize_t k = bR.len / 72;
-    if (get_buf(ot, &bt, 3 * k, 0, "ts") < 0) {
-        PyBuffer_Release(&bR);
-        return NULL;
-    }
-    if (get_buf(oz, &bz, 2 * k, 0, "zs") < 0) {
-        PyBuffer_Release(&bR);
-        PyBuffer_Release(&bt);
-        return NULL;
-    }
-    if (get_buf(ox, &bx, 3, 0, "x0") < 0) {
-        PyBuffer_Release(&bR);
-        PyBuffer_Release(&bt);
-        PyBuffer_Release(&bz);
-        return NULL;
-    }
-    const double *Rs = bR.buf, *ts = bt.buf, *zs = bz.buf;
-    double sol[3];
-    memcpy(sol, bx.buf, sizeof sol);
+/* Levenberg-Marquardt on (alpha, beta, rho) over k views x_i = R_i x + t_i (feature_position_initializer.py:31-70);
+ * `inner` counts over the whole optimisation, as in the reference.  Returns -1 when the normal equations are singular. */
+static int lm_solve(const double* Rs, const double* ts, const double* zs, Py_ssize_t k, double* sol, double huber, double precision,
+                    double lambd, int outer_max, int inner_max) {
     int outer = 0, inner = 0, singular = 0;
     double delta_norm = INFINITY, total = lm_cost(Rs, ts, zs, k, sol);
     while (outer < outer_max && delta_norm > precision && !singular) {
@@ -378,7 +356,7 @@ static PyObject* py_triangulate(PyObject* self, PyObject* args) {
             const double nc = lm_cost(Rs, ts, zs, k, ns);
             if (nc < total) {
                 reduced = 1;
-                memcpy(sol, ns, sizeof sol);
+                memcpy(sol, ns, 3 * sizeof(double));
                 total = nc;
                 lambd = fmax(lambd / 10.0, 1e-10);
             } else {
@@ -388,6 +366,36 @@ static PyObject* py_triangulate(PyObject* self, PyObject* args) {
         }
         ++outer;
     }
+    return singular ? -1 : 0;
+}
+
+static PyObject* py_triangulate(PyObject* self, PyObject* args) {
+    PyObject *oR, *ot, *oz, *ox;
+    double huber, precision, lambd;
+    int outer_max, inner_max;
+    if (!PyArg_ParseTuple(args, "OOOOdddii", &oR, &ot, &oz, &ox, &huber, &precision, &lambd, &outer_max, &inner_max)) return NULL;
+    Py_buffer bR, bt, bz, bx;
+    if (get_buf(oR, &bR, 9, 0, "Rs") < 0) return NULL;
+    const Py_ssize_t k = bR.len / 72;
+    if (get_buf(ot, &bt, 3 * k, 0, "ts") < 0) {
+        PyBuffer_Release(&bR);
+        return NULL;
+    }
+    if (get_buf(oz, &bz, 2 * k, 0, "zs") < 0) {
+        PyBuffer_Release(&bR);
+        PyBuffer_Release(&bt);
+        return NULL;
+    }
+    if (get_buf(ox, &bx, 3, 0, "x0") < 0) {
+        PyBuffer_Release(&bR);
+        PyBuffer_Release(&bt);
+        PyBuffer_Release(&bz);
+        return NULL;
+    }
+    const double *Rs = bR.buf, *ts = bt.buf, *zs = bz.buf;
+    double sol[3];
+    memcpy(sol, bx.buf, sizeof sol);
+    const int singular = lm_solve(Rs, ts, zs, k, sol, huber, precision, lambd, outer_max, inner_max) < 0;
     PyBuffer_Release(&bR);
     PyBuffer_Release(&bt);
     PyBuffer_Release(&bz);
@@ -397,6 +405,77 @@ static PyObject* py_triangulate(PyObject* self, PyObject* args) {
         return NULL;
     }
     return Py_BuildValue("(ddd)", sol[0], sol[1], sol[2]);
+}
+
+/* triangulate_world(Rw (m,3,3), pw (m,3), Z (m,4), R01 (3,3), t01 (3), huber, precision, lambd, outer_max, inner_max)
+ *   -> (x, y, z, valid): MSCKF.initialize_position in one call.  Poses of cam0 / cam1 of every observation relative to
+ *   the first cam0, the two-view initial guess from the first stereo pair, the LM refinement, the positive-depth check
+ *   and the feature position in the world frame (feature_position_initializer.py:6-76, feature_depth_estimator.py:4-14). */
+static PyObject* py_triangulate_world(PyObject* self, PyObject* args) {
+    PyObject *oR, *op, *oz, *o01, *ot01;
+    double huber, precision, lambd;
+    int outer_max, inner_max;
+    if (!PyArg_ParseTuple(args, "OOOOOdddii", &oR, &op, &oz, &o01, &ot01, &huber, &precision, &lambd, &outer_max, &inner_max)) return NULL;
+    Py_buffer b[5];
+    PyObject* objs[5] = {oR, op, oz, o01, ot01};
+    static const char* names[5] = {"Rw", "pw", "Z", "R01", "t01"};
+    int got = 0;
+    for (; got < 5; ++got)
+        if (get_buf(objs[got], &b[got], 1, 0, names[got]) < 0) break;
+    PyObject* ret = NULL;
+    if (got == 5) {
+        const Py_ssize_t m = b[0].len / 72;
+        if (m < 1 || b[0].len != m * 72 || b[1].len != m * 24 || b[2].len != m * 32 || b[3].len != 72 || b[4].len != 24) {
+            PyErr_SetString(PyExc_ValueError, "triangulate_world: inconsistent array sizes");
+        } else {
+            const double *Rw = b[0].buf, *pw = b[1].buf, *Z = b[2].buf, *R01 = b[3].buf, *t01 = b[4].buf;
+            double* W = PyMem_Malloc(sizeof(double) * (size_t)(2 * m) * (9 + 3 + 2));
+            if (!W) {
+                PyErr_NoMemory();
+            } else {
+                double *Rs = W, *ts = W + 18 * m, *zs = ts + 6 * m;
+                const double *R0w = Rw, *p0 = pw;
+                for (Py_ssize_t i = 0; i < m; ++i) {
+                    double* Rc0 = Rs + 18 * i;
+                    double* Rc1 = Rc0 + 9;
+                    double *tc0 = ts + 6 * i, *tc1 = tc0 + 3;
+                    const double d[3] = {p0[0] - pw[3 * i], p0[1] - pw[3 * i + 1], p0[2] - pw[3 * i + 2]};
+                    mat3_mul_bt(Rw + 9 * i, R0w, Rc0);
+                    mat3_vec(Rw + 9 * i, d, tc0);
+                    mat3_mul(R01, Rc0, Rc1);
+                    mat3_vec(R01, tc0, tc1);
+                    tc1[0] += t01[0];
+                    tc1[1] += t01[1];
+                    tc1[2] += t01[2];
+                    memcpy(zs + 4 * i, Z + 4 * i, 4 * sizeof(double));
+                }
+                const double z1[3] = {zs[0], zs[1], 1.0};
+                double mm[3];
+                mat3_vec(Rs + 9, z1, mm);
+                const double a0 = mm[0] - zs[2] * mm[2], a1 = mm[1] - zs[3] * mm[2];
+                const double b0 = zs[2] * ts[5] - ts[3], b1 = zs[3] * ts[5] - ts[4];
+                const double depth = (a0 * b0 + a1 * b1) / (a0 * a0 + a1 * a1);
+                double sol[3] = {zs[0], zs[1], 1.0 / depth};
+                if (lm_solve(Rs, ts, zs, 2 * m, sol, huber, precision, lambd, outer_max, inner_max) < 0) {
+                    PyErr_SetString(PyExc_ArithmeticError, "singular normal equations in feature triangulation");
+                } else {
+                    const double fin[3] = {sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]};
+                    int valid = 1;
+                    for (Py_ssize_t i = 0; i < 2 * m; ++i) {
+                        const double* R = Rs + 9 * i;
+                        const double dep = (R[6] * fin[0] + R[7] * fin[1] + R[8] * fin[2]) + ts[3 * i + 2];
+                        if (!(dep > 0)) valid = 0;
+                    }
+                    double pos[3];
+                    mat3_tvec(R0w, fin, pos);
+                    ret = Py_BuildValue("(dddi)", pos[0] + p0[0], pos[1] + p0[1], pos[2] + p0[2], valid);
+                }
+                PyMem_Free(W);
+            }
+        }
+    }
+    for (int i = 0; i < got; ++i) PyBuffer_Release(&b[i]);
+    return ret;
 }
 
 /* ---- stereo measurement Jacobians of F features x m camera states (msckf.py:443-502 of the reference) ------------------
@@ -574,6 +653,7 @@ static PyMethodDef methods[] = {
     {"jacobians", py_jacobians, METH_VARARGS, "Stereo measurement Jacobians of F features x m camera states."},
     {"propagate", py_propagate, METH_VARARGS, "IMU batch propagation (msckf.py:251-388 of the reference)."},
     {"triangulate", py_triangulate, METH_VARARGS, "Levenberg-Marquardt feature triangulation on inverse depth."},
+    {"triangulate_world", py_triangulate_world, METH_VARARGS, "MSCKF.initialize_position in one call: relative poses, guess, LM, depth check."},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_msckfhost", "Scalar inner loops of the host MSCKF.", -1, methods};

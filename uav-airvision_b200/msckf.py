@@ -523,6 +523,13 @@ class MSCKF:
         # poses of cam0 / cam1 of every observation, expressed relative to the first cam0: x_ci = R x_c0 + t
         Rw = cams.R[slots]                                                       # world -> cam0_i
         pw = cams.p[slots]
+        if self.use_c:                  # the statements below, in one call
+            x, y, z, valid = _C.triangulate_world(Rw, pw, np.ascontiguousarray(Z), self.R_cam0_cam1, self.t_cam0_cam1,
+                                                  oc.huber_epsilon, oc.estimation_precision, oc.initial_damping,
+                                                  oc.outer_loop_max_iteration, oc.inner_loop_max_iteration)
+            feat.position = np.array([x, y, z])
+            feat.is_initialized = bool(valid)
+            return feat.is_initialized
         R0w, p0 = Rw[0], pw[0]
         R_c0 = Rw @ R0w.T                                                        # (m, 3, 3)
         t_c0 = np.einsum('mij,mj->mi', Rw, p0 - pw)
