@@ -402,7 +402,7 @@ def main():
     n_prof = 12
     # multi-stream leg = BASELINE config C4: `--streams` (64) independent time-offset runs in total, sharded over the GPUs
     S_ms = max(1, args.streams // world) if args.streams > 0 else 0
-    n_extra = (2 * (S_ms - 1) + 4 + 1 + args.ms_steps + 2) if S_ms > 0 else 0
+    n_extra = (2 * (S_ms - 1) + max(4 + 1 + args.ms_steps + 2, 105)) if S_ms > 0 else 0      # >= 100 timed steps for the store-fed sweep
     n = max(W + K + 1 + n_prof, n_extra)
     stream = make_sequence(skw, n)
     frames = [stream.frame(k) for k in range(n)]
