@@ -6,7 +6,7 @@ same constructor argument, `imu_callback(imu_msg)`, `feature_callback(feature_ms
 reference that shapes the trajectory kept: 21-dimensional IMU error state, third-order transition matrix with the
 observability-constrained null-space fix (msckf.py:274-338), RK4 state prediction (:340-388), 6-dof camera-state
 augmentation (:390-423), Levenberg-Marquardt triangulation (feature/feature_position_initializer.py:6-76), left
-null-space projection, chi-square gating at chi2.ppf(0.05, dof) (:111-113, :605-612), thin-QR measurement compression,
+null-space projection, chi-square gating at chi2.ppf(0.05, dof) (:111-113, :605-612), measurement compression,
 the `(I - K H) P` covariance update (:600-603), the two-out-of-the-window pruning rule (:678-786), online reset (:822-843).
 
 SURVEY.md section 8(f3): this runs on the host, not on the GPU -- at ~0.13 ms per frame the front end leaves the filter as
@@ -18,7 +18,8 @@ work is laid out, not what is computed:
   * the measurement Jacobians of ALL observations of all features with the same number of camera states are formed in one
     pass (per-observation blocks in C), the null-space basis comes from a complete QR of the 4m x 3 feature Jacobian (the
     update and the gate are invariant to the choice of orthonormal basis), accepted features stay batched up to the
-    stacked matrix, which is kept compact in its non-zero columns (the thin QR and the update run on those alone);
+    stacked matrix, which is kept compact in its non-zero columns; the update is computed from H^T H and H^T r on those
+    columns (what the reference's thin QR compresses to, without the QR: same K r and (I - K H) P);
   * no printing (the reference prints ~15 lines per frame), no per-frame file open unless an output file is asked for.
 Results agree with the reference to rounding (tests/test_msckf_host.py replays a 400-frame feature dump against the
 reference filter's committed trajectory).
@@ -734,28 +735,19 @@ class MSCKF:
         two camera states that leave: 12 of up to 120 columns)."""
         if len(Hc) == 0 or len(r) == 0:
             return
-        nc = len(cols)
-        if Hc.shape[0] > nc:
-            # Thin QR as in the reference (msckf.py:548-554), on the non-zero columns alone, and without forming Q: Q^T r
-            # comes from the Householder reflectors (dgeqrf + dormqr).  R scattered into `cols` and the reference's R have
-            # the same Gram matrix H^T H and the same H^T r, which is all K r and (I - K H) P depend on.
-            from scipy.linalg import get_lapack_funcs
-            Hf = np.asfortranarray(Hc)
-            geqrf, ormqr = get_lapack_funcs(('geqrf', 'ormqr'), (Hf,))
-            qr_, tau, _, info = geqrf(Hf, overwrite_a=True)
-            c = np.asfortranarray(r.reshape(-1, 1))
-            cq, _, info2 = ormqr('L', 'T', qr_, tau, c, max(64 * c.shape[0], 1), overwrite_c=True)
-            if info != 0 or info2 != 0:
-                raise np.linalg.LinAlgError('QR of the stacked measurement Jacobian failed')
-            H_thin, r_thin = np.triu(qr_[:nc]), cq[:nc, 0]
-        else:
-            H_thin, r_thin = Hc, r
+        # K r and (I - K H) P depend on H only through G = H^T H and b = H^T r (push-through identity:
+        # H^T (H P H^T + s I)^-1 = (G P + s I)^-1 H^T), so neither the reference's thin QR of the stacked Jacobian
+        # (msckf.py:548-554; 4 ms for 1500 x 120) nor the row-sized S is formed: with E selecting the non-zero columns,
+        #   K r = P E (G P_cc + s I)^-1 b,      K H P = P E (G P_cc + s I)^-1 G E^T P
+        # -- one nc x nc solve with 1 + n right-hand sides, whatever the number of rows.
         P = self.state_cov
-        HP = H_thin @ P[cols]                                         # H P with H's zero columns skipped
-        S = HP[:, cols] @ H_thin.T
-        S[np.diag_indices(len(S))] += self.config.observation_noise
-        Kt = np.linalg.solve(S, HP)
-        delta = Kt.T @ r_thin
+        G = Hc.T @ Hc
+        Pc = P[cols]                                                  # (nc, n) = E^T P
+        M = G @ Pc[:, cols]
+        M[np.diag_indices(len(M))] += self.config.observation_noise
+        X = np.linalg.solve(M, np.column_stack([Hc.T @ r, G @ Pc]))   # (nc, 1 + n)
+        delta = Pc.T @ X[:, 0]
+        KHP = Pc.T @ X[:, 1:]
 
         st = self.imu_state
         d_imu = delta[:21]
@@ -801,7 +793,7 @@ class MSCKF:
         cams.R[:n] = _rotations(qn)
         cams.p[:n] += dc[:, 3:]
         cams.p_null[:n] = cams.p[:n]
-        Pn = P - Kt.T @ HP                                            # (I - K H) P
+        Pn = P - KHP                                                  # (I - K H) P
         self.state_cov = (Pn + Pn.T) / 2.0
 
     def _stack(self, blocks):
