@@ -358,7 +358,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
         for (int p = 0; p < 2 && r == AVB_OK; ++p) {
             r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 160, 36);
             if (r == AVB_OK) r = make_map(c, enc, &c->maps.pair0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 44);
-            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 24);
+            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 40);
         }
         for (int l = 1; l < g.nlev - 1 && r == AVB_OK; ++l)
             r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,

@@ -4,17 +4,17 @@
 //   best  = max over the 16 arcs of 9 contiguous ring pixels of min(ring - c) / min(c - ring)
 //   corner <=> best > thr;  response = best - 1;  tested only for 3 <= x <= W-4, 3 <= y <= H-4
 //   keypoint <=> response strictly greater than the 8 neighbours' responses (non-corners = 0)
-// The score map never goes to HBM: each CTA scores a (64+2) x (16+2) patch in shared memory and
-// suppresses its 64x16 interior.  Keypoints are appended to the bucket of their grid cell as a
+// The score map never goes to HBM: each CTA scores a (64+2) x (32+2) patch in shared memory and
+// suppresses its 64x32 interior.  Keypoints are appended to the bucket of their grid cell as a
 // 32-bit key (response << 24 | inverted scan index) so every later ranking is a plain integer max
 // that equals the reference's stable sort by response (Appendix B9).
 #include "avb_common.cuh"
 
 #define FT_W 64
-#define FT_H 16
+#define FT_H 32
 #define FB_W 96                     // TMA box: 16 left halo (TMA start column must be a 16-byte multiple) + FT_W + 16
 #define FB_X 16
-#define FB_H 24                     // FT_H + 8
+#define FB_H 40                     // FT_H + 8
 #define SC_PITCH 68
 
 __device__ __forceinline__ void f_mbar_init(uint64_t* bar, int count) {
