@@ -85,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _stamp(HOST_EXT, HOST_DEPS)
     if force or _stale(MSCKF_EXT, [os.path.join(CSRC, 'msckf_host.c'), os.path.abspath(__file__)]):
         inc = sysconfig.get_paths()['include']
-        _run([os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-ffp-contract=off', '-Wall', '-I', inc,
+        _run([os.environ.get('CC', 'gcc'), '-O3', '-fPIC', '-shared', '-ffp-contract=off', '-Wall', '-I', inc,
               os.path.join(CSRC, 'msckf_host.c'), '-o', MSCKF_EXT, '-lm'], verbose, 'gcc (_msckfhost)')
         _stamp(MSCKF_EXT, [os.path.join(CSRC, 'msckf_host.c'), os.path.abspath(__file__)])
     return LIB

@@ -648,7 +648,134 @@ static PyObject* py_null_project(PyObject* self, PyObject* args) {
     return ret;
 }
 
+/* ---- chi-square gate statistic without the projected Jacobian (msckf.py:605-612 of the reference) ---------------------
+ * gate(Hx (F,m,4,6), Hf (F,4m,3), r (F,4m), P (n,n), slots int64 (F,m), sigma, gamma out (F))
+ * The reference computes gamma = r_p^T (H_p P H_p^T + s I)^-1 r_p with H_p = A^T H_x, r_p = A^T r, A an orthonormal
+ * basis of the left null space of H_f.  With W = H_x P H_x^T + s I (4m x 4m) this is r^T A (A^T W A)^-1 A^T r, and for
+ * [A N] orthogonal, range(N) = range(H_f):
+ *     A (A^T W A)^-1 A^T = W^-1 - W^-1 H_f (H_f^T W^-1 H_f)^-1 H_f^T W^-1,
+ * so one Cholesky of W with four right-hand sides (r and the three columns of H_f) gives gamma.  H_x is block diagonal
+ * (observation k: rows 4k.., columns of camera state slots[k]), so W costs ~500 m^2 flops instead of the ~500 m^3 of the
+ * dense products. */
+static PyObject* py_gate(PyObject* self, PyObject* args) {
+    PyObject *oHx, *oHf, *orr, *oP, *osl, *og;
+    double sigma;
+    if (!PyArg_ParseTuple(args, "OOOOOdO", &oHx, &oHf, &orr, &oP, &osl, &sigma, &og)) return NULL;
+    Py_buffer bHx, bHf, br, bP, bs, bg;
+    if (get_buf(oHx, &bHx, 1, 0, "Hx") < 0) return NULL;
+    if (get_buf(oHf, &bHf, 1, 0, "Hf") < 0) { PyBuffer_Release(&bHx); return NULL; }
+    if (get_buf(orr, &br, 1, 0, "r") < 0) { PyBuffer_Release(&bHx); PyBuffer_Release(&bHf); return NULL; }
+    if (get_buf(oP, &bP, 1, 0, "P") < 0) { PyBuffer_Release(&bHx); PyBuffer_Release(&bHf); PyBuffer_Release(&br); return NULL; }
+    if (get_buf(osl, &bs, 1, 0, "slots") < 0) {
+        PyBuffer_Release(&bHx); PyBuffer_Release(&bHf); PyBuffer_Release(&br); PyBuffer_Release(&bP);
+        return NULL;
+    }
+    if (get_buf(og, &bg, 1, 1, "gamma") < 0) {
+        PyBuffer_Release(&bHx); PyBuffer_Release(&bHf); PyBuffer_Release(&br); PyBuffer_Release(&bP); PyBuffer_Release(&bs);
+        return NULL;
+    }
+    PyObject* ret = NULL;
+    const Py_ssize_t F = bg.len / 8, fm = bs.len / 8;
+    const Py_ssize_t m = F > 0 ? fm / F : 0, R = 4 * m;
+    Py_ssize_t n = 0;
+    while (n * n * 8 < bP.len) ++n;
+    if (F <= 0 || m <= 0 || fm != F * m || bHx.len != fm * 192 || bHf.len != F * R * 24 || br.len != F * R * 8 || n * n * 8 != bP.len) {
+        PyErr_SetString(PyExc_ValueError, "gate: inconsistent array sizes");
+    } else {
+        const double *Hxa = bHx.buf, *Hfa = bHf.buf, *ra = br.buf, *P = bP.buf;
+        const long long* sl = bs.buf;
+        double* gam = bg.buf;
+        double* Wk = PyMem_Malloc(sizeof(double) * (size_t)(R * 6 * m + R * R + R * 4));
+        int bad = 0;
+        if (!Wk) {
+            PyErr_NoMemory();
+        } else {
+            double *HP = Wk, *W = Wk + R * 6 * m, *B = W + R * R;     /* HP (R x 6m), W (R x R), B (R x 4) = [r | Hf] */
+            for (Py_ssize_t f = 0; f < F && !bad; ++f) {
+                const long long* s = sl + f * m;
+                for (Py_ssize_t k = 0; k < m; ++k)
+                    if (21 + 6 * s[k] + 6 > n || s[k] < 0) bad = 1;
+                if (bad) break;
+                /* HP[4k+a, 6l+b] = sum_c Hx[k][a][c] P[21+6 s_k + c, 21 + 6 s_l + b]: rows of P streamed contiguously */
+                for (Py_ssize_t k = 0; k < m; ++k) {
+                    const double* hx = Hxa + (f * m + k) * 24;
+                    for (int a = 0; a < 4; ++a) {
+                        double* out = HP + (4 * k + a) * 6 * m;
+                        for (Py_ssize_t j = 0; j < 6 * m; ++j) out[j] = 0.0;
+                        for (int c = 0; c < 6; ++c) {
+                            const double h = hx[6 * a + c];
+                            const double* prow = P + (21 + 6 * s[k] + c) * n + 21;
+                            for (Py_ssize_t l = 0; l < m; ++l) {
+                                const double* pb = prow + 6 * s[l];
+                                double* o = out + 6 * l;
+                                for (int b2 = 0; b2 < 6; ++b2) o[b2] += h * pb[b2];
+                            }
+                        }
+                    }
+                }
+                /* W = HP Hx^T + sigma I (lower triangle): W[i, 4l+a] = sum_b HP[i, 6l+b] Hx[l][a][b] */
+                for (Py_ssize_t i = 0; i < R; ++i)
+                    for (Py_ssize_t l = 0; 4 * l <= i; ++l) {
+                        const double* hx = Hxa + (f * m + l) * 24;
+                        const double* hp = HP + i * 6 * m + 6 * l;
+                        for (int a = 0; a < 4; ++a)
+                            W[i * R + 4 * l + a] = ((hp[0] * hx[6 * a] + hp[1] * hx[6 * a + 1]) + (hp[2] * hx[6 * a + 2] + hp[3] * hx[6 * a + 3])) +
+                                                   (hp[4] * hx[6 * a + 4] + hp[5] * hx[6 * a + 5]);
+                    }
+                for (Py_ssize_t i = 0; i < R; ++i) W[i * R + i] += sigma;
+                /* Cholesky W = L L^T, right-looking on the lower triangle (the updates are axpys over contiguous rows) */
+                for (Py_ssize_t j = 0; j < R && !bad; ++j) {
+                    double d = W[j * R + j];
+                    if (!(d > 0.0)) { bad = 2; break; }
+                    d = sqrt(d);
+                    W[j * R + j] = d;
+                    const double id = 1.0 / d;
+                    for (Py_ssize_t i = j + 1; i < R; ++i) W[i * R + j] *= id;
+                    for (Py_ssize_t i = j + 1; i < R; ++i) {
+                        const double lij = W[i * R + j];
+                        double* wi = W + i * R;
+                        for (Py_ssize_t k = j + 1; k <= i; ++k) wi[k] -= lij * W[k * R + j];
+                    }
+                }
+                if (bad) break;
+                /* Y = L^-1 [r | Hf]  (forward substitution, 4 right-hand sides) */
+                for (Py_ssize_t i = 0; i < R; ++i) {
+                    double v[4] = {ra[f * R + i], Hfa[(f * R + i) * 3], Hfa[(f * R + i) * 3 + 1], Hfa[(f * R + i) * 3 + 2]};
+                    for (Py_ssize_t k = 0; k < i; ++k)
+                        for (int c = 0; c < 4; ++c) v[c] -= W[i * R + k] * B[k * 4 + c];
+                    for (int c = 0; c < 4; ++c) B[i * 4 + c] = v[c] / W[i * R + i];
+                }
+                /* with y = L^-1 r, Z = L^-1 Hf:  r^T W^-1 r = y.y,  Hf^T W^-1 r = Z^T y,  Hf^T W^-1 Hf = Z^T Z */
+                double yy = 0.0, q[3] = {0, 0, 0}, G[9] = {0};
+                for (Py_ssize_t i = 0; i < R; ++i) {
+                    const double* bi = B + 4 * i;
+                    yy += bi[0] * bi[0];
+                    for (int a = 0; a < 3; ++a) {
+                        q[a] += bi[1 + a] * bi[0];
+                        for (int c = 0; c < 3; ++c) G[3 * a + c] += bi[1 + a] * bi[1 + c];
+                    }
+                }
+                double x[3];
+                if (solve3(G, q, x) < 0) { bad = 2; break; }
+                gam[f] = yy - (q[0] * x[0] + q[1] * x[1] + q[2] * x[2]);
+            }
+            PyMem_Free(Wk);
+            if (bad == 1)
+                PyErr_SetString(PyExc_ValueError, "gate: camera-state slot outside the covariance");
+            else if (bad == 2)
+                PyErr_SetString(PyExc_ArithmeticError, "gate: innovation covariance not positive definite");
+            else if (!PyErr_Occurred()) {
+                ret = Py_None;
+                Py_INCREF(ret);
+            }
+        }
+    }
+    PyBuffer_Release(&bHx); PyBuffer_Release(&bHf); PyBuffer_Release(&br); PyBuffer_Release(&bP); PyBuffer_Release(&bs); PyBuffer_Release(&bg);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"gate", py_gate, METH_VARARGS, "Chi-square gate statistic of F features from H_x, H_f, r and the covariance."},
     {"null_project", py_null_project, METH_VARARGS, "Projection of H_x and r onto the left null space of H_f."},
     {"jacobians", py_jacobians, METH_VARARGS, "Stereo measurement Jacobians of F features x m camera states."},
     {"propagate", py_propagate, METH_VARARGS, "IMU batch propagation (msckf.py:251-388 of the reference)."},

@@ -238,6 +238,7 @@ class MSCKF:
         `blas_threads`: process-wide BLAS thread limit set once here (None = leave alone).  The filter's matrices are at
         most 1500 x 141; a threaded OpenBLAS is 2x SLOWER on them than one thread."""
         self.use_c = bool(use_c) and _C is not None
+        self._gamma = None                  # gate statistics of the last _jacobians call (C path)
         if blas_threads is not None:
             try:
                 from threadpoolctl import threadpool_limits
@@ -677,9 +678,15 @@ class MSCKF:
             Hx, Hf, r = self._jacobian_blocks(R0, cams.p[slots], cams.R_null[slots], cams.p_null[slots], p_w, Z)
         # left null space of H_f: the last 4m - 3 columns of its complete QR
         if self.use_c:
+            # gate statistic straight from H_x, H_f, r (one 4m x 4m Cholesky per feature, see _msckfhost.gate), then the
+            # projection for the stacked Jacobian
+            self._gamma = np.empty(F)
+            _C.gate(Hx, Hf, r, self.state_cov, np.ascontiguousarray(slots, dtype=np.int64), float(self.config.observation_noise),
+                    self._gamma)
             H, rp = np.empty((F, 4 * m - 3, 6 * m)), np.empty((F, 4 * m - 3))
             _C.null_project(Hx, Hf, r, H, rp)
             return H, rp, slots
+        self._gamma = None
         Q, _ = np.linalg.qr(Hf, mode='complete')
         At = Q[:, :, 3:].transpose(0, 2, 1)                                         # (F, 4m - 3, 4m)
         H = np.einsum('fakr,fkrc->fakc', At.reshape(F, 4 * m - 3, m, 4), Hx).reshape(F, 4 * m - 3, 6 * m)
@@ -712,7 +719,10 @@ class MSCKF:
         rows_all = np.zeros(len(feats), dtype=np.int64)
         for m, idx in groups.items():
             H, r, slots = self._jacobians([feats[i] for i in idx], [cam_ids[i] for i in idx])
-            ok = self._gates(H, r, slots, m + dof_offset)
+            if self._gamma is not None:                                 # msckf.py:605-612, statistic computed in C
+                ok = self._gamma < self.chi_squared_test_table[m + dof_offset]
+            else:
+                ok = self._gates(H, r, slots, m + dof_offset)
             idx = np.asarray(idx)
             ok_all[idx] = ok
             rows_all[idx] = H.shape[1]
