@@ -1,15 +1,20 @@
 /*
- * _msckfhost -- the two scalar inner loops of the host MSCKF (uav-airvision_b200/msckf.py) in C:
+ * _msckfhost -- the scalar inner loops of the host MSCKF (uav-airvision_b200/msckf.py) in C:
  *
- *   propagate(...)    IMU batch between two images: per sample the closed-form transition matrix, RK4 state
- *                     prediction, observability-constrained blocks and the 21x21 covariance update
- *                     (reference behaviour: src/msckf.py:251-388); returns the accumulated transition matrix
- *   triangulate(...)  Levenberg-Marquardt on inverse depth over all stereo observations of a feature
- *                     (reference behaviour: src/feature/feature_position_initializer.py:31-70,
- *                     feature_observation.py:4-39)
+ *   propagate(...)          IMU batch between two images: per sample the closed-form transition matrix, RK4 state
+ *                           prediction, observability-constrained blocks and the 21x21 covariance update
+ *                           (reference behaviour: src/msckf.py:251-388); returns the accumulated transition matrix
+ *   triangulate(...) / triangulate_world(...)
+ *                           Levenberg-Marquardt on inverse depth over all stereo observations of a feature
+ *                           (src/feature/feature_position_initializer.py:6-76, feature_observation.py:4-39)
+ *   jacobians(...)          per-observation measurement Jacobian blocks with the observability constraint
+ *                           (src/msckf.py:443-502)
+ *   gate(...)               chi-square gate statistic of every feature of a group (src/msckf.py:605-612)
+ *   null_project(...)       projection onto the left null space of the feature Jacobian (src/msckf.py:504-540)
  *
- * Both are a few dozen 3x3 / 21x21 operations per call: numpy spends ~0.35 ms per IMU sample and ~0.5 ms per
- * feature on call overhead, this spends microseconds.  msckf.py keeps the numpy statement of both (tests compare).
+ * All are small fixed-size loops per sample / observation / feature: numpy spends its time on call overhead there
+ * (~0.35 ms per IMU sample, ~0.5 ms per triangulated feature), this spends microseconds.  msckf.py keeps the numpy
+ * statement of each (tests/test_msckf_host.py compares the two).
  * Plain C, no BLAS; every argument is a C-contiguous float64 buffer.
  */
 #define PY_SSIZE_T_CLEAN
