@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import os
 from collections import namedtuple
+from itertools import chain
 
 import numpy as np
 
@@ -664,8 +665,10 @@ class MSCKF:
         Returns H (F, 4m - 3, 6m), r (F, 4m - 3), slots (F, m): column block k of H[f] belongs to window slot slots[f, k]."""
         cams = self.cams
         F, m = len(feats), len(cam_ids[0])
-        slots = np.array([[cams.index[c] for c in ids] for ids in cam_ids])         # (F, m)
-        Z = np.array([[f.observations[c] for c in ids] for f, ids in zip(feats, cam_ids)])    # (F, m, 4)
+        index = cams.index
+        slots = np.fromiter((index[c] for ids in cam_ids for c in ids), dtype=np.int64, count=F * m).reshape(F, m)
+        Z = np.fromiter(chain.from_iterable(f.observations[c] for f, ids in zip(feats, cam_ids) for c in ids),
+                        dtype=np.float64, count=F * m * 4).reshape(F, m, 4)
         p_w = np.array([f.position for f in feats])                                 # (F, 3)
         R01, t01, g = self.R_cam0_cam1, self.t_cam0_cam1, self.gravity
         R0 = cams.R[slots]                                                          # (F, m, 3, 3) world -> cam0
