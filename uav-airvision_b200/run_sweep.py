@@ -21,7 +21,6 @@ import os
 import sys
 import time
 
-import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 if HERE not in sys.path:
