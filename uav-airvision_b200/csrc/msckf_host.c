@@ -779,7 +779,66 @@ static PyObject* py_gate(PyObject* self, PyObject* args) {
     return ret;
 }
 
+/* ---- correction of every camera state of the window (msckf.py:583-591 of the reference) -----------------------------
+ * update_cams(q (cap,4), p (cap,3), R (cap,3,3), p_null (cap,3), dc (n,6)): for the first n states
+ *   q <- small_angle_quaternion(dc[:3]) * q  (utils.py:78-97, 61-76), R <- to_rotation(q), p <- p + dc[3:], and
+ *   p_null <- p (position_null is an alias of position in the reference from the augmentation on). */
+static PyObject* py_update_cams(PyObject* self, PyObject* args) {
+    PyObject *oq, *op, *oR, *opn, *od;
+    if (!PyArg_ParseTuple(args, "OOOOO", &oq, &op, &oR, &opn, &od)) return NULL;
+    Py_buffer bq, bp, bR, bn, bd;
+    if (get_buf(oq, &bq, 1, 1, "q") < 0) return NULL;
+    if (get_buf(op, &bp, 1, 1, "p") < 0) { PyBuffer_Release(&bq); return NULL; }
+    if (get_buf(oR, &bR, 1, 1, "R") < 0) { PyBuffer_Release(&bq); PyBuffer_Release(&bp); return NULL; }
+    if (get_buf(opn, &bn, 1, 1, "p_null") < 0) { PyBuffer_Release(&bq); PyBuffer_Release(&bp); PyBuffer_Release(&bR); return NULL; }
+    if (get_buf(od, &bd, 1, 0, "dc") < 0) {
+        PyBuffer_Release(&bq); PyBuffer_Release(&bp); PyBuffer_Release(&bR); PyBuffer_Release(&bn);
+        return NULL;
+    }
+    PyObject* ret = NULL;
+    const Py_ssize_t n = bd.len / 48, cap = bq.len / 32;
+    if (bd.len != n * 48 || n > cap || bp.len != cap * 24 || bR.len != cap * 72 || bn.len != cap * 24) {
+        PyErr_SetString(PyExc_ValueError, "update_cams: inconsistent array sizes");
+    } else {
+        double *qa = bq.buf, *pa = bp.buf, *Ra = bR.buf, *pna = bn.buf;
+        const double* dca = bd.buf;
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            const double* dc = dca + 6 * i;
+            double* q = qa + 4 * i;
+            const double h[3] = {dc[0] / 2.0, dc[1] / 2.0, dc[2] / 2.0};
+            const double n2 = (h[0] * h[0] + h[1] * h[1]) + h[2] * h[2];
+            double dq[4] = {h[0], h[1], h[2], 1.0};
+            if (n2 <= 1.0) {
+                dq[3] = sqrt(1.0 - n2);
+            } else {
+                const double s = sqrt(1.0 + n2);
+                for (int k = 0; k < 4; ++k) dq[k] /= s;
+            }
+            double nd = sqrt(((dq[0] * dq[0] + dq[1] * dq[1]) + dq[2] * dq[2]) + dq[3] * dq[3]);
+            for (int k = 0; k < 4; ++k) dq[k] /= nd;
+            const double nq = sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+            const double q2[4] = {q[0] / nq, q[1] / nq, q[2] / nq, q[3] / nq};
+            const double x = dq[0], y = dq[1], z = dq[2], w = dq[3];
+            double qn[4] = {((w * q2[0] + z * q2[1]) - y * q2[2]) + x * q2[3], ((-z * q2[0] + w * q2[1]) + x * q2[2]) + y * q2[3],
+                            ((y * q2[0] - x * q2[1]) + w * q2[2]) + z * q2[3], ((-x * q2[0] - y * q2[1]) - z * q2[2]) + w * q2[3]};
+            const double nn = sqrt(((qn[0] * qn[0] + qn[1] * qn[1]) + qn[2] * qn[2]) + qn[3] * qn[3]);
+            for (int k = 0; k < 4; ++k) q[k] = qn[k] / nn;
+            to_rotation(q, Ra + 9 * i);
+            double* p = pa + 3 * i;
+            for (int k = 0; k < 3; ++k) {
+                p[k] += dc[3 + k];
+                pna[3 * i + k] = p[k];
+            }
+        }
+        ret = Py_None;
+        Py_INCREF(ret);
+    }
+    PyBuffer_Release(&bq); PyBuffer_Release(&bp); PyBuffer_Release(&bR); PyBuffer_Release(&bn); PyBuffer_Release(&bd);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"update_cams", py_update_cams, METH_VARARGS, "EKF correction of every camera state of the window."},
     {"gate", py_gate, METH_VARARGS, "Chi-square gate statistic of F features from H_x, H_f, r and the covariance."},
     {"null_project", py_null_project, METH_VARARGS, "Projection of H_x and r onto the left null space of H_f."},
     {"jacobians", py_jacobians, METH_VARARGS, "Stereo measurement Jacobians of F features x m camera states."},

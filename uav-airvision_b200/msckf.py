@@ -786,6 +786,11 @@ class MSCKF:
         cams = self.cams
         n = len(cams)
         dc = delta[21:].reshape(-1, 6)
+        if self.use_c:                  # the statements below, one loop in C
+            _C.update_cams(cams.q, cams.p, cams.R, cams.p_null, np.ascontiguousarray(dc))
+            Pn = P - KHP                                              # (I - K H) P
+            self.state_cov = (Pn + Pn.T) / 2.0
+            return
         # every camera state at once: q <- dq(dtheta) * q  (small_angle_quaternion + quaternion_multiplication, vectorised)
         h = dc[:, :3] / 2.0
         n2 = (h * h).sum(axis=1)
