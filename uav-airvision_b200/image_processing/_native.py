@@ -312,6 +312,21 @@ class Context:
         n = int(hdr['n_features'][0])
         return hdr[0], ids[:n], meas[:n]
 
+    def result_block(self):
+        """The result blocks of all S streams as one array: (block uint8[S, stride] -- a view of the pinned memory,
+        valid until the next frame --, ids offset, meas offset).  Stream s: header at block[s, :48] (HEADER_DTYPE), ids
+        int64[capacity] at the ids offset, meas float64[capacity, 4] at the meas offset."""
+        if getattr(self, '_block', None) is None:
+            def ptrs(s):
+                hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                self._ck(self._lib.avb_get_result(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
+                return hp.value, ip_.value, mp.value
+            h0, i0, m0 = ptrs(0)
+            stride = (ptrs(1)[0] - h0) if self.S > 1 else (m0 - h0) + self.capacity * 32
+            blk = np.ctypeslib.as_array(C.cast(C.c_void_p(h0), C.POINTER(C.c_uint8)), shape=(self.S * stride,))
+            self._block = (blk.reshape(self.S, stride), i0 - h0, m0 - h0)
+        return self._block
+
     def features(self, s=0):
         """Grid-ordered state of stream s: (cell, lifetime, cam0_xy, cam1_xy)."""
         n = int(self.result(s)[0]['n_features'])

@@ -159,20 +159,30 @@ class MultiStreamFrontEnd:
         self._in_flight = msgs
 
     def end_step_from_store(self):
-        """Waits for the step begun last and returns its results (see step_from_store)."""
+        """Waits for the step begun last and returns its results (see step_from_store).  The S result blocks leave the
+        pinned memory in ONE copy (the next step may be launched right after this returns); the per-stream arrays are
+        views into that copy."""
         msgs, self._in_flight = self._in_flight, None
         self.ctx.sync()
+        blk, ids_off, meas_off = self.ctx.result_block()
+        cap = self.ctx.capacity
+        blk = blk.copy()
+        hdr = blk[:, :_native.HEADER_DTYPE.itemsize].view(_native.HEADER_DTYPE)[:, 0]
+        ids = blk[:, ids_off:ids_off + 8 * cap].view(np.int64)
+        meas = blk[:, meas_off:meas_off + 32 * cap].view(np.float64).reshape(self.S, cap, 4)
+        n_all = hdr['n_features']
+        next_id, before = hdr['next_feature_id'].tolist(), hdr['before_tracking'].tolist()
+        counts = (hdr['after_tracking'].tolist(), hdr['after_matching'].tolist(), hdr['after_ransac'].tolist())
         out = []
         for s, m in enumerate(msgs):
-            hdr, ids, meas = self.ctx.result(s)
-            self.next_feature_id[s] = int(hdr['next_feature_id'])
+            self.next_feature_id[s] = next_id[s]
             if not self.first_frame:
                 nf = self.num_features[s]
-                nf['before_tracking'] = int(hdr['before_tracking'])
-                if nf['before_tracking']:
-                    nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = \
-                        int(hdr['after_tracking']), int(hdr['after_matching']), int(hdr['after_ransac'])
-            out.append((m.timestamp, ids.copy(), meas.copy()))
+                nf['before_tracking'] = before[s]
+                if before[s]:
+                    nf['after_tracking'], nf['after_matching'], nf['after_ransac'] = counts[0][s], counts[1][s], counts[2][s]
+            n = int(n_all[s])
+            out.append((m.timestamp, ids[s, :n], meas[s, :n]))
         self.first_frame = False
         return out
 
