@@ -36,7 +36,7 @@ def main(argv=None):
     ap.add_argument('--offsets', nargs='+', type=float, default=[1, 5, 10, 15, 20, 30, 40], help='start offsets in seconds (run.bat:5-9)')
     ap.add_argument('--max-frames', type=int, default=None, help='decode at most this many stereo frames per sequence')
     ap.add_argument('--steps', type=int, default=None, help='frames per run (default: to the end of the shortest run)')
-    ap.add_argument('--workers', type=int, default=0, help='estimator processes (0 = allowed host cores - 1)')
+    ap.add_argument('--workers', type=int, default=0, help='estimator processes (0 = allowed host cores)')
     ap.add_argument('--out', default='results', help='output directory (txts/ and metrics_summary.csv below it)')
     ap.add_argument('--device', type=int, default=None, help='CUDA device (default: LOCAL_RANK, else 0)')
     a = ap.parse_args(argv)
@@ -62,7 +62,7 @@ def main(argv=None):
         seqs.append(CachedSequence(ds, device=device, max_frames=a.max_frames, name=name))
         names.append(name)
     decode_s = time.perf_counter() - t0
-    workers = a.workers if a.workers > 0 else max(1, len(os.sched_getaffinity(0)) - 1)
+    workers = a.workers if a.workers > 0 else max(1, len(os.sched_getaffinity(0)))
     res = run_sweep(cfg, seqs, a.offsets, device=device, n_steps=a.steps, estimator_workers=workers)
     txts = os.path.join(a.out, 'txts')
     os.makedirs(txts, exist_ok=True)
