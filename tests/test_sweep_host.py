@@ -69,3 +69,11 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
     assert traj[2].shape[1] == 8 and len(traj[2]) >= len(want) - 2
     with pytest.raises(ValueError):
         EstimatorPool.push_step(pool, [frames[0]])
+
+
+def test_estimator_pool_reports_a_worker_that_cannot_start():
+    """A configuration the filter cannot be built from: the pool raises instead of hanging on the ready handshake."""
+    from estimator_pool import EstimatorPool
+    from frontend_config import FrontEndConfig
+    with pytest.raises(RuntimeError, match='failed to start'):
+        EstimatorPool(FrontEndConfig(), 2, 1)                 # no filter fields (with_filter_fields not applied)

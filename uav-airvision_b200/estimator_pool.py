@@ -142,12 +142,18 @@ class EstimatorPool:
             self.workers.append(dict(streams=streams, shm=shm, ring=ring, filled=filled, free=free, conn=parent, proc=p,
                                      slot=0))
         for w in self.workers:          # interpreter start + imports + filter construction: ~1 s, all workers in parallel
-            if not w['conn'].poll(120) or w['conn'].recv() != 'ready':
+            try:
+                ok = w['conn'].poll(120) and w['conn'].recv() == 'ready'
+            except (EOFError, OSError):
+                ok = False
+            if not ok:
                 self.close()
-                raise RuntimeError('estimator worker failed to start')
+                raise RuntimeError('estimator worker failed to start (see its traceback above)')
 
     def _post(self, w, kind, fill):
-        w['free'].acquire()
+        while not w['free'].acquire(timeout=5.0):                   # ring full: wait, but not for a dead worker
+            if not w['proc'].is_alive():
+                raise RuntimeError('estimator worker died (see its traceback above)')
         slot = w['slot']
         if fill is not None:
             fill(w['ring'], slot)
@@ -190,7 +196,10 @@ class EstimatorPool:
         self._stopped = True
         traj, busy, frames = {}, [], 0
         for w in self.workers:
-            r = w['conn'].recv()
+            try:
+                r = w['conn'].recv()
+            except (EOFError, OSError):
+                raise RuntimeError('estimator worker died before delivering its trajectories') from None
             traj.update(r['traj'])
             busy.append(r['busy_s'])
             frames += r['frames']
