@@ -204,3 +204,34 @@ def test_equidistant_model_matches_cv2_fisheye(dtype):
     assert np.abs(ref - got).max() <= tol
     with pytest.raises(cv2.error):                            # the reference's call shape (camera_model.py:70)
         cv2.fisheye.distortPoints(und, Km, De)
+
+
+def test_integer_stages_against_cv2_on_random_shapes():
+    """Property check over random sizes and contents (incl. odd sizes, constant and saturated images): pyrDown, Scharr
+    and FAST (keypoints in scan order with responses, with and without a mask) equal cv2's, bit for bit."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    det = cv2.FastFeatureDetector_create(15)
+
+    @settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(8, 70), st.integers(8, 90), st.integers(0, 2 ** 31 - 1), st.sampled_from(['noise', 'smooth', 'flat', 'sat']))
+    def check(h, w, seed, kind):
+        g = np.random.default_rng(seed)
+        if kind == 'noise':
+            img = g.integers(0, 256, (h, w)).astype(np.uint8)
+        elif kind == 'smooth':
+            img = cv2.GaussianBlur(g.integers(0, 256, (h, w)).astype(np.uint8), (0, 0), 1.5)
+        elif kind == 'flat':
+            img = np.full((h, w), int(g.integers(0, 256)), np.uint8)
+        else:
+            img = (g.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+        assert np.array_equal(cs.pyr_down(img), cv2.pyrDown(img))
+        dx, dy = cs.scharr(img)
+        assert np.array_equal(dx, cv2.Scharr(img, cv2.CV_16S, 1, 0)) and np.array_equal(dy, cv2.Scharr(img, cv2.CV_16S, 0, 1))
+        mask = (g.integers(0, 4, (h, w)) > 0).astype(np.uint8)
+        for m in (None, mask):
+            kps = det.detect(img, mask=m) if m is not None else det.detect(img)
+            xs, ys, rs = cs.fast_detect(img, 15, m)
+            assert [(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kps] == list(zip(xs.tolist(), ys.tolist(), rs.tolist()))
+
+    check()
