@@ -93,6 +93,30 @@ def test_c_inner_loops_equal_their_numpy_statement(golden_dir):
     assert np.abs(a[:, 2:12] - b[:, 2:12]).max() < 1e-9
 
 
+def test_array_entry_point_equals_the_message_entry_point(golden_dir):
+    """feature_callback_arrays(ts, ids, meas) (what a sweep's estimator processes call) is feature_callback(feature_msg)
+    without the per-feature objects: identical states on every frame."""
+    from msckf import MSCKF
+    z = np.load(os.path.join(golden_dir, 'ate_gpu_features.npz'))
+    imu = np.load(os.path.join(golden_dir, 'ref_msckf_traj.npz'))['imu']
+    a, b = MSCKF(_msckf_config(), outfile=False), MSCKF(_msckf_config(), outfile=False)
+    j = 0
+    for k in range(70):
+        ts = float(z[f'f{k}_ts'][0])
+        while j < len(imu) and imu[j, 0] <= ts:
+            for est in (a, b):
+                est.imu_callback(imu_msg(imu[j, 0], imu[j, 1:4].copy(), imu[j, 4:7].copy()))
+            j += 1
+        ids, meas = z[f'f{k}_ids'], z[f'f{k}_meas']
+        ra = a.feature_callback(feature_msg(ts, [Meas(int(i), *row) for i, row in zip(ids, meas.tolist())]))
+        rb = b.feature_callback_arrays(ts, ids, meas)
+        assert (ra is None) == (rb is None)
+        if ra is not None:
+            assert np.array_equal(ra.pose.t, rb.pose.t) and np.array_equal(a.imu_state.orientation, b.imu_state.orientation)
+            assert np.array_equal(a.state_cov, b.state_cov) and list(a.map_server) == list(b.map_server)
+    assert len(a.cams) == len(b.cams) > 10
+
+
 def test_returns_none_until_gravity_is_initialised_and_reset(golden_dir):
     from msckf import MSCKF
     est = MSCKF(_msckf_config(), outfile=False)

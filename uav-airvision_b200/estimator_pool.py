@@ -40,11 +40,13 @@ def feed(est, imu_rows, ts, ids, meas):
     """One frame into an estimator: IMU rows (t, gyro xyz, acc xyz) in order, then the feature message."""
     for row in imu_rows:
         est.imu_callback(imu_msg(float(row[0]), row[1:4].copy(), row[4:7].copy()))
+    if hasattr(est, 'feature_callback_arrays'):            # msckf.MSCKF of this package: the arrays as they are
+        return est.feature_callback_arrays(float(ts), ids, meas)
     if _host is not None and ids.flags.c_contiguous and meas.flags.c_contiguous and ids.dtype == np.int64 and meas.dtype == np.float64:
         feats = _host.features_from_arrays(ids, meas, _FM)
     else:
         feats = [Meas(int(i), *r) for i, r in zip(ids.tolist(), meas.tolist())]
-    return est.feature_callback(feature_msg(float(ts), feats))
+    return est.feature_callback(feature_msg(float(ts), feats))    # any estimator with the reference's interface
 
 
 def state_row(est):

@@ -299,16 +299,26 @@ class MSCKF:
         """msckf.py:177-228."""
         if not self.is_gravity_set:
             return None
+        return self._feature_step(feature_msg.timestamp, lambda: self.add_feature_observations(feature_msg))
+
+    def feature_callback_arrays(self, timestamp, ids, meas):
+        """feature_callback for a frame that arrives as arrays (ids int64[n], meas float64[n, 4] = u0 v0 u1 v1), the form
+        a sweep's estimator processes receive it in: the same step without building and re-reading 300 objects."""
+        if not self.is_gravity_set:
+            return None
+        return self._feature_step(float(timestamp), lambda: self._add_observation_rows(ids.tolist(), meas.tolist()))
+
+    def _feature_step(self, timestamp, add_observations):
         if self.is_first_img:
             self.is_first_img = False
-            self.imu_state.timestamp = feature_msg.timestamp
-        self.batch_imu_processing(feature_msg.timestamp)
-        self.state_augmentation(feature_msg.timestamp)
-        self.add_feature_observations(feature_msg)
+            self.imu_state.timestamp = timestamp
+        self.batch_imu_processing(timestamp)
+        self.state_augmentation(timestamp)
+        add_observations()
         self.remove_lost_features()
         self.prune_cam_state_buffer()
         try:
-            return self.publish(feature_msg.timestamp)
+            return self.publish(timestamp)
         finally:
             self.online_reset()
 
@@ -498,6 +508,21 @@ class MSCKF:
             else:
                 tracked += 1
             feat.observations[state_id] = (float(f.u0), float(f.v0), float(f.u1), float(f.v1))
+        self.tracking_rate = tracked / (before + 1e-5)
+
+    def _add_observation_rows(self, ids, rows):
+        """add_feature_observations from plain lists: ids[i] observed at rows[i] = [u0, v0, u1, v1]."""
+        state_id = self.imu_state.id
+        ms = self.map_server
+        before = len(ms)
+        tracked = 0
+        for fid, row in zip(ids, rows):
+            feat = ms.get(fid)
+            if feat is None:
+                feat = ms[fid] = Feature(fid)
+            else:
+                tracked += 1
+            feat.observations[state_id] = tuple(row)
         self.tracking_rate = tracked / (before + 1e-5)
 
     # -- triangulation (feature/*.py) -----------------------------------------------------------------------------------
