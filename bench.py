@@ -565,7 +565,7 @@ def main():
                 return self.st.imu()
         cached = CachedSequence(_Seq(frames, stream), device=local, name='bench sequence')
         # every frame the offsets leave available (at most 200 steps): a window of a few milliseconds is all noise
-        sw = run_sweep(cfg, [cached], [max(0.0, (2 * s_ - 0.5) / stream.rate) for s_ in range(S)], device=local,
+        sw = run_sweep(cfg, [cached], [(2 * s_ + 0.5) / stream.rate for s_ in range(S)], device=local,
                        n_steps=min(200, len(frames) - 2 * (S - 1)), warmup_steps=WM + 1)
         barrier()
         sw_wall = max_over_ranks(sw['wall_s'])

@@ -155,7 +155,9 @@ const uint8_t* avb_store_image(const avb_store* store, int k, int cam);
 int  avb_process_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, const double* R_p_c0,
                               const double* R_p_c1);
 /* Enqueue-only variant (avb_sync waits): the caller prepares the next step (IMU windows of every stream) while
- * this one runs.  One frame in flight per context: call avb_sync before the next enqueue or any result read. */
+ * this one runs.  One frame in flight per context: call avb_sync before any result read.  A second enqueue without
+ * avb_sync is safe but not useful: it waits until the previous frame's rotation section has left the (single) pinned
+ * staging area, and the result block holds the latest frame only. */
 int  avb_enqueue_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, const double* R_p_c0,
                               const double* R_p_c1);
 

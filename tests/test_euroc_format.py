@@ -78,8 +78,11 @@ def test_write_then_read_round_trip_and_offset(tmp_path):
     imu = list(ds.imu)
     assert len(imu) == len(imu_ref)
     assert all(np.array_equal(a.angular_velocity, b.angular_velocity) for a, b in zip(imu, imu_ref))
-    # start time = max(first imu, first image) + offset; everything before it is skipped (dataset.py:206-214)
-    assert ds.starttime == pytest.approx(max(next(iter(st.imu())).timestamp, frames[0].timestamp), abs=1e-6)
+    # start time = first IMU stamp + offset, also when the cameras start later (here 50 ms): the reference's
+    # Stereo.start_time() returns cam0.starttime = -inf at that point (dataset.py:184-185, 203); everything before the
+    # start time is skipped (dataset.py:206-214)
+    assert frames[0].timestamp > next(iter(st.imu())).timestamp + 0.04
+    assert ds.starttime == pytest.approx(next(iter(st.imu())).timestamp, abs=1e-6)
     ds.set_starttime(0.22)                                   # between two frames: no float-boundary ambiguity
     assert len(list(ds.stereo)) == sum(1 for f in frames if f.timestamp >= ds.starttime + 0.22)
     kinds = [k for k, _ in ds.events()]
@@ -123,6 +126,16 @@ def test_reader_matches_the_reference_reader(tmp_path):
         ia, ib = list(a.imu), list(b.imu)
         assert len(ia) == len(ib) and all(p.timestamp == q.timestamp and np.array_equal(p.linear_acceleration, q.linear_acceleration)
                                           for p, q in zip(ia, ib))
+    # cameras that start 50 ms after the IMU (MH_01: ~5 ms): both readers count offsets from the first IMU stamp
+    st2 = SlidingTextureStream(width=96, height=80, n_frames=8, seed=3, gyro=(0.01, 0.0, 0.02))
+    write_euroc(str(tmp_path / 'late'), st2)
+    c, d = EuRoCDataset(str(tmp_path / 'late')), ref.EuRoCDataset(str(tmp_path / 'late'))
+    assert c.starttime == d.starttime < c.cam0.timestamps[0] - 0.04
+    for off in (0, 0.03, 0.07, 0.16):
+        c.set_starttime(off)
+        d.set_starttime(off)
+        assert [m.timestamp for m in c.stereo] == [m.timestamp for m in d.stereo]
+        assert [m.timestamp for m in c.imu] == [m.timestamp for m in d.imu]
     # the reference's GroundTruthReader cannot iterate (its namedtuple lacks the timestamp field it passes,
     # dataset.py:16,35); ours carries the timestamp, so check it against what was written
     a.set_starttime(0)

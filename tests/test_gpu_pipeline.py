@@ -353,7 +353,8 @@ def test_sweep_from_hbm_store_equals_single_pipelines():
     cfg = with_filter_fields(FrontEndConfig(grid_row=5, grid_col=6))
     kws = [dict(n_frames=12, seed=60 + q, sigma=2.0 + 0.5 * q, drift=(1.3, -0.4 - 0.3 * q), gyro=(0.02, -0.01 * q, 0.03),
                 noise=0.5) for q in range(2)]
-    offsets = (0.0, 0.07, 0.21)                                    # frame period 0.05 s: runs start at frames 0, 2, 5
+    offsets = (0.0, 0.12, 0.27)                                    # counted from the first IMU stamp (50 ms before frame 0,
+                                                                   # dataset.py:203); frame period 0.05 s: runs start at frames 0, 2, 5
     seqs = [CachedSequence(SlidingTextureStream(**kw)) for kw in kws]
     assert seqs[0].store.nbytes >= 12 * 2 * 752 * 480
     steps = 6
@@ -366,7 +367,7 @@ def test_sweep_from_hbm_store_equals_single_pipelines():
         for off in offsets:
             st = SlidingTextureStream(**kw)
             frames = list(st.frames())
-            start = max(frames[0].timestamp, next(iter(st.imu())).timestamp) + off
+            start = next(iter(st.imu())).timestamp + off
             ip = ImageProcessor(cfg)
             out = []
             for kind, m in st.events():

@@ -143,3 +143,38 @@ def test_output_file_format(tmp_path, golden_dir):
     est.feature_callback(feature_msg(1.0, []))
     cols = out.read_text().strip().split()
     assert len(cols) == 8 and abs(float(cols[0]) - 1.0) < 1e-9
+
+
+def test_gate_with_an_indefinite_covariance_follows_the_reference_lu_path(golden_dir):
+    """The reference's gating_test (msckf.py:605-612) solves S gamma-wise with an LU and only raises when S is exactly
+    singular; its (I - KH) P update does not keep P positive definite on a diverging run.  The C gate (Cholesky) must
+    not raise then: it marks the feature and the numpy LU statement supplies the statistic."""
+    import _msckfhost as C
+    g = np.random.default_rng(4)
+    F, m, n = 5, 3, 21 + 6 * 4
+    Hx, Hf, r = g.normal(size=(F, m, 4, 6)), g.normal(size=(F, 4 * m, 3)), g.normal(size=(F, 4 * m))
+    slots = np.tile(np.array([0, 2, 3], np.int64), (F, 1))
+    A = g.normal(size=(n, n))
+    P_pd = A @ A.T + np.eye(n)
+    P_bad = P_pd - 40.0 * np.eye(n)                                         # symmetric, indefinite
+    gam = np.empty(F)
+    C.gate(Hx, Hf, r, P_pd, slots, 0.035 ** 2, gam)
+    assert np.isfinite(gam).all()
+    C.gate(Hx, Hf, r, P_bad, slots, 0.035 ** 2, gam)                        # used to raise ArithmeticError
+    assert np.isnan(gam).all()
+    # through the filter: a covariance made indefinite mid-run; the frame is processed, decisions come from the LU path
+    from msckf import MSCKF
+    est_c, est_np = _replay(golden_dir, 45)[4], _replay(golden_dir, 45, use_c=False)[4]
+    z = np.load(os.path.join(golden_dir, 'ate_gpu_features.npz'))
+    imu = np.load(os.path.join(golden_dir, 'ref_msckf_traj.npz'))['imu']
+    ts = float(z['f45_ts'][0])
+    feats = [Meas(int(i), *row) for i, row in zip(z['f45_ids'], z['f45_meas'].tolist())]
+    out = []
+    for est in (est_c, est_np):
+        est.state_cov[21:, 21:] -= 1e-3 * np.eye(len(est.state_cov) - 21)  # camera blocks: indefinite
+        for row in imu[(imu[:, 0] > float(z['f44_ts'][0])) & (imu[:, 0] <= ts)]:
+            est.imu_callback(imu_msg(row[0], row[1:4].copy(), row[4:7].copy()))
+        res = est.feature_callback(feature_msg(ts, feats))
+        assert res is not None
+        out.append((res.pose.t.copy(), len(est.map_server), len(est.cams)))
+    assert out[0][1:] == out[1][1:] and np.abs(out[0][0] - out[1][0]).max() < 1e-6

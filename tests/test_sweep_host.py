@@ -9,7 +9,7 @@ from synth_euroc import SlidingTextureStream
 
 
 def test_offset_start_equals_the_dataset_reader(tmp_path):
-    """`--offset s` drops everything older than max(first IMU, first image) + s (dataset.py:206-214): the cached
+    """`--offset s` drops everything older than first IMU stamp + s (dataset.py:203, 206-214): the cached
     sequence's start indices select exactly the messages the reader yields."""
     from euroc import EuRoCDataset, write_euroc
     from sweep import offset_start
@@ -65,7 +65,9 @@ def test_estimator_pool_equals_in_process_filter(golden_dir):
     finally:
         pool.close()
     assert stats['frames'] == 3 * len(frames) and len(stats['worker_busy_s']) == 2
-    assert np.array_equal(traj[0], want) and np.array_equal(traj[1], want)
+    # the workers cap BLAS at one thread, this process does not: same arithmetic up to the summation order inside BLAS
+    assert traj[0].shape == want.shape and np.array_equal(traj[0], traj[1])
+    assert np.abs(traj[0] - want).max() < 1e-9 and not stats['errors']
     assert traj[2].shape[1] == 8 and len(traj[2]) >= len(want) - 2
     with pytest.raises(ValueError):
         EstimatorPool.push_step(pool, [frames[0]])

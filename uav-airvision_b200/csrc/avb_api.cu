@@ -100,6 +100,7 @@ struct avb_ctx {
     int parity = 1;                 // parity of the current frame; the first frame lands in parity 0
     bool first_frame = true;
     bool have_frame = false;
+    bool rot_copy_pending = false;  // an enqueued (not waited-for) gather frame's rotation copy may not have run yet
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // steady-state frame, per parity, host-input variant
     cudaGraphExec_t graph_dev[2] = {nullptr, nullptr}; // same, device-input variant (no H2D of images)
     std::vector<void*> allocs;
@@ -720,12 +721,21 @@ static int gather_frame(avb_ctx* c, const uint8_t* const* d_images, const double
         if (!d_images[i] || (reinterpret_cast<uintptr_t>(d_images[i]) & 15))
             return fail(c, AVB_E_INVALID, "image %d (stream %d cam %d): null or not 16-byte aligned", i, i / 2, i & 1);
     const int p = c->parity ^ 1;
+    // One frame may be in flight while the next is enqueued (avb_enqueue_frame_gather).  The rotation section travels
+    // from ONE pinned staging area: before it is rewritten, the copy that carried the previous frame's rotations must
+    // have executed (it waits for the frame before that, so this blocks only a caller that runs more than one frame
+    // ahead -- and then it is what keeps frame k from reading the rotations of frame k+1).
+    if (c->rot_copy_pending) {
+        CK(cudaEventSynchronize(c->ev_join));
+        c->rot_copy_pending = false;
+    }
     CK(cudaEventRecord(c->ev_t0, c->st));
     avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     const size_t ro = in_images_bytes(g);
     CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));
     CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
     CK(cudaEventRecord(c->ev_join, c->st_side));
+    c->rot_copy_pending = !wait;
     CK(launch_gather_frames(g, c->d.in[p], d_images, c->st));
     CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
     return run_frame(c, 2, wait);
@@ -744,6 +754,7 @@ extern "C" int avb_enqueue_frame_gather(avb_ctx* c, const uint8_t* const* d_imag
 extern "C" int avb_sync(avb_ctx* c) {
     if (!c) return AVB_E_INVALID;
     CK(cudaStreamSynchronize(c->st));
+    c->rot_copy_pending = false;
     return AVB_OK;
 }
 

@@ -729,9 +729,10 @@ static PyObject* py_gate(PyObject* self, PyObject* args) {
                     }
                 for (Py_ssize_t i = 0; i < R; ++i) W[i * R + i] += sigma;
                 /* Cholesky W = L L^T, right-looking on the lower triangle (the updates are axpys over contiguous rows) */
-                for (Py_ssize_t j = 0; j < R && !bad; ++j) {
+                int notpd = 0;
+                for (Py_ssize_t j = 0; j < R; ++j) {
                     double d = W[j * R + j];
-                    if (!(d > 0.0)) { bad = 2; break; }
+                    if (!(d > 0.0)) { notpd = 1; break; }
                     d = sqrt(d);
                     W[j * R + j] = d;
                     const double id = 1.0 / d;
@@ -742,7 +743,10 @@ static PyObject* py_gate(PyObject* self, PyObject* args) {
                         for (Py_ssize_t k = j + 1; k <= i; ++k) wi[k] -= lij * W[k * R + j];
                     }
                 }
-                if (bad) break;
+                /* W not positive definite (the reference's (I - KH) P update does not preserve that on a diverging run): the
+                 * reference's gating_test still answers through an LU solve (msckf.py:605-612).  Mark the feature; the caller
+                 * recomputes its statistic that way. */
+                if (notpd) { gam[f] = NAN; continue; }
                 /* Y = L^-1 [r | Hf]  (forward substitution, 4 right-hand sides) */
                 for (Py_ssize_t i = 0; i < R; ++i) {
                     double v[4] = {ra[f * R + i], Hfa[(f * R + i) * 3], Hfa[(f * R + i) * 3 + 1], Hfa[(f * R + i) * 3 + 2]};
@@ -761,14 +765,12 @@ static PyObject* py_gate(PyObject* self, PyObject* args) {
                     }
                 }
                 double x[3];
-                if (solve3(G, q, x) < 0) { bad = 2; break; }
+                if (solve3(G, q, x) < 0) { gam[f] = NAN; continue; }
                 gam[f] = yy - (q[0] * x[0] + q[1] * x[1] + q[2] * x[2]);
             }
             PyMem_Free(Wk);
             if (bad == 1)
                 PyErr_SetString(PyExc_ValueError, "gate: camera-state slot outside the covariance");
-            else if (bad == 2)
-                PyErr_SetString(PyExc_ArithmeticError, "gate: innovation covariance not positive definite");
             else if (!PyErr_Occurred()) {
                 ret = Py_None;
                 Py_INCREF(ret);

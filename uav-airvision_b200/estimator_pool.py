@@ -86,8 +86,9 @@ def _worker(shm_name, depth, cap, filled, free, conn, config, streams):
     shm = shared_memory.SharedMemory(name=shm_name)
     try:
         ring = _Ring(shm.buf, depth, len(streams), cap)
-        ests = [MSCKF(config, outfile=False) for _ in streams]
+        ests = [MSCKF(config, outfile=False, blas_threads=1) for _ in streams]     # this process runs nothing but filters
         traj = [[] for _ in streams]
+        dead = {}                       # stream -> error text: a filter that raised is retired, the other runs go on
         busy, frames, slot = 0.0, 0, 0
         conn.send('ready')
         while True:
@@ -97,12 +98,18 @@ def _worker(shm_name, depth, cap, filled, free, conn, config, streams):
                 break
             t0 = time.perf_counter()
             for i, est in enumerate(ests):
-                n_imu, n_feat = (int(v) for v in ring.count[slot, i])
-                if kind == IMU_ONLY:
-                    for row in ring.imu[slot, i, :n_imu]:
-                        est.imu_callback(imu_msg(float(row[0]), row[1:4].copy(), row[4:7].copy()))
+                if streams[i] in dead:
                     continue
-                r = feed(est, ring.imu[slot, i, :n_imu], ring.ts[slot, i], ring.ids[slot, i, :n_feat], ring.meas[slot, i, :n_feat])
+                n_imu, n_feat = (int(v) for v in ring.count[slot, i])
+                try:
+                    if kind == IMU_ONLY:
+                        for row in ring.imu[slot, i, :n_imu]:
+                            est.imu_callback(imu_msg(float(row[0]), row[1:4].copy(), row[4:7].copy()))
+                        continue
+                    r = feed(est, ring.imu[slot, i, :n_imu], ring.ts[slot, i], ring.ids[slot, i, :n_feat], ring.meas[slot, i, :n_feat])
+                except Exception as e:  # e.g. a singular innovation covariance on a diverged run (msckf.py:605-612 raises too)
+                    dead[streams[i]] = f'{type(e).__name__}: {e}'
+                    continue
                 frames += 1
                 if r is not None:
                     traj[i].append(state_row(est))
@@ -110,7 +117,7 @@ def _worker(shm_name, depth, cap, filled, free, conn, config, streams):
             free.release()
             slot = (slot + 1) % depth
         conn.send({'traj': {s: np.array(v, dtype=np.float64).reshape(-1, 8) for s, v in zip(streams, traj)},
-                   'busy_s': busy, 'frames': frames})
+                   'busy_s': busy, 'frames': frames, 'errors': dead})
         conn.close()
         del ring
     finally:
@@ -196,7 +203,7 @@ class EstimatorPool:
         for w in self.workers:
             self._post(w, STOP, None)
         self._stopped = True
-        traj, busy, frames = {}, [], 0
+        traj, busy, frames, errors = {}, [], 0, {}
         for w in self.workers:
             try:
                 r = w['conn'].recv()
@@ -205,7 +212,9 @@ class EstimatorPool:
             traj.update(r['traj'])
             busy.append(r['busy_s'])
             frames += r['frames']
-        return [traj[s] for s in range(self.S)], {'worker_busy_s': busy, 'frames': frames}
+            errors.update(r.get('errors', {}))
+        # `errors`: stream -> text for filters that raised (their trajectories end where they stopped)
+        return [traj[s] for s in range(self.S)], {'worker_busy_s': busy, 'frames': frames, 'errors': errors}
 
     def _release(self):
         for w in self.workers:

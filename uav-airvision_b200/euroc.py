@@ -195,7 +195,10 @@ class EuRoCDataset:
         self.cam1 = ImageReader(*self.list_imgs(os.path.join(mav, 'cam1', 'data')))
         self.stereo = Stereo(self.cam0, self.cam1)
         self.timestamps = self.cam0.timestamps
-        self.starttime = max(self.imu.start_time(), self.stereo.cam0.start_time())
+        # The reference takes max(imu.start_time(), stereo.start_time()), and Stereo.start_time() returns
+        # cam0.starttime, which is still -inf here (dataset.py:184-185, 203): the start time IS the first IMU stamp,
+        # also when the cameras start later.  Reproduced, not repaired: every --offset run counts from there.
+        self.starttime = max(self.imu.start_time(), self.stereo.start_time())
         self.set_starttime(0)
 
     def set_starttime(self, offset):

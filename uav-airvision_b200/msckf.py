@@ -232,12 +232,13 @@ class Feature:
 
 
 class MSCKF:
-    def __init__(self, config, outfile=None, use_c=True, blas_threads=1):
+    def __init__(self, config, outfile=None, use_c=True, blas_threads=None):
         """`outfile`: None = the reference's rule (results/txts/output_<DATASET_NAME>_offset<TIME_OFFSET>.txt, one line
         appended per published state, msckf.py:10-16,152-160); a path = write there; False = do not write.
         `use_c`: run the IMU propagation and the triangulation through _msckfhost (False: the numpy statements).
-        `blas_threads`: process-wide BLAS thread limit set once here (None = leave alone).  The filter's matrices are at
-        most 1500 x 141; a threaded OpenBLAS is 2x SLOWER on them than one thread."""
+        `blas_threads`: opt-in, PROCESS-WIDE BLAS thread limit (None, the default, leaves the hosting process alone).  The
+        filter's matrices are at most 1500 x 141 and a threaded OpenBLAS is 2x SLOWER on them than one thread, so the
+        estimator worker processes (estimator_pool._worker), which run nothing else, pass 1."""
         self.use_c = bool(use_c) and _C is not None
         self._gamma = None                  # gate statistics of the last _jacobians call (C path)
         if blas_threads is not None:
@@ -713,6 +714,9 @@ class MSCKF:
                     self._gamma)
             H, rp = np.empty((F, 4 * m - 3, 6 * m)), np.empty((F, 4 * m - 3))
             _C.null_project(Hx, Hf, r, H, rp)
+            bad = np.flatnonzero(np.isnan(self._gamma))
+            if len(bad):                # innovation covariance not positive definite: the reference's LU path decides
+                self._gamma[bad] = self._gamma_lu(H[bad], rp[bad], slots[bad])
             return H, rp, slots
         self._gamma = None
         Q, _ = np.linalg.qr(Hf, mode='complete')
@@ -721,7 +725,12 @@ class MSCKF:
         return H, np.einsum('fab,fb->fa', At, r), slots
 
     def _gates(self, H, r, slots, dof):
-        """msckf.py:605-612 for a batch: H by its non-zero column blocks.  Returns the boolean decisions."""
+        """msckf.py:605-612 for a batch.  Returns the boolean decisions."""
+        return self._gamma_lu(H, r, slots) < self.chi_squared_test_table[dof]
+
+    def _gamma_lu(self, H, r, slots):
+        """The reference's gate statistic r^T (H P H^T + sigma I)^-1 r through an LU solve (msckf.py:605-612; no
+        definiteness assumed, a singular S raises as it does there), H by its non-zero column blocks."""
         if (slots == slots[0]).all():                                               # the usual case: one set of states
             c0 = ((21 + 6 * slots[0])[:, None] + np.arange(6)).reshape(-1)
             P = self.state_cov[np.ix_(c0, c0)]                                      # (6m, 6m), broadcast over the features
@@ -731,8 +740,7 @@ class MSCKF:
             P = self.state_cov[cols[:, :, None], cols[:, None, :]]                  # (F, 6m, 6m)
         S = H @ P @ H.transpose(0, 2, 1)
         S[:, np.arange(S.shape[1]), np.arange(S.shape[1])] += self.config.observation_noise
-        gamma = np.einsum('fa,fa->f', r, np.linalg.solve(S, r[:, :, None])[:, :, 0])
-        return gamma < self.chi_squared_test_table[dof]
+        return np.einsum('fa,fa->f', r, np.linalg.solve(S, r[:, :, None])[:, :, 0])
 
     def _evaluate(self, feats, cam_ids, dof_offset, max_rows=None):
         """Jacobians + gate for a list of features, grouped by their number of camera states so that every group is one

@@ -27,9 +27,10 @@ SweepRun = namedtuple('SweepRun', ['sequence', 'offset', 'first_frame', 'first_i
 
 
 def offset_start(frame_times, imu_times, offset_s):
-    """(first frame index, first IMU index) of the run `--offset offset_s`: starttime = max(first IMU, first image) +
-    offset, and every reader drops what is older than it (streaming/dataset.py:206-214, 72-75, 119-123)."""
-    start = max(imu_times[0] if len(imu_times) else -np.inf, frame_times[0]) + float(offset_s)
+    """(first frame index, first IMU index) of the run `--offset offset_s`: starttime = first IMU stamp + offset (the
+    reference's max(imu.start_time(), stereo.start_time()) sees cam0.starttime = -inf, streaming/dataset.py:184-185,
+    203), and every reader drops what is older than it (dataset.py:206-214, 72-75, 119-123)."""
+    start = (imu_times[0] if len(imu_times) else frame_times[0]) + float(offset_s)
     return (int(np.searchsorted(frame_times, start, side='left')), int(np.searchsorted(imu_times, start, side='left')))
 
 
