@@ -1,30 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- stereo frames/s and tracked features/s of the B200 image front end.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c5]
 
 A "step" is one stereo frame of one stream through the whole front end (pyramid build, temporal KLT, stereo
 KLT + filters, FAST + grid ranking, new-feature stereo match, prune, publish).  At N GPUs every rank owns one
 independent synthetic EuRoC-format stream (no collective on the data path: "scaling": "weak"); rank 0 prints ONE
 JSON line.
 
-  value     frames/s with the whole frame sequence already resident in HBM (K dependent frames enqueued on the
-            context's stream, CUDA events on that stream, max over ranks)
-  e2e       the same frames through the public API, ImageProcessor.stereo_callback(stereo_msg) with HOST numpy
-            images: host->pinned copy, H2D, the CUDA-graph frame, D2H of the result block and construction of the
-            FeatureMeasurement list are all inside the timed region
+  value     DEVICE-RESIDENT frames/s: the whole frame sequence already lies in HBM, K dependent frames are enqueued on
+            the context's stream, CUDA events on that stream, max over ranks.  No host result is awaited per frame, so
+            this is NOT the SURVEY 8(d) metric ("frames whose feature_msg is fully materialised on the host"): it
+            explains `e2e`.
+  e2e       the 8(d) metric: the same frames through the public API, ImageProcessor.stereo_callback(stereo_msg) with
+            HOST numpy images: host->pinned copy, H2D, the CUDA-graph frame, D2H of the result block and construction
+            of the FeatureMeasurement list are all inside the timed region
+  repeats   a timed region of K steps is repeated R times (R chosen so that the regions add up to >= 0.25 s) and the
+            MEDIAN region is reported; `steps` stays K
   roofline  the frame's kernel chain against the HBM copy peak of MEASURED_PEAKS.json
+  multi_stream / c4_weak   BASELINE config C4 (64 time-offset runs): 64 runs in total sharded over the GPUs (strong) and
+            64 runs per GPU (weak); the last frame of the first and last run is checked against single-stream contexts
+  c3, c5    compact legs of the other BASELINE configurations (N = 1 only)
   cpu_baseline / --impl reference
-            the reference front end's CPU path (oracle/pipeline_port.py calling cv2 exactly where the reference
-            does; the reference itself is Python and cannot travel to the GPU box) on the same frames
+            the UNMODIFIED reference front end (oracle/_ref, copied from /root/reference/src by
+            tools/make_oracle_ref.sh) on the box's host cores, same frames: one stream with cv2's default threads, one
+            stream with cv2.setNumThreads(1), and os.cpu_count() single-thread processes side by side (aggregate)
 
-Inputs are synthetic (seeded sliding-texture stereo + IMU, synth_euroc.py).  The timed sequence (W+K+1 distinct
-frames of 0.72 MB) is larger than L2 once K >= 180, and every frame is read exactly once.
+Inputs are synthetic (seeded sliding-texture stereo + IMU, synth_euroc.py): >= 200 distinct frames (> the 126 MB L2)
+rendered once; longer timed sequences walk them forth and back (continuous motion), so between two reads of a frame
+more than an L2 of other frames has passed.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -41,6 +51,9 @@ sys.dont_write_bytecode = True
 
 METRIC = 'stereo_frames_per_s'
 UNIT = 'frames/s'
+DTYPE = 'u8/int32 fixed-point + f32 (LK), f64 (undistort)'
+MIN_REGION_S = 0.25
+REF_RUNNER = os.path.join(ROOT, 'oracle', 'ref_runner.py')
 
 
 def workload(name):
@@ -55,6 +68,14 @@ def workload(name):
             'C3: 1280x1024 stereo, grid 10x10 x max 20 = 2000 features, 5-level pyramid (intrinsics scaled with ' \
             'the image), batched two-point RANSAC on (not a reference stage: the reference stubs it out; oracle/ransac.py defines it)'
     raise SystemExit(f'unknown workload {name}')
+
+
+def line_config(wname, world):
+    """`config` of the JSON line: identical for the repo arm and the reference arm (static description only; measured
+    quantities live in other keys of the line)."""
+    return {'workload': wname, 'streams_per_gpu': 1, 'streams_total': world,
+            'frames': 'synthetic sliding-texture stereo + IMU, >= 200 distinct frames (> L2) walked forth and back',
+            'timing': f'median of `repeats` regions of `steps` frames each (regions add up to >= {MIN_REGION_S} s)'}
 
 
 def stage_bytes(w, h, max_level, S):
@@ -125,9 +146,45 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def make_sequence(skw, n_frames):
-    from synth_euroc import SlidingTextureStream
-    return SlidingTextureStream(n_frames=n_frames, **skw)
+class ForthAndBack:
+    """`total` frames from `n` distinct rendered ones: 0, 1, .., n-1, n-2, .., 1, 0, 1, ..  The sliding texture then
+    moves forth and back -- continuous motion, every frame tracks from its predecessor -- while time stamps and IMU
+    samples keep increasing as in the base stream."""
+
+    def __init__(self, base, frames, total):
+        self.base, self.src, self.n = base, frames, int(total)
+        self.w, self.h, self.rate = base.w, base.h, base.rate
+        nb = len(frames)
+        period = max(2 * (nb - 1), 1)
+        m = np.arange(self.n) % period
+        self.index = np.where(m < nb, m, period - m).astype(np.int64)
+
+    def frame(self, k):
+        from synth_euroc import img_msg, stereo_msg
+        f = self.src[int(self.index[k])]
+        ts = self.base.t0 + k / self.base.rate
+        return stereo_msg(ts, f.cam0_image, f.cam1_image, img_msg(ts, f.cam0_image), img_msg(ts, f.cam1_image))
+
+    def frames(self):
+        return (self.frame(k) for k in range(self.n))
+
+    def imu(self):
+        from synth_euroc import imu_msg
+        b = self.base
+        n_imu = int(np.floor((self.n - 1) / b.rate * b.imu_rate)) + 1
+        acc = np.array([0.0, 0.0, 9.81])
+        lead = int(0.05 * b.imu_rate)
+        for j in range(-lead, n_imu + 1):
+            yield imu_msg(b.t0 + j / b.imu_rate, b.gyro.copy(), acc.copy())
+
+    def events(self):
+        imu_it = iter(self.imu())
+        pending = next(imu_it, None)
+        for f in self.frames():
+            while pending is not None and pending.timestamp <= f.timestamp:
+                yield 'imu', pending
+                pending = next(imu_it, None)
+            yield 'stereo', f
 
 
 def rotations_for(cfg, stream):
@@ -146,9 +203,37 @@ def rotations_for(cfg, stream):
     return out
 
 
-def cpu_front_end(cfg, stream, n_frames, budget_s=30.0):
-    """Reference CPU path (port, cv2 backend) on the first frames of the same stream.  Returns per-frame seconds
-    (frame 0 first), features per frame."""
+def repeats_for(K, est_ms_per_step, cap_frames=3000):
+    """Number of timed regions of K steps so that they add up to >= MIN_REGION_S (at most 50, at most cap_frames frames)."""
+    region = K * est_ms_per_step * 1e-3
+    if region >= MIN_REGION_S:
+        return 1
+    return int(max(1, min(50, math.ceil(MIN_REGION_S / region), cap_frames // max(K, 1))))
+
+
+# ---- the reference on the host cores (oracle/_ref through oracle/ref_runner.py, its own process) -----------------------
+def ref_available():
+    return os.path.isdir(os.path.join(ROOT, 'oracle', '_ref'))
+
+
+def run_ref(wl, frames, warmup, threads=0, procs=1, timeout=900):
+    """One oracle/ref_runner.py bench run -> its JSON (None when it failed)."""
+    cmd = [sys.executable, REF_RUNNER, 'bench', '--workload', wl, '--frames', str(frames), '--warmup', str(warmup),
+           '--threads', str(threads), '--procs', str(procs)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr[-1500:])
+            return None
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                                  # pragma: no cover
+        sys.stderr.write(f'reference runner failed: {e}\n')
+        return None
+
+
+def port_front_end(cfg, stream, n_frames, budget_s=30.0):
+    """The oracle port (oracle/pipeline_port.py, cv2 backend) on the first frames of the stream: kept BESIDE the
+    reference figure (its array-style bookkeeping is faster than the reference's per-keypoint Python loops)."""
     import cv2
     from oracle.pipeline_port import FrontEndPort
     fe = FrontEndPort(cfg, backend='cv2')
@@ -169,40 +254,85 @@ def cpu_front_end(cfg, stream, n_frames, budget_s=30.0):
     return times, feats, cv2.getNumThreads(), cv2.__version__
 
 
+def cpu_variants(wl, frames, warmup, cores, with_one_thread=True, with_aggregate=True):
+    """(i) one stream, cv2 default threads; (ii) one stream, one thread; (iii) `cores` single-thread processes, aggregate."""
+    out = {}
+    a = run_ref(wl, frames, warmup, threads=0)
+    if a is None:
+        return None
+    out['one_stream_default_threads'] = {'value': a['fps'], 'cv2_threads': a['cv2_threads'], 'frames_timed': a['frames_timed'],
+                                         'ms_median': a['ms_median'], 'frame0_ms': a['frame0_ms'],
+                                         'tracked_features_per_s': a['features_per_s']}
+    out['cv2'] = a['cv2']
+    if with_one_thread:
+        b = run_ref(wl, frames, warmup, threads=1)
+        if b is not None:
+            out['one_stream_one_thread'] = {'value': b['fps'], 'frames_timed': b['frames_timed'], 'ms_median': b['ms_median']}
+    if with_aggregate and cores > 1:
+        c = run_ref(wl, frames, warmup, threads=1, procs=cores)
+        if c is not None:
+            out['all_cores_one_stream_each'] = {'value': c['fps'], 'processes': c['procs'], 'frames_timed': c['frames_timed'],
+                                                'tracked_features_per_s': c['features_per_s'],
+                                                'note': f'{c["procs"]} single-thread processes side by side, each its own stream; '
+                                                        'aggregate = timed frames of all / slowest span'}
+    return out
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU front end alone, rank 0 only."""
+    """--impl reference: the UNMODIFIED reference front end (oracle/_ref) on the host cores, rank 0 only.  N = 1: one
+    stream with all the threads cv2 takes (what a user of the reference gets for this workload); N > 1: the repo arm
+    runs N streams on N GPUs, so the like-for-like figure is the whole host: os.cpu_count() single-thread processes."""
     if rank != 0:
         return
     cfg, skw, wname = workload(args.workload)
-    n = args.warmup + args.steps + 1
-    stream = make_sequence(skw, n)
-    frames = [stream.frame(k) for k in range(n)]          # pre-decoded in RAM
-    stream.frames = lambda: iter(frames)
-    times, feats, threads, cvv = cpu_front_end(cfg, stream, n, budget_s=150.0)
-    done = len(times)
-    w = min(args.warmup + 1, max(done - 1, 1))            # frame 0 + warm-up frames are not timed
-    timed = times[w:]
-    total = float(np.sum(timed))
-    k = len(timed)
-    val = k / total if total > 0 else 0.0
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': k, 'warmup': w, 'ms_per_step': 1e3 * total / max(k, 1), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (cv2)', 'data': 'synthetic',
-        'config': {'workload': wname, 'streams': 1, 'frames_timed': k,
-                   'note': 'reference front end restated in oracle/pipeline_port.py, cv2 %s called exactly where '
-                           'the reference calls it; the Python reference itself cannot travel to the GPU box' % cvv},
-        'tracked_features_per_s': float(np.sum(feats[w:]) / total) if total > 0 else 0.0,
-        'frame0_ms': 1e3 * times[0],
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': f'{k} consecutive frames of the workload stream after frame 0 + {w - 1} warm-up '
-                                   f'frames; host cores {os.cpu_count()}, cv2 threads {threads}'},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
+    W, K = args.warmup, args.steps
+    cores = os.cpu_count() or 1
+    est_fps = 60.0 if args.workload == 'c2' else 4.0
+    frames = int(min(W + 1 + K, W + 1 + max(8, est_fps * 60)))    # a leg stays within about a minute
+    line = {'impl': 'reference', 'metric': METRIC, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': K, 'warmup': W,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (cv2)',
+            'data': 'synthetic', 'config': line_config(wname, world), 'gpu_launches': 0}
+    if not ref_available():
+        # the oracle port is the stand-in (kind "port"): same cv2 calls at the same call sites
+        from synth_euroc import SlidingTextureStream
+        st = SlidingTextureStream(n_frames=frames, **skw)
+        fr = [st.frame(k) for k in range(frames)]
+        st.frames = lambda: iter(fr)
+        times, feats, threads, cvv = port_front_end(cfg, st, frames, budget_s=120.0)
+        w = min(W + 1, max(len(times) - 1, 1))
+        tot = float(np.sum(times[w:]))
+        val = (len(times) - w) / tot
+        line.update(value=val, ms_per_step=1e3 / val, frames_timed=len(times) - w,
+                    cpu_baseline={'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                  'sample': f'{len(times) - w} frames; oracle/_ref missing (tools/make_oracle_ref.sh was not run)'},
+                    e2e={'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
+        print(json.dumps(line), flush=True)
+        return
+    v = cpu_variants(args.workload, frames, W, cores)
+    if v is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/ref_runner.py failed (see stderr)'}), flush=True)
+        return
+    one = v['one_stream_default_threads']
+    agg = v.get('all_cores_one_stream_each')
+    if world > 1 and agg is not None:
+        val, used = agg['value'], agg['processes']
+        what = f'{agg["processes"]} single-thread reference processes side by side (whole host)'
+        feats = agg['tracked_features_per_s']
+    else:
+        val, used, what = one['value'], one['cv2_threads'], f'one stream, cv2 threads {one["cv2_threads"]}'
+        feats = one['tracked_features_per_s']
+    line.update(value=val, ms_per_step=1e3 / val if val > 0 else None, frames_timed=one['frames_timed'],
+                tracked_features_per_s=feats, frame0_ms=one['frame0_ms'],
+                cpu_baseline={'value': val, 'unit': UNIT, 'cores': used, 'kind': 'reference',
+                              'sample': f'{what}; {one["frames_timed"]} consecutive frames of the workload stream after frame 0 + '
+                                        f'{W} warm-up frames; unmodified reference (oracle/_ref: image_processing/pipeline.py:46-150), '
+                                        f'cv2 {v["cv2"]}, host cores {cores}',
+                              'variants': v},
+                e2e={'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
     print(json.dumps(line), flush=True)
 
 
+# ---- C5 ------------------------------------------------------------------------------------------------------------------
 def _render_sequence(job):
     """Worker of the C5 leg: one rendered EuRoC-geometry sequence (images, IMU rows, ground truth) as arrays."""
     q, n_frames = job
@@ -243,20 +373,22 @@ class _ArraySequence:
         return (gt_msg(float(t), p, None, z, z, z) for t, p in zip(self.d['gt_t'], self.d['gt_p']))
 
 
-def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_over_ranks, bound):
+def run_c5(B, n_seq, n_off, n_steps, n_workers, bound):
     """BASELINE config C5: sequences x time offsets, full front end + host MSCKF, sharded over the GPUs by sequence.
     Every rank renders its sequences (synthetic, EuRoC geometry), uploads each ONCE into an HBM frame store, and runs
-    all offset runs of its sequences in lock-step through one context; estimators run in worker processes."""
+    all offset runs of its sequences in lock-step through one context; estimators run in worker processes.  Returns the
+    JSON line (rank 0) or None."""
     import multiprocessing as mp
     from frontend_config import config_c2, with_filter_fields
     from metrics import trajectory_metrics
     from multi_stream import shard_streams
     from sweep import CachedSequence, run_sweep
+    rank, world, local, torch = B.rank, B.world, B.local, B.torch
     cfg = with_filter_fields(config_c2())
-    mine = shard_streams(args.c5_sequences, world, rank)
+    mine = shard_streams(n_seq, world, rank)
     step_frames = 2                                           # offsets 0, 0.1 s, 0.2 s, ... (20 Hz frames)
-    offsets = [o * step_frames / 20.0 for o in range(args.c5_offsets)]
-    n_frames = args.c5_steps + step_frames * (args.c5_offsets - 1) + 1
+    offsets = [o * step_frames / 20.0 for o in range(n_off)]
+    n_frames = n_steps + step_frames * (n_off - 1) + 1
     cores = sorted(os.sched_getaffinity(0))
     t0 = time.perf_counter()
     with mp.get_context('spawn').Pool(min(len(mine), max(1, len(cores)))) as pool:
@@ -267,69 +399,332 @@ def run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_o
     torch.cuda.synchronize()
     upload_s = time.perf_counter() - t0
     store_bytes = sum(q.store.nbytes for q in seqs)
-    # the ranks of a box share its cores unless each is bound to its own NUMA node
+    # the ranks of a box share its cores unless each is bound to its own slice
     share = len(cores) if bound else len(cores) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
-    # one estimator per core of the rank: the driver thread mostly waits on the GPU (16 workers on 16 cores: 10,280
-    # frames/s, 15 workers: 9,841)
-    workers = args.c5_workers if args.c5_workers > 0 else max(1, share)
+    # one estimator per core of the rank: the driver thread mostly waits on the GPU
+    workers = n_workers if n_workers > 0 else max(1, share)
     warm = 2
     sampler = ClockSampler(local) if rank == 0 else None
     # front end alone (what the GPU side of the sweep sustains from the HBM store, results as arrays on the host)
-    barrier()
-    fe_only = run_sweep(cfg, seqs, offsets, device=local, n_steps=args.c5_steps, warmup_steps=warm)
-    barrier()
+    B.barrier()
+    fe_only = run_sweep(cfg, seqs, offsets, device=local, n_steps=n_steps, warmup_steps=warm)
+    B.barrier()
     t_a = time.perf_counter()
-    full = run_sweep(cfg, seqs, offsets, device=local, n_steps=args.c5_steps, estimator_workers=workers, warmup_steps=warm)
-    barrier()
+    full = run_sweep(cfg, seqs, offsets, device=local, n_steps=n_steps, estimator_workers=workers, warmup_steps=warm)
+    B.barrier()
     t_b = time.perf_counter()
     assert np.array_equal(fe_only['features'], full['features'])
     S, timed = full['streams'], full['timed_steps']
-    wall = max_over_ranks(full['wall_s'])
-    fe_wall = max_over_ranks(fe_only['wall_s'])
-    frames_total = sum_over_ranks(S * timed)
-    feats_total = sum_over_ranks(float(full['features'][:, warm:].sum()))
-    published = sum_over_ranks(float(sum(len(t) for t in full['trajectories'])))
-    upload_max = max_over_ranks(upload_s)
+    wall = B.max_over_ranks(full['wall_s'])
+    fe_wall = B.max_over_ranks(fe_only['wall_s'])
+    frames_total = B.sum_over_ranks(S * timed)
+    feats_total = B.sum_over_ranks(float(full['features'][:, warm:].sum()))
+    published = B.sum_over_ranks(float(sum(len(t) for t in full['trajectories'])))
+    upload_max = B.max_over_ranks(upload_s)
     # accuracy of the offset-0 run of this rank's first sequence against its ground truth (sanity, not a parity gate)
     ate = None
     tr = full['trajectories'][0]
     if len(tr) > 10 and seqs[0].groundtruth is not None:
         m = trajectory_metrics(tr[:, 0], tr[:, 1:4], *seqs[0].groundtruth)
         ate = {'ate_rmse_m': m['ate_rmse_m'], 'path_m': m['path_m'], 'poses': int(len(tr))}
+    img_bytes = 2 * seqs[0].width * seqs[0].height
     for q in seqs:
         q.close()
     clocks = sampler.summary([(t_a, t_b)]) if sampler is not None else None
-    if rank == 0:
-        img_bytes = 2 * seqs[0].width * seqs[0].height
-        busy = full['estimator']['worker_busy_s']
-        line = {
-            'metric': METRIC, 'value': frames_total / wall, 'unit': UNIT, 'n_gpus': world, 'steps': timed, 'warmup': warm,
-            'ms_per_step': 1e3 * wall / timed, 'higher_is_better': True, 'scaling': 'weak' if world <= args.c5_sequences else 'strong',
-            'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (LK), f64 (undistort, MSCKF)', 'data': 'synthetic',
-            'config': {'workload': f'C5: {args.c5_sequences} EuRoC-geometry synthetic sequences x {args.c5_offsets} time offsets '
-                                   f'= {args.c5_sequences * args.c5_offsets} runs, full front end (C2 grid, 300 features) + host MSCKF, '
-                                   f'sharded by sequence over {world} GPU(s)',
-                       'runs_per_gpu': S, 'offset_spacing_s': step_frames / 20.0,
-                       'estimator_workers_per_gpu': workers, 'host_cores_per_rank': len(cores),
-                       'host_cpus_bound': sorted(bound) if bound else None,
-                       'frame_source': f'HBM frame store: each sequence uploaded once ({store_bytes / 1e6:.0f} MB on rank 0), '
-                                       f'every offset run gathers its frames on the device'},
-            'tracked_features_per_s': feats_total / wall,
-            'poses_published': int(published),
-            'front_end_only': {'value': frames_total / fe_wall, 'unit': UNIT, 'ms_per_step': 1e3 * fe_wall / timed,
-                               'note': 'same sweep without estimators: gather + frame chain + result arrays on the host'},
-            'estimator': {'worker_busy_s': [round(b, 3) for b in busy],
-                          'ms_per_frame': 1e3 * float(np.sum(busy)) / max(full['estimator']['frames'], 1),
-                          'note': 'host MSCKF (uav-airvision_b200/msckf.py) in worker processes; it bounds this leg'},
-            'e2e': {'value': frames_total / (wall + upload_max), 'unit': UNIT,
-                    'h2d_bytes_per_step': int(len(mine) * n_frames * img_bytes / args.c5_steps),
-                    'd2h_bytes_per_step': int(S * (48 + 300 * 40)),
-                    'note': 'includes the one-time upload of every sequence frame into the store (amortised over its offset runs); '
-                            'rendering the synthetic frames is excluded'},
-            'setup_s': {'render': round(render_s, 2), 'upload': round(upload_s, 3)},
-            'accuracy_run0': ate, 'gpu_launches': int(timed * full['kernels_per_step']), 'clocks': clocks,
-        }
-        print(json.dumps(line), flush=True)
+    if rank != 0:
+        return None
+    busy = full['estimator']['worker_busy_s']
+    return {
+        'metric': METRIC, 'value': frames_total / wall, 'unit': UNIT, 'n_gpus': world, 'steps': timed, 'warmup': warm,
+        'ms_per_step': 1e3 * wall / timed, 'higher_is_better': True, 'scaling': 'weak' if world <= n_seq else 'strong',
+        'vs_baseline': None, 'dtype': 'u8/int32 fixed-point + f32 (LK), f64 (undistort, MSCKF)', 'data': 'synthetic',
+        'config': {'workload': f'C5: {n_seq} EuRoC-geometry synthetic sequences x {n_off} time offsets '
+                               f'= {n_seq * n_off} runs, full front end (C2 grid, 300 features) + host MSCKF, '
+                               f'sharded by sequence over {world} GPU(s)',
+                   'runs_per_gpu': S, 'offset_spacing_s': step_frames / 20.0,
+                   'estimator_workers_per_gpu': workers, 'host_cores_per_rank': len(cores),
+                   'host_cpus_bound': sorted(bound) if bound else None,
+                   'frame_source': f'HBM frame store: each sequence uploaded once ({store_bytes / 1e6:.0f} MB on rank 0), '
+                                   f'every offset run gathers its frames on the device'},
+        'tracked_features_per_s': feats_total / wall,
+        'poses_published': int(published),
+        'front_end_only': {'value': frames_total / fe_wall, 'unit': UNIT, 'ms_per_step': 1e3 * fe_wall / timed,
+                           'note': 'same sweep without estimators: gather + frame chain + result arrays on the host'},
+        'estimator': {'worker_busy_s': [round(b, 3) for b in busy],
+                      'ms_per_frame': 1e3 * float(np.sum(busy)) / max(full['estimator']['frames'], 1),
+                      'errors': full['estimator'].get('errors') or None,
+                      'note': 'host MSCKF (uav-airvision_b200/msckf.py) in worker processes; it bounds this leg'},
+        'e2e': {'value': frames_total / (wall + upload_max), 'unit': UNIT,
+                'h2d_bytes_per_step': int(len(mine) * n_frames * img_bytes / n_steps),
+                'd2h_bytes_per_step': int(S * (48 + 300 * 40)),
+                'note': 'includes the one-time upload of every sequence frame into the store (amortised over its offset runs); '
+                        'rendering the synthetic frames is excluded'},
+        'setup_s': {'render': round(render_s, 2), 'upload': round(upload_s, 3)},
+        'accuracy_run0': ate, 'gpu_launches': int(timed * full['kernels_per_step']), 'clocks': clocks,
+    }
+
+
+# ---- one workload through the device-resident and the end-to-end leg --------------------------------------------------------
+class Bench:
+    """Shared state of a repo-arm run: torch handles, rank info, clock sampling windows."""
+
+    def __init__(self, torch, dist, rank, world, local):
+        self.torch, self.dist, self.rank, self.world, self.local = torch, dist, rank, world, local
+        self.windows = []
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        a = np.asarray(x, dtype=np.float64)
+        if self.world == 1:
+            return float(a) if a.ndim == 0 else a
+        t = self.torch.tensor(a.reshape(-1), device='cuda', dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        r = t.cpu().numpy().reshape(a.shape)
+        return float(r) if a.ndim == 0 else r
+
+    def max_over_ranks(self, x):
+        return self._reduce(x, 'MAX')
+
+    def sum_over_ranks(self, x):
+        return self._reduce(x, 'SUM')
+
+
+def measure(B, wl, W, K, est_ms, n_base, n_prof=12, pageable=True):
+    """Device-resident leg + end-to-end leg(s) of one workload.  Returns a dict of raw results."""
+    torch = B.torch
+    from image_processing import ImageProcessor, _native
+    from synth_euroc import SlidingTextureStream, img_msg, stereo_msg
+    cfg, skw, wname = workload(wl)
+    skw = dict(skw, seed=skw['seed'] + B.rank)            # every rank owns its own stream
+    R = repeats_for(K, est_ms)
+    base = SlidingTextureStream(n_frames=n_base, **skw)
+    frames = [base.frame(k) for k in range(n_base)]       # rendered once, decoded in RAM
+    base.frames = lambda: iter(frames)
+    T = W + 1 + R * K + n_prof
+    seq = ForthAndBack(base, frames, T)
+    Rs = rotations_for(cfg, seq)
+    width, height = base.w, base.h
+    img_bytes = width * height
+
+    # ---- device-resident leg ("value") --------------------------------------------------------------------
+    ctx = _native.Context(cfg, width, height, num_streams=1, device=B.local, use_graph=True)
+    bb = ctx.block_bytes
+    host_blocks = torch.empty((n_base, bb), dtype=torch.uint8).pin_memory()
+    hb = host_blocks.numpy()
+    Rs_base = rotations_for(cfg, base)                    # rotation sections of the base blocks (the C4 legs read them)
+    for k, f in enumerate(frames):
+        hb[k, :img_bytes] = f.cam0_image.reshape(-1)
+        hb[k, img_bytes:2 * img_bytes] = f.cam1_image.reshape(-1)
+        ctx.fill_rotations(hb[k], Rs_base[k][0], Rs_base[k][1])
+    dev_base = host_blocks.cuda(non_blocking=False)
+    # the timed sequence: T blocks, images gathered from the base frames, every step its own rotation section
+    rot_off, rot_len = ctx.rot_offset, ctx.rot_stride
+    scratch = np.zeros(bb, np.uint8)
+    rot_host = np.empty((T, rot_len), np.uint8)
+    for k in range(T):
+        ctx.fill_rotations(scratch, Rs[k][0], Rs[k][1])
+        rot_host[k] = scratch[rot_off:rot_off + rot_len]
+    dev_seq = dev_base[torch.from_numpy(seq.index).cuda()]
+    dev_seq[:, rot_off:rot_off + rot_len] = torch.from_numpy(rot_host).cuda()
+    torch.cuda.synchronize()
+    ptr = dev_seq.data_ptr()
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=B.local)
+    ctx.process_device(ptr)                               # frame 0 (first-frame chain, launched without a graph)
+    frame0_dev_ms = ctx.last_frame_ms()
+    for k in range(1, W + 1):
+        ctx.process_device(ptr + k * bb)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    B.barrier()
+    t_a = time.perf_counter()
+    ev[0].record(ext)
+    for r in range(R):
+        for k in range(W + 1 + r * K, W + 1 + (r + 1) * K):
+            ctx.enqueue_device(ptr + k * bb)
+        ev[r + 1].record(ext)
+    ctx.sync()
+    B.barrier()
+    B.windows.append((t_a, time.perf_counter()))
+    region_ms = np.atleast_1d(B.max_over_ranks(np.array([ev[r].elapsed_time(ev[r + 1]) for r in range(R)])))
+    hdr, ids, _ = ctx.result(0)
+    last_n_dev = int(hdr['n_features'])
+    kernels_per_frame = ctx.kernels_per_frame()
+    # per-stage device times of the steady-state chain, serialised (explains `value`; not a bench number)
+    stage_ms = {}
+    for k in range(W + 1 + R * K, T):
+        st = ctx.profile_frame_device(ptr + k * bb)
+        for name, v in st.items():
+            stage_ms.setdefault(name, []).append(v)
+    stage_ms = {k_: float(np.median(v)) for k_, v in stage_ms.items()}
+    ctx.close()
+
+    # ---- end-to-end leg through the public API ----------------------------------------------------------------
+    # With the frames' numpy arrays living in page-locked memory (the contract's "inputs in pinned host memory": libavb
+    # then DMAs straight from them) and, optionally, with ordinary pageable arrays (staged through the library's own
+    # pinned block, copy pipelined with the H2D).  The headline e2e is the pinned-input one.
+    n_e2e = W + 1 + R * K
+
+    def e2e_leg(pinned_inputs):
+        ip = ImageProcessor(cfg, device=B.local, use_graph=True)
+        counts, evs, nst = [], [], 0
+        for kind, msg in seq.events():
+            if kind == 'stereo':
+                if nst >= n_e2e:
+                    break
+                if pinned_inputs:
+                    b = int(seq.index[nst])
+                    i0 = hb[b, :img_bytes].reshape(height, width)
+                    i1 = hb[b, img_bytes:2 * img_bytes].reshape(height, width)
+                    msg = stereo_msg(msg.timestamp, i0, i1, img_msg(msg.timestamp, i0), img_msg(msg.timestamp, i1))
+                nst += 1
+            evs.append((kind, msg))
+        state = {'idx': 0, 'frames': 0}
+
+        def pump(until_frames):
+            while state['idx'] < len(evs) and state['frames'] < until_frames:
+                kind, msg = evs[state['idx']]
+                state['idx'] += 1
+                if kind == 'imu':
+                    ip.imu_callback(msg)
+                else:
+                    fm = ip.stereo_callback(msg)
+                    counts.append(len(fm.features))
+                    state['frames'] += 1
+
+        t0 = time.perf_counter()
+        pump(1)
+        frame0_ms = 1e3 * (time.perf_counter() - t0)
+        pump(W + 1)
+        B.barrier()
+        t_a = time.perf_counter()
+        spans = []
+        for r in range(R):
+            t0 = time.perf_counter()
+            pump(W + 1 + (r + 1) * K)
+            torch.cuda.synchronize()
+            spans.append(time.perf_counter() - t0)
+        B.barrier()
+        B.windows.append((t_a, time.perf_counter()))
+        cap = ip.context.capacity
+        ip.context.close()
+        return np.atleast_1d(B.max_over_ranks(np.array(spans))), counts, cap, frame0_ms
+
+    e2e_spans, feats_per_frame, cap, frame0_e2e_ms = e2e_leg(True)
+    assert feats_per_frame[W + R * K] == last_n_dev, 'device-resident and end-to-end legs disagree on the last frame'
+    res = dict(cfg=cfg, wname=wname, width=width, height=height, bb=bb, R=R, W=W, K=K, region_ms=region_ms,
+               e2e_spans=e2e_spans, feats_per_frame=feats_per_frame, cap=cap, kernels_per_frame=kernels_per_frame,
+               stage_ms=stage_ms, frame0_dev_ms=frame0_dev_ms, frame0_e2e_ms=frame0_e2e_ms, base=base, frames=frames,
+               dev_base=dev_base, hb=hb, n_base=n_base,
+               d2h_bytes=(int(_native.C.sizeof(_native.AvbFrameHeader)) + cap * 64 + 255) & ~255)
+    if pageable:
+        pg_spans, feats_pg, _, _ = e2e_leg(False)
+        assert feats_pg == feats_per_frame
+        res['pageable_spans'] = pg_spans
+    del dev_seq
+    return res
+
+
+def c4_leg(B, m, S, KM, with_sweep):
+    """BASELINE config C4 on this GPU: S time-offset runs of the bench sequence (run s starts 2*s frames in) lock-stepped in
+    one context, inputs resident in HBM.  The last timed frame of the first and the last run is compared with a
+    single-stream context fed the same frames (ids and published coordinates identical)."""
+    torch = B.torch
+    from image_processing import _native
+    cfg, width, height = m['cfg'], m['width'], m['height']
+    img_bytes = width * height
+    WM = 4
+    dev_base, bb1 = m['dev_base'], m['bb']
+    mctx = _native.Context(cfg, width, height, num_streams=S, device=B.local, use_graph=True)
+    mbb = mctx.block_bytes
+    rot_off = mctx.rot_offset
+    nblk = WM + 1 + KM + 2                            # + 2 frames for the serialised stage timing
+    assert 2 * (S - 1) + nblk <= m['n_base']
+    mblocks = torch.zeros((nblk, mbb), dtype=torch.uint8, device='cuda')
+    imgs = dev_base[:, :2 * img_bytes]
+    one = _native.Context(cfg, width, height, num_streams=1, device=B.local, use_graph=True)
+    rs_ = one.rot_stride                              # H | cam0_R_p_c | cam1_R_p_c per stream
+    Hs = dev_base[:, one.rot_offset:one.rot_offset + rs_]
+    for k in range(nblk):
+        src = torch.arange(S, device='cuda') * 2 + k      # run s starts 2*s frames into the sequence
+        mblocks[k, :S * 2 * img_bytes] = imgs[src].reshape(-1)
+        mblocks[k, rot_off:rot_off + S * rs_] = Hs[src].reshape(-1)
+    torch.cuda.synchronize()
+    mptr = mblocks.data_ptr()
+    mext = torch.cuda.ExternalStream(mctx.cuda_stream(), device=B.local)
+    for k in range(WM + 1):
+        mctx.process_device(mptr + k * mbb)
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    B.barrier()
+    t_a = time.perf_counter()
+    m0.record(mext)
+    for k in range(WM + 1, WM + 1 + KM):
+        mctx.enqueue_device(mptr + k * mbb)
+    m1.record(mext)
+    mctx.sync()
+    B.barrier()
+    B.windows.append((t_a, time.perf_counter()))
+    m_ms = B.max_over_ranks(m0.elapsed_time(m1))
+    nf = sum(int(mctx.result(s)[0]['n_features']) for s in range(S))
+    # parity of the timed shape: the first and the last run against a single-stream context on the same frames
+    checked = []
+    for s in sorted({0, S - 1}):
+        _, ids_m, meas_m = mctx.result(s)
+        ids_m, meas_m = ids_m.copy(), meas_m.copy()
+        one.reset()
+        for k in range(WM + 1 + KM):
+            one.process_device(dev_base.data_ptr() + (2 * s + k) * bb1)
+        _, ids_1, meas_1 = one.result(0)
+        assert np.array_equal(ids_m, ids_1) and np.array_equal(meas_m, meas_1), \
+            f'C4 leg: run {s} of the {S}-run context differs from a single-stream context on its last timed frame'
+        checked.append(s)
+    one.close()
+    mctx.profile_frame_device(mptr + (nblk - 2) * mbb)
+    st = mctx.profile_frame_device(mptr + (nblk - 1) * mbb)
+    kern = mctx.kernels_per_frame()
+    mctx.close()
+    bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nf / S)
+    world = B.world
+    out = {'streams_total': S * world, 'streams_per_gpu': S, 'steps': KM, 'value': world * S * KM / (m_ms * 1e-3),
+           'unit': UNIT, 'ms_per_step': m_ms / KM, 'features_per_frame': nf / S, 'kernels_per_step': kern,
+           'hbm_gbs': bpf * S * KM / (m_ms * 1e-3) / 1e9,
+           'stage_ms': {k_: round(v, 4) for k_, v in st.items()},
+           'stage_hbm_gbs': {k_: round(b / (st[k_] * 1e-3) / 1e9, 1)
+                             for k_, b in stage_bytes(width, height, cfg.pyramid_levels, S).items() if st.get(k_, 0) > 0},
+           'parity_checked': f'last timed frame of runs {checked}: ids and published coordinates identical to a single-stream '
+                             f'context on the same frames (tests/test_gpu_many_streams.py pins every run and frame to the port)',
+           'note': 'S time-offset runs of the sequence (run s starts 2*s frames in), lock-stepped in one context: every '
+                   'kernel launch covers all S runs; inputs resident in HBM (device-resident figure, like `value`)'}
+    del mblocks
+    if with_sweep:
+        # the same sweep through the public driver: the sequence cached once in an HBM frame store, every run gathers its
+        # frames on the device, results come back as host arrays (sweep.run_sweep; wall clock, IMU windows included)
+        from sweep import CachedSequence, run_sweep
+
+        class _Seq:
+            def __init__(self, fr, st):
+                self.fr, self.st, self.n = fr, st, len(fr)
+
+            def frames(self):
+                return iter(self.fr)
+
+            def imu(self):
+                return self.st.imu()
+        base = m['base']
+        cached = CachedSequence(_Seq(m['frames'], base), device=B.local, name='bench sequence')
+        sw = run_sweep(cfg, [cached], [(2 * s_ + 0.5) / base.rate for s_ in range(S)], device=B.local,
+                       n_steps=min(200, len(m['frames']) - 2 * (S - 1)), warmup_steps=WM + 1)
+        B.barrier()
+        sw_wall = B.max_over_ranks(sw['wall_s'])
+        cached.close()
+        out['e2e_from_store'] = {'value': world * S * sw['timed_steps'] / sw_wall, 'unit': UNIT,
+                                 'ms_per_step': 1e3 * sw_wall / sw['timed_steps'], 'steps': sw['timed_steps'],
+                                 'features_per_frame': float(sw['features'][:, WM + 1:].mean()),
+                                 'note': 'sweep.run_sweep: frames gathered from the HBM frame store (sequence uploaded once), '
+                                         'per-run IMU windows on the host, ids + measurements of every run copied to host arrays'}
+    return out
 
 
 def main():
@@ -344,9 +739,10 @@ def main():
     ap.add_argument('--c5-steps', type=int, default=60)
     ap.add_argument('--c5-workers', type=int, default=0, help='estimator processes per GPU (0 = host cores of the rank)')
     ap.add_argument('--streams', type=int, default=64,
-                    help='total streams of the extra multi-stream leg (config C4), sharded over the GPUs (0 = skip)')
+                    help='total runs of the multi-stream leg (config C4), sharded over the GPUs (0 = skip)')
     ap.add_argument('--ms-steps', type=int, default=20)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-sublegs', action='store_true', help='skip the compact c3 / c5 legs of the default line')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -371,229 +767,94 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    B = Bench(torch, dist, rank, world, local)
 
     if args.workload == 'c5':
-        run_c5(args, rank, world, local, torch, dist, barrier, max_over_ranks, sum_over_ranks, bound)
+        line = run_c5(B, args.c5_sequences, args.c5_offsets, args.c5_steps, args.c5_workers, bound)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    from image_processing import ImageProcessor, _native
-    cfg, skw, wname = workload(args.workload)
-    skw = dict(skw, seed=skw['seed'] + rank)              # every rank owns its own stream
     W, K = args.warmup, args.steps
-    n_prof = 12
-    # multi-stream leg = BASELINE config C4: `--streams` (64) independent time-offset runs in total, sharded over the GPUs
-    S_ms = max(1, args.streams // world) if args.streams > 0 else 0
-    n_extra = (2 * (S_ms - 1) + max(4 + 1 + args.ms_steps + 2, 105)) if S_ms > 0 else 0      # >= 100 timed steps for the store-fed sweep
-    n = max(W + K + 1 + n_prof, n_extra)
-    stream = make_sequence(skw, n)
-    frames = [stream.frame(k) for k in range(n)]
-    stream.frames = lambda: iter(frames)
-    Rs = rotations_for(cfg, stream)
-    width, height = stream.w, stream.h
-
-    # ---- device-resident leg ("value") --------------------------------------------------------------------
-    ctx = _native.Context(cfg, width, height, num_streams=1, device=local, use_graph=True)
-    bb = ctx.block_bytes
-    host_blocks = torch.empty((n, bb), dtype=torch.uint8).pin_memory()
-    hb = host_blocks.numpy()
-    img_bytes = width * height
-    for k, f in enumerate(frames):
-        hb[k, :img_bytes] = f.cam0_image.reshape(-1)
-        hb[k, img_bytes:2 * img_bytes] = f.cam1_image.reshape(-1)
-        ctx.fill_rotations(hb[k], Rs[k][0], Rs[k][1])
-    dev_blocks = host_blocks.cuda(non_blocking=False)
-    ptr = dev_blocks.data_ptr()
-    ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local)
     sampler = ClockSampler(local) if rank == 0 else None
-    windows = []
+    # multi-stream legs = BASELINE config C4: `--streams` (64) time-offset runs in total, sharded over the GPUs (strong), and
+    # `--streams` runs on every GPU (weak)
+    c4 = args.streams > 0 and args.workload == 'c2'
+    S_strong = max(1, args.streams // world) if c4 else 0
+    S_weak = args.streams if c4 else 0
+    n_extra = (2 * (max(S_strong, S_weak) - 1) + max(4 + 1 + args.ms_steps + 2, 105)) if c4 else 0
+    est = {'c2': 0.12, 'c3': 0.35}[args.workload]
+    m = measure(B, args.workload, W, K, est, n_base=max(200 if args.workload == 'c2' else 48, n_extra))
+    cfg, wname, width, height = m['cfg'], m['wname'], m['width'], m['height']
+    R = m['R']
+    timed_feats = float(np.sum(m['feats_per_frame'][W + 1:W + 1 + R * K])) / R      # per region of K frames
+    total_feats = B.sum_over_ranks(timed_feats)
 
-    for k in range(W + 1):                                # frame 0 (first-frame chain) + W warm-up frames
-        ctx.process_device(ptr + k * bb)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_a = time.perf_counter()
-    e0.record(ext)
-    for k in range(W + 1, W + 1 + K):
-        ctx.enqueue_device(ptr + k * bb)
-    e1.record(ext)
-    ctx.sync()
-    barrier()
-    windows.append((t_a, time.perf_counter()))
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    hdr, ids, _ = ctx.result(0)
-    last_n_dev = int(hdr['n_features'])
-    kernels_per_frame = ctx.kernels_per_frame()
+    multi = weak = None
+    if c4:
+        multi = c4_leg(B, m, S_strong, args.ms_steps, with_sweep=True)
+        multi['config'] = f'C4 strong: {S_strong * world} independent time-offset runs sharded over {world} GPU(s)'
+        if world > 1:
+            weak = c4_leg(B, m, S_weak, args.ms_steps, with_sweep=False)
+            weak['config'] = f'C4 weak: {S_weak} time-offset runs on each of {world} GPU(s)'
+        else:
+            weak = {'same_as': 'multi_stream (one GPU: 64 runs in total = 64 runs per GPU)', 'value': multi['value'],
+                    'unit': UNIT, 'streams_per_gpu': S_weak, 'streams_total': S_weak}
 
-    # per-stage device times of the steady-state chain, serialised (explains `value`; not a bench number)
-    stage_ms = {}
-    for k in range(W + 1 + K, W + 1 + K + n_prof):
-        st = ctx.profile_frame_device(ptr + k * bb)
-        for name, v in st.items():
-            stage_ms.setdefault(name, []).append(v)
-    stage_ms = {k_: float(np.median(v)) for k_, v in stage_ms.items()}
-    ctx.close()
+    # ---- compact legs of the other BASELINE configurations (one GPU only: the driver's BENCH record carries them) ----------
+    c3 = c5 = None
+    if world == 1 and args.workload == 'c2' and not args.no_sublegs:
+        m3 = measure(B, 'c3', 3, 30, 0.35, n_base=40, n_prof=4, pageable=False)
+        r3 = float(np.median(m3['region_ms']))
+        e3 = float(np.median(m3['e2e_spans']))
+        c3 = {'workload': m3['wname'], 'steps': 30, 'warmup': 3, 'repeats': m3['R'],
+              'value': 30 / (r3 * 1e-3), 'ms_per_step': r3 / 30, 'unit': UNIT,
+              'e2e': {'value': 30 / e3, 'ms_per_step': 1e3 * e3 / 30, 'h2d_bytes_per_step': int(m3['bb']),
+                      'd2h_bytes_per_step': int(m3['d2h_bytes'])},
+              'features_per_frame': float(np.mean(m3['feats_per_frame'][4:])), 'kernels_per_frame': m3['kernels_per_frame'],
+              'frame0_ms': {'device': m3['frame0_dev_ms'], 'e2e': m3['frame0_e2e_ms']},
+              'stage_ms_serialised': {k_: round(v, 4) for k_, v in m3['stage_ms'].items()}}
+        del m3
+        torch.cuda.empty_cache()
+        c5line = run_c5(B, 2, 8, 40, 0, bound)
+        c5 = {k_: c5line[k_] for k_ in ('value', 'unit', 'steps', 'ms_per_step', 'tracked_features_per_s', 'poses_published',
+                                        'front_end_only', 'accuracy_run0', 'setup_s')}
+        c5['workload'] = c5line['config']['workload'] + ' (compact: the full C5 is `--workload c5`)'
+        c5['estimator'] = {'ms_per_frame': c5line['estimator']['ms_per_frame'],
+                           'workers': c5line['config']['estimator_workers_per_gpu'], 'errors': c5line['estimator']['errors']}
 
-    # ---- end-to-end leg through the public API ----------------------------------------------------------------
-    # Run twice: with the frames' numpy arrays living in page-locked memory (the contract's "inputs in pinned host
-    # memory": libavb then DMAs straight from them) and with ordinary pageable arrays (staged through the library's
-    # own pinned block, copy pipelined with the H2D).  The headline e2e is the pinned-input one.
-    from synth_euroc import img_msg, stereo_msg
-
-    def e2e_leg(pinned_inputs):
-        ip = ImageProcessor(cfg, device=local, use_graph=True)
-        counts = []
-        evs = []
-        for kind, msg in stream.events():
-            if kind == 'stereo' and pinned_inputs:
-                k = len([1 for e in evs if e[0] == 'stereo'])
-                i0 = hb[k, :img_bytes].reshape(height, width)
-                i1 = hb[k, img_bytes:2 * img_bytes].reshape(height, width)
-                msg = stereo_msg(msg.timestamp, i0, i1, img_msg(msg.timestamp, i0), img_msg(msg.timestamp, i1))
-            evs.append((kind, msg))
-        state = {'idx': 0, 'frames': 0}
-
-        def pump(until_frames):
-            while state['idx'] < len(evs) and state['frames'] < until_frames:
-                kind, msg = evs[state['idx']]
-                state['idx'] += 1
-                if kind == 'imu':
-                    ip.imu_callback(msg)
-                else:
-                    fm = ip.stereo_callback(msg)
-                    counts.append(len(fm.features))
-                    state['frames'] += 1
-
-        pump(W + 1)
-        barrier()
-        t0 = time.perf_counter()
-        pump(W + 1 + K)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        barrier()
-        windows.append((t0, t1))
-        cap = ip.context.capacity
-        ip.context.close()
-        return max_over_ranks(t1 - t0), counts, cap
-
-    e2e_s, feats_per_frame, cap = e2e_leg(True)
-    e2e_pageable_s, feats_pg, _ = e2e_leg(False)
-    d2h_bytes = (int(_native.C.sizeof(_native.AvbFrameHeader)) + cap * 64 + 255) & ~255
-    timed_feats = sum(feats_per_frame[W + 1:W + 1 + K])
-    assert feats_per_frame[W + K] == last_n_dev, 'device-resident and end-to-end legs disagree on the last frame'
-    assert feats_pg == feats_per_frame
-    total_feats = sum_over_ranks(timed_feats)
-
-    # ---- multi-stream leg: S time-offset runs of the same sequence per GPU (run.bat sweep shape) ---------------
-    multi = None
-    if S_ms > 0:
-        S, KM, WM = S_ms, args.ms_steps, 4
-        mctx = _native.Context(cfg, width, height, num_streams=S, device=local, use_graph=True)
-        mbb = mctx.block_bytes
-        rot_off = mctx.rot_offset
-        nblk = WM + 1 + KM + 2                            # + 2 frames for the serialised stage timing
-        mblocks = torch.zeros((nblk, mbb), dtype=torch.uint8, device='cuda')
-        imgs = dev_blocks[:, :2 * img_bytes]
-        rs_ = ctx.rot_stride                              # H | cam0_R_p_c | cam1_R_p_c per stream
-        Hs = dev_blocks[:, ctx.rot_offset:ctx.rot_offset + rs_]
-        for k in range(nblk):
-            src = torch.arange(S, device='cuda') * 2 + k      # stream s starts 2*s frames into the sequence
-            mblocks[k, :S * 2 * img_bytes] = imgs[src].reshape(-1)
-            mblocks[k, rot_off:rot_off + S * rs_] = Hs[src].reshape(-1)
-        mptr = mblocks.data_ptr()
-        mext = torch.cuda.ExternalStream(mctx.cuda_stream(), device=local)
-        for k in range(WM + 1):
-            mctx.process_device(mptr + k * mbb)
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        t_a = time.perf_counter()
-        m0.record(mext)
-        for k in range(WM + 1, WM + 1 + KM):
-            mctx.enqueue_device(mptr + k * mbb)
-        m1.record(mext)
-        mctx.sync()
-        barrier()
-        windows.append((t_a, time.perf_counter()))
-        m_ms = max_over_ranks(m0.elapsed_time(m1))
-        nf = sum(int(mctx.result(s)[0]['n_features']) for s in range(S))
-        mctx.profile_frame_device(mptr + (nblk - 2) * mbb)
-        st = mctx.profile_frame_device(mptr + (nblk - 1) * mbb)
-        mctx.close()
-        bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nf / S)
-        m_fps = world * S * KM / (m_ms * 1e-3)
-        multi = {'config': f'C4: {S * world} independent time-offset runs sharded over {world} GPU(s)', 'streams_total': S * world,
-                 'streams_per_gpu': S, 'steps': KM, 'value': m_fps, 'unit': UNIT, 'ms_per_step': m_ms / KM,
-                 'features_per_frame': nf / S, 'hbm_gbs': bpf * S * KM / (m_ms * 1e-3) / 1e9,
-                 'stage_ms': {k_: round(v, 4) for k_, v in st.items()},
-                 'stage_hbm_gbs': {k_: round(b / (st[k_] * 1e-3) / 1e9, 1)
-                                   for k_, b in stage_bytes(width, height, cfg.pyramid_levels, S).items() if st.get(k_, 0) > 0},
-                 'note': 'S time-offset runs of the sequence (stream s starts 2*s frames in), lock-stepped in one '
-                         'context: every kernel launch covers all S streams; inputs resident in HBM'}
-        del mblocks
-        # the same sweep through the public driver: the sequence cached once in an HBM frame store, every run gathers its
-        # frames on the device, results come back as host arrays (sweep.run_sweep; wall clock, IMU windows included)
-        from sweep import CachedSequence, run_sweep
-
-        class _Seq:
-            def __init__(self, fr, st):
-                self.fr, self.st, self.n = fr, st, len(fr)
-
-            def frames(self):
-                return iter(self.fr)
-
-            def imu(self):
-                return self.st.imu()
-        cached = CachedSequence(_Seq(frames, stream), device=local, name='bench sequence')
-        # every frame the offsets leave available (at most 200 steps): a window of a few milliseconds is all noise
-        sw = run_sweep(cfg, [cached], [(2 * s_ + 0.5) / stream.rate for s_ in range(S)], device=local,
-                       n_steps=min(200, len(frames) - 2 * (S - 1)), warmup_steps=WM + 1)
-        barrier()
-        sw_wall = max_over_ranks(sw['wall_s'])
-        cached.close()
-        multi['e2e_from_store'] = {'value': world * S * sw['timed_steps'] / sw_wall, 'unit': UNIT,
-                                   'ms_per_step': 1e3 * sw_wall / sw['timed_steps'], 'steps': sw['timed_steps'],
-                                   'features_per_frame': float(sw['features'][:, WM + 1:].mean()),
-                                   'note': 'sweep.run_sweep: frames gathered from the HBM frame store (sequence uploaded once), '
-                                           'per-run IMU windows on the host, ids + measurements of every run copied to host arrays'}
-
-    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N=1 only): the unmodified reference on a bounded sample -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, full_affinity)            # the CPU path may use every host core
-        import cv2
-        cv2.setNumThreads(-1)
-        times, cfeats, threads, cvv = cpu_front_end(cfg, stream, min(n, W + 1 + K), budget_s=25.0)
-        done = len(times)
-        w_ = min(W + 1, max(done - 1, 1))
-        tot = float(np.sum(times[w_:]))
-        cpu = {'value': (done - w_) / tot if tot > 0 else 0.0, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': f'{done - w_} consecutive frames of the same stream (after frame 0 + {w_ - 1} warm-up frames), '
-                         f'oracle/pipeline_port.py with cv2 {cvv} where the reference calls cv2; host cores '
-                         f'{os.cpu_count()}, cv2 threads {threads}',
-               'ms_per_frame_median': 1e3 * float(np.median(times[w_:])), 'frame0_ms': 1e3 * times[0],
-               'tracked_features_per_s': float(np.sum(cfeats[w_:]) / tot) if tot > 0 else 0.0}
+        cores = os.cpu_count() or 1
+        n_cpu = int(min(W + 1 + K, 300))
+        port_t, port_f, port_threads, cvv = port_front_end(cfg, ForthAndBack(m['base'], m['frames'], n_cpu), n_cpu, budget_s=12.0)
+        pw = min(W + 1, max(len(port_t) - 1, 1))
+        port = {'value': (len(port_t) - pw) / float(np.sum(port_t[pw:])), 'kind': 'port', 'cores': port_threads,
+                'note': 'oracle/pipeline_port.py (vectorised restatement, cv2 at the same call sites): kept beside the reference figure'}
+        v = cpu_variants(args.workload, n_cpu, W, cores) if ref_available() else None
+        if v is not None and c3 is not None:
+            v3 = run_ref('c3', 3 + 1 + 8, 3, threads=0)
+            if v3 is not None:
+                c3['cpu_reference'] = {'value': v3['fps'], 'kind': 'reference', 'cores': v3['cv2_threads'],
+                                       'frames_timed': v3['frames_timed'],
+                                       'note': 'unmodified reference, one stream, cv2 default threads; no RANSAC stage exists there'}
+                c3['e2e_vs_cpu_reference'] = c3['e2e']['value'] / v3['fps']
+        if v is not None:
+            one = v['one_stream_default_threads']
+            cpu = {'value': one['value'], 'unit': UNIT, 'cores': one['cv2_threads'], 'kind': 'reference',
+                   'sample': f'{one["frames_timed"]} consecutive frames of the same stream (after frame 0 + {W} warm-up frames) through the '
+                             f'UNMODIFIED reference front end (oracle/_ref: image_processing/pipeline.py:46-150), one stream, cv2 {v["cv2"]} '
+                             f'with its default {one["cv2_threads"]} threads; host cores {cores}',
+                   'ms_per_frame_median': one['ms_median'], 'frame0_ms': one['frame0_ms'],
+                   'tracked_features_per_s': one['tracked_features_per_s'], 'variants': v, 'port': port}
+        else:
+            cpu = dict(port, unit=UNIT, sample=f'{len(port_t) - pw} frames; oracle/_ref missing: the PORT stands in (tools/make_oracle_ref.sh)')
 
-    clocks = sampler.summary(windows) if sampler is not None else None
+    clocks = sampler.summary(B.windows) if sampler is not None else None
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -601,11 +862,15 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
         else:
             peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        dev_ms = float(np.median(m['region_ms']))
+        e2e_s = float(np.median(m['e2e_spans']))
+        pg_s = float(np.median(m['pageable_spans']))
         fps = world * K / (dev_ms * 1e-3)
         nfeat = timed_feats / K
         bpf = algorithmic_bytes_per_frame(width, height, cfg.pyramid_levels, nfeat)
         chain_ms = dev_ms / K
         achieved = bpf / (chain_ms * 1e-3) / 1e9
+        bb = m['bb']
         traffic, traffic_src = None, None                 # measured DRAM bytes of one frame chain (ncu --set full capture)
         tpath = os.path.join(ROOT, 'profiles', f'roofline_traffic_{args.workload}.json')
         if os.path.exists(tpath):
@@ -613,35 +878,40 @@ def main():
             if 'warm' in tj:            # the chain as it runs (caches left alone); the cold-cache replay figure beside it
                 traffic = float(tj['warm']['bytes_per_frame']) + float(bb)
                 traffic_src = (f"profiles/{os.path.basename(tpath)}: {float(tj['warm']['bytes_per_frame']):.0f} B by the kernels "
-                               f"(ncu --cache-control none, DRAM counters of the running chain, 200 distinct frames: the kernels "
-                               f"find the just-copied input block and both pyramids in L2) + {int(bb)} B read by the copy engine "
-                               f"that places the frame's input block; cold-cache replay of the same kernels (--set full, caches "
-                               f"flushed before every kernel): {float(tj['bytes_per_frame']):.0f} B")
+                               f"(ncu --cache-control none, DRAM counters of the running chain: the kernels find the just-copied "
+                               f"input block and both pyramids in L2) + {int(bb)} B read by the copy engine that places the "
+                               f"frame's input block; cold-cache replay of the same kernels (--set full, caches flushed before "
+                               f"every kernel): {float(tj['bytes_per_frame']):.0f} B")
             else:
                 traffic, traffic_src = float(tj['bytes_per_frame']), f"profiles/{os.path.basename(tpath)} ({tj.get('note', '')})"
+        stage_ms = m['stage_ms']
         kernel_stages = {k_: v for k_, v in stage_ms.items() if k_ not in ('input_copy', 'result_copy')}
         dominant = max(kernel_stages, key=kernel_stages.get)
+        kpf = m['kernels_per_frame']
         line = {
-            'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'repeats': R,
             'ms_per_step': chain_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u8/int32 fixed-point + f32 (LK), f64 (undistort)', 'data': 'synthetic',
-            'config': {'workload': wname, 'streams_per_gpu': 1, 'features_per_frame': nfeat,
-                       'l2_policy': f'{W + K + 1} distinct frames x {2 * img_bytes} B = '
-                                    f'{(W + K + 1) * 2 * img_bytes / 1e6:.0f} MB device-resident sequence, each read once '
-                                    f'(larger than the 126 MB L2 when steps >= 180)',
-                       'frame_graph': 'one CUDA-graph launch per frame',
-                       'host_cpus_bound': sorted(bound) if bound else None},
+            'dtype': DTYPE, 'data': 'synthetic', 'config': line_config(wname, world),
+            'value_is': 'device-resident (inputs in HBM, no host result awaited per frame): explains e2e; the SURVEY 8(d) metric '
+                        '(feature_msg materialised on the host) is `e2e`',
+            'region_ms': {'median': dev_ms, 'min': float(np.min(m['region_ms'])), 'max': float(np.max(m['region_ms']))},
+            'features_per_frame': nfeat, 'host_cpus_bound': sorted(bound) if bound else None,
+            'frame_graph': 'one CUDA-graph launch per frame',
             'tracked_features_per_s': total_feats / (dev_ms * 1e-3),
+            'frame0_ms': {'device': m['frame0_dev_ms'], 'e2e': m['frame0_e2e_ms'],
+                          'note': 'first frame of a stream: FAST + stereo match of EVERY keypoint (feature_initializer.py:45-85), '
+                                  'launched without a graph'},
             'e2e': {'value': world * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(bb),
-                    'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': 1e3 * e2e_s / K,
+                    'd2h_bytes_per_step': int(m['d2h_bytes']), 'ms_per_step': 1e3 * e2e_s / K, 'repeats': R,
+                    'region_s': {'median': e2e_s, 'min': float(np.min(m['e2e_spans'])), 'max': float(np.max(m['e2e_spans']))},
                     'tracked_features_per_s': total_feats / e2e_s,
                     'api': 'ImageProcessor.stereo_callback(stereo_msg) -> feature_msg, host numpy images (page-locked) in, '
                            'FeatureMeasurement list out',
-                    'pageable_inputs': {'value': world * K / e2e_pageable_s, 'ms_per_step': 1e3 * e2e_pageable_s / K,
+                    'pageable_inputs': {'value': world * K / pg_s, 'ms_per_step': 1e3 * pg_s / K,
                                         'note': 'same call with ordinary pageable numpy arrays: staged through the '
                                                 'library pinned block, host copy pipelined with the H2D'}},
-            'gpu_launches': int(K * kernels_per_frame),
-            'roofline': {'bound': 'hbm', 'kernel': f'frame chain ({kernels_per_frame} kernels, one CUDA graph); '
+            'gpu_launches': int(K * kpf),
+            'roofline': {'bound': 'hbm', 'kernel': f'frame chain ({kpf} kernels, one CUDA graph); '
                                                    f'dominant stage by time: {dominant}',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
@@ -649,7 +919,7 @@ def main():
                          'stage_ms_serialised': {k_: round(v, 4) for k_, v in stage_ms.items()},
                          'note': 'single stream = latency-bound dependent chain; see multi_stream for the '
                                  'batched figure and DESIGN.md section 5'},
-            'multi_stream': multi,
+            'multi_stream': multi, 'c4_weak': weak, 'c3': c3, 'c5': c5,
             'cpu_baseline': cpu,
             'clocks': clocks,
         }

@@ -62,7 +62,7 @@ def test_no_cpu_fallback_without_device():
     if torch.cuda.is_available():
         pytest.skip('a GPU is present; the no-device path cannot be exercised here')
     from image_processing import _native
-    from oracle.configs import config_default
+    from frontend_config import config_default
     with pytest.raises(RuntimeError, match='no CUDA device|AVB|avb_create'):
         _native.Context(config_default(), 752, 480)
     from image_processing import ImageProcessor
@@ -91,7 +91,7 @@ def test_imu_processor_matches_port():
     """Host-side gyro integration (C helper behind the Python class) against the oracle port, incl. the window
     quirks (B13).  Equal to a few ulp: the C code sums R^T w in a fixed order, numpy's matmul in its own."""
     from image_processing import IMUProcessor
-    from oracle.configs import config_default
+    from frontend_config import config_default
     from oracle.pipeline_port import FrontEndPort
     from synth_euroc import img_msg, imu_msg
     cfg = config_default()
@@ -117,7 +117,7 @@ def test_host_extension_imu_integration_matches_python_rule():
     """_avbhost.integrate_imu (C) == the window rule of the reference's IMUProcessor.integrate_imu_data
     (imu_processor.py:28-67): first t >= t_prev-0.01 .. first t >= t_curr-0.004, identity + no trim when open."""
     from image_processing.imu_processor import IMUProcessor, rodrigues
-    from oracle.configs import config_default
+    from frontend_config import config_default
     from synth_euroc import img_msg, imu_msg
     cfg = config_default()
     imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
@@ -185,7 +185,7 @@ def test_host_side_stage_logic_without_gpu():
     """FeaturePruner and FeatureTracker.predict_feature_tracking are pure host code: check them against the rules
     (stable lifetime ranking, B9; H = K R K^-1 in float64 -> float32)."""
     from image_processing import FeatureMetaData, FeaturePruner, FeatureTracker, IMUProcessor
-    from oracle.configs import config_default
+    from frontend_config import config_default
     cfg = config_default()
     feats = []
     for i, life in enumerate([3, 7, 7, 1, 7, 2, 9]):

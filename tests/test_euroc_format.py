@@ -112,7 +112,7 @@ def test_reader_matches_the_reference_reader(tmp_path):
     spec.loader.exec_module(ref)
     from euroc import EuRoCDataset, write_euroc
     from synth_euroc import RoomSceneStream
-    from oracle.configs import config_default
+    from frontend_config import config_default
     st = RoomSceneStream(config_default(), n_frames=4, seed=1, tex_size=512)
     write_euroc(str(tmp_path / 'room'), st)
     a, b = EuRoCDataset(str(tmp_path / 'room')), ref.EuRoCDataset(str(tmp_path / 'room'))

@@ -1,0 +1,193 @@
+"""GPU parity of the MANY-STREAM launch shapes (BASELINE config C4: time-offset runs of a sequence, `run.bat:4-12`, 64 in
+total = 64 per GPU or 8 per GPU on eight).  A context with many streams takes different launch paths from the
+single-stream one the other parity tests pin: one warp per feature in the LK kernels, `k_pyr_down` for every pyramid
+level instead of `k_pyr_pair`, new-feature stereo matching in two dense rounds, a device mirror of the result block and
+one bulk D2H copy instead of zero-copy stores.  Here those shapes are compared, stream by stream and frame by frame,
+with single-stream contexts AND with the oracle port (reference: `image_processing/pipeline.py:46-150` per stream)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from frontend_config import FrontEndConfig, config_c2
+from oracle import cv_semantics as cs
+from oracle.pipeline_port import FrontEndPort
+from synth_euroc import SlidingTextureStream
+
+LOSSY = dict(seed=5, sigma=2.0, drift=(2.2, -1.4), gyro=(0.02, 0.01, -0.03), noise=2.5,
+             movers=[(200, 150, 40, -3.0, 4.0), (520, 300, 50, 5.0, -2.5), (380, 240, 30, -6.0, -5.0)])
+
+
+def _rotations(cfg, stream):
+    """cam0_R_p_c / cam1_R_p_c between consecutive frames of the sequence, as the pipeline's IMUProcessor forms them."""
+    from image_processing import IMUProcessor
+    imu = IMUProcessor(cfg.T_imu_cam0, cfg.T_imu_cam1)
+    out, prev = [], None
+    for kind, msg in stream.events():
+        if kind == 'imu':
+            imu.imu_callback(msg)
+            continue
+        imu.cam0_prev_img_msg, imu.cam0_curr_img_msg = prev, msg.cam0_msg
+        out.append((np.eye(3), np.eye(3)) if prev is None else tuple(imu.integrate_imu_data()))
+        prev = msg.cam0_msg
+    return out
+
+
+def _snapshot(ctx, s):
+    hdr, ids, meas = ctx.result(s)
+    cell, life, p0, p1 = ctx.features(s)
+    return dict(ids=ids.copy(), meas=meas.copy(), cell=cell, life=life, p0=p0, p1=p1,
+                hdr=tuple(int(hdr[k]) for k in ('n_features', 'next_feature_id', 'before_tracking', 'after_tracking',
+                                                'after_matching', 'after_ransac', 'has_new', 'n_fast', 'n_candidates',
+                                                'frame_index')))
+
+
+def _offset_runs(cfg, S, n_steps, stride, skw, width=752, height=480):
+    """S time-offset runs of ONE sequence (run s starts `stride * s` frames in), lock-stepped in one S-stream context
+    and, for comparison, each alone in a single-stream context.  Returns (multi[s][k], single[s][k], frames, Rs)."""
+    from image_processing import _native
+    n = stride * (S - 1) + n_steps
+    st = SlidingTextureStream(width=width, height=height, n_frames=n, **skw)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    multi = [[] for _ in range(S)]
+    ctx = _native.Context(cfg, width, height, num_streams=S)
+    try:
+        for k in range(n_steps):
+            idx = [stride * s + k for s in range(S)]
+            R0 = None if k == 0 else np.stack([Rs[i][0] for i in idx])
+            R1 = None if k == 0 else np.stack([Rs[i][1] for i in idx])
+            ctx.process([frames[i].cam0_image for i in idx], [frames[i].cam1_image for i in idx], R0, R1)
+            for s in range(S):
+                multi[s].append(_snapshot(ctx, s))
+        kernels = ctx.kernels_per_frame()
+    finally:
+        ctx.close()
+    single = [[] for _ in range(S)]
+    one = _native.Context(cfg, width, height, num_streams=1)
+    try:
+        for s in range(S):
+            one.reset()
+            for k in range(n_steps):
+                i = stride * s + k
+                one.process([frames[i].cam0_image], [frames[i].cam1_image], None if k == 0 else Rs[i][0],
+                            None if k == 0 else Rs[i][1])
+                single[s].append(_snapshot(one, 0))
+    finally:
+        one.close()
+    return multi, single, frames, Rs, kernels
+
+
+def _port_run(cfg, st, first, n_steps):
+    """The oracle port on frames first .. first + n_steps - 1 of the sequence (IMU samples older than the run's first
+    frame never reach a window: imu_processor.py:28-48 starts at t_prev - 0.01)."""
+    fe = FrontEndPort(cfg, backend='cv2')
+    out, k = [], 0
+    for kind, msg in st.events():
+        if kind == 'imu':
+            fe.imu_callback(msg)
+            continue
+        if k >= first:
+            fm = fe.stereo_callback(msg)
+            pub = np.array([[f.u0, f.v0, f.u1, f.v1] for f in fm.features], np.float64).reshape(-1, 4)
+            out.append(dict(ids=fe.ids.copy(), cell=fe.cell.copy(), life=fe.life.copy(), p0=fe.p0.astype(np.float64),
+                            p1=fe.p1.astype(np.float64), pub=pub))
+            if len(out) == n_steps:
+                break
+        k += 1
+    return out
+
+
+def _assert_equal_runs(a, b, what):
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x['hdr'] == y['hdr'], f'{what} frame {k}: header / counters {x["hdr"]} vs {y["hdr"]}'
+        for key in ('ids', 'cell', 'life', 'p0', 'p1', 'meas'):
+            assert np.array_equal(x[key], y[key]), f'{what} frame {k}: {key} differ'
+
+
+def _assert_equals_port(run, ref, what):
+    worst = 0.0
+    for k, (f, r) in enumerate(zip(run, ref)):
+        assert np.array_equal(f['ids'], r['ids']), f'{what} frame {k}: ids differ from the port'
+        assert np.array_equal(f['cell'], r['cell']) and np.array_equal(f['life'], r['life']), f'{what} frame {k}'
+        if len(f['ids']):
+            d = max(np.abs(f['p0'] - r['p0']).max(), np.abs(f['p1'] - r['p1']).max())
+            worst = max(worst, float(d))
+            assert d <= 0.01, f'{what} frame {k}: position off by {d} px'
+            assert np.abs(f['meas'] - r['pub']).max() <= 1e-4, f'{what} frame {k}: published coordinates'
+    return worst
+
+
+@pytest.mark.parametrize('S', [8, 64])
+def test_offset_runs_in_one_context_equal_single_contexts_and_the_port(S):
+    """The C4 shape at C2 geometry (752x480, 6x10 cells x 5): S offset runs of a LOSSY sequence (moving patches, noise,
+    gyro) over 7 frames incl. frame 0.  S = 64 is the one-GPU sweep (per-level pyramid kernel, two candidate rounds,
+    bulk result copy), S = 8 the per-GPU shard of the eight-GPU sweep."""
+    cfg = config_c2()
+    n_steps, stride = 7, 2
+    multi, single, frames, Rs, kernels = _offset_runs(cfg, S, n_steps, stride, LOSSY)
+    for s in range(S):
+        _assert_equal_runs(multi[s], single[s], f'S={S} stream {s}')
+    st = SlidingTextureStream(n_frames=len(frames), **LOSSY)
+    st.frames = lambda: iter(frames)
+    worst = 0.0
+    for s in sorted({0, S // 2, S - 1}):
+        worst = max(worst, _assert_equals_port(multi[s], _port_run(cfg, st, stride * s, n_steps), f'S={S} stream {s}'))
+    lost = sum(f['hdr'][3] - f['hdr'][4] for s in range(S) for f in multi[s][1:])
+    new_ids = sum(multi[s][-1]['hdr'][1] for s in range(S))
+    print(f'S={S}: {S} x {n_steps} frames equal {S} single-stream contexts bit for bit ({kernels} kernels per frame); streams '
+          f'0, {S // 2}, {S - 1} equal the port (worst {worst:.3g} px); {lost} features lost in stereo matching, {new_ids} ids handed out')
+    assert lost > 0
+    if S == 64:
+        assert kernels == 10            # clear, fast, 3 x k_pyr_down, track, select, 2 candidate rounds, finish
+
+
+def test_forced_two_round_candidates_and_bulk_result_copy_on_a_small_context(monkeypatch):
+    """The many-stream choices forced onto ONE stream (AVB_WPF=1, AVB_CAND_ROUNDS=2, AVB_PYR_PAIR=0, AVB_ZC_OUT=0): 30
+    lossy frames against the port.  Round 1 of the candidate matching leaves stale inlier flags behind unmatched tail
+    positions (avb_points.cu); a stream whose cells keep losing and refilling is what would expose them."""
+    for k, v in (('AVB_WPF', '1'), ('AVB_CAND_ROUNDS', '2'), ('AVB_PYR_PAIR', '0'), ('AVB_ZC_OUT', '0')):
+        monkeypatch.setenv(k, v)
+    from image_processing import _native
+    cfg = FrontEndConfig(grid_row=6, grid_col=10, grid_min=2, grid_max=5)
+    n = 30
+    st = SlidingTextureStream(n_frames=n, **LOSSY)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    ctx = _native.Context(cfg, 752, 480, num_streams=1)
+    got = []
+    try:
+        assert ctx.kernels_per_frame() == 2 + 3 + 1 + 1 + 2 + 1
+        for k in range(n):
+            ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
+            got.append(_snapshot(ctx, 0))
+    finally:
+        ctx.close()
+    worst = _assert_equals_port(got, _port_run(cfg, st, 0, n), 'forced many-stream paths')
+    print(f'forced two-round candidates + per-level pyramid + bulk result copy: 30 lossy frames equal the port (worst {worst:.3g} px), '
+          f'{got[-1]["hdr"][1]} ids handed out')
+
+
+@pytest.mark.parametrize('w,h,levels', [(752, 480, 3), (1280, 1024, 4), (1040, 1030, 5)])
+def test_per_level_pyramid_kernel_on_every_level(w, h, levels, monkeypatch):
+    """AVB_PYR_PAIR=0: `k_pyr_down` builds EVERY level (what a many-stream context does), including the two smallest
+    ones that `k_pyr_pair` builds in a small context; AVB_PYR_PAIR=1: the pair kernel.  Both bit-exact against pyrDown."""
+    from image_processing import _native
+    cfg = FrontEndConfig(pyramid_levels=levels, width=w, height=h)
+    g = np.random.default_rng(w * 3 + h)
+    img0 = g.integers(0, 256, (h, w)).astype(np.uint8)
+    img1 = g.integers(0, 256, (h, w)).astype(np.uint8)
+    for pair in ('0', '1'):
+        monkeypatch.setenv('AVB_PYR_PAIR', pair)
+        c = _native.Context(cfg, w, h, use_graph=False)
+        try:
+            c.upload(img0, img1)
+            c.build_pyramids()
+            for slot, img in ((0, img0), (1, img1)):
+                ref = cs.build_pyramid(img, levels)
+                for lvl in range(levels + 1):
+                    assert np.array_equal(c.download_level(slot, lvl), ref[lvl]), (pair, slot, lvl)
+        finally:
+            c.close()

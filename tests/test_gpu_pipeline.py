@@ -7,8 +7,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from oracle.configs import FrontEndConfig, config_c3
-from oracle.driver import run_stream
+from frontend_config import FrontEndConfig, config_c3
+from replay import run_stream
 from oracle.pipeline_port import FrontEndPort
 from synth_euroc import SlidingTextureStream
 from tools.make_golden import CASES

@@ -8,8 +8,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import ransac as rs
-from oracle.configs import FrontEndConfig, config_c3
-from oracle.driver import run_stream
+from frontend_config import FrontEndConfig, config_c3
+from replay import run_stream
 from oracle.pipeline_port import FrontEndPort
 from ransac_cases import D_EUROC, D_EUROC1, K_EUROC, K_EUROC1, make_pixels, undistorted
 from synth_euroc import SlidingTextureStream

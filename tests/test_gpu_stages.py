@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import cv_semantics as cs
-from oracle.configs import FrontEndConfig, config_c2, config_c3, config_default
+from frontend_config import FrontEndConfig, config_c2, config_c3, config_default
 from oracle.pipeline_port import FrontEndPort
 from synth_euroc import SlidingTextureStream
 

@@ -15,7 +15,7 @@ Meas = namedtuple('FeatureMeasurement', ['id', 'u0', 'v0', 'u1', 'v1'])
 
 def _msckf_config():
     """The filter fields of the reference's ConfigEuRoC (/root/reference/src/config.py:7-17, 47-72, 93-122)."""
-    from oracle.configs import FrontEndConfig
+    from frontend_config import FrontEndConfig
 
     class Opt:
         translation_threshold = -1.0

@@ -105,5 +105,10 @@ def test_bind_to_gpu_numa_deals_the_node_cores_to_its_ranks(tmp_path):
         (tmp_path / 'bus' / 'pci' / 'devices' / '0000:fe:00.0' / 'numa_node').write_text('-1\n')
         assert bind_to_gpu_numa('0000:fe:00.0', 0, 1, sysfs=str(tmp_path)) is None      # single-node box
         assert os.sched_getaffinity(0) == full
+        if len(cpus) >= 4:              # unknown topology, several ranks on the box: contiguous, disjoint core slices
+            a = bind_to_gpu_numa('0000:fe:00.0', 0, 2, sysfs=str(tmp_path))
+            os.sched_setaffinity(0, full)
+            b = bind_to_gpu_numa('0000:fe:00.0', 1, 2, sysfs=str(tmp_path))
+            assert a and b and not (a & b) and (a | b) <= full and max(a) < min(b)
     finally:
         os.sched_setaffinity(0, full)

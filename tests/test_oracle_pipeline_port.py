@@ -7,8 +7,8 @@ import pytest
 
 pytest.importorskip('cv2')
 
-from oracle.configs import FrontEndConfig
-from oracle.driver import run_stream
+from frontend_config import FrontEndConfig
+from replay import run_stream
 from oracle.pipeline_port import FrontEndPort
 from synth_euroc import SlidingTextureStream
 from tools.make_golden import CASES

@@ -32,7 +32,7 @@ def test_trajectory_metrics_recover_a_known_rigid_transform():
 def test_room_scene_stream_is_consistent():
     """At rest the IMU reads gravity along +x of the IMU frame and no rotation; frames are deterministic; a static
     point of the scene projects consistently into both cameras (checked through the stereo disparity sign)."""
-    from oracle.configs import config_default
+    from frontend_config import config_default
     from synth_euroc import RoomSceneStream
     st = RoomSceneStream(config_default(), n_frames=3, seed=5, tex_size=512)
     gyro, acc = st.imu_sample(0.5)
@@ -68,7 +68,7 @@ import ate_parity as ap
 sys.path.insert(0, '/root/reference/src')
 from config import ConfigEuRoC
 from image_processing import ImageProcessor
-from oracle.driver import run_stream
+from replay import run_stream
 cfg = ConfigEuRoC(); cfg.grid_row, cfg.grid_col, cfg.grid_num = 6, 10, 60
 z = np.load(%r)
 msgs = run_stream(ImageProcessor(cfg), ap.make_stream(40))

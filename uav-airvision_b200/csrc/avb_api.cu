@@ -253,6 +253,12 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     g.ransac_seed = cfg->ransac_seed;
     g.ransac_iters = (int)ceil(log(1.0 - 0.99) / log(1.0 - 0.7 * 0.7));     // success probability 0.99, inlier ratio 0.7
     g.ransac_thr = cfg->ransac_threshold;
+    // Launch-shape choices that depend on how many streams share a launch; the environment overrides exist so that the
+    // parity tests can force the many-stream shapes (per-level pyramid kernel, two candidate rounds) on a small context.
+    g.pyr_pair_level = avb_pyramid_pair_level(g);
+    if (const char* e = getenv("AVB_PYR_PAIR")) g.pyr_pair_level = atoi(e) ? (g.nlev - 1 >= 2 ? g.nlev - 2 : 0) : 0;
+    g.cand_rounds = avb_candidate_rounds(g);
+    if (const char* e = getenv("AVB_CAND_ROUNDS")) g.cand_rounds = (atoi(e) == 2 && g.wpf == 1 && g.gmin < g.gmax) ? 2 : 1;
     if (g.NMAX > 8192) {
         delete c;
         return fail(nullptr, AVB_E_INVALID, "grid_num*grid_max = %d exceeds 8192", g.NMAX);
@@ -512,7 +518,7 @@ extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
     // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
     // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish
-    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (avb_candidate_rounds(c->g) == 2 ? 1 : 0);
+    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (c->g.cand_rounds == 2 ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {

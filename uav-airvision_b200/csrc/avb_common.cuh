@@ -47,6 +47,8 @@ struct Geom {
     int NMAX;                      // NC * gmax
     int KPC;                       // FAST bucket capacity of one cell
     int wpf;                       // warps per feature in the LK kernels: 4 = latency mapping, 1 = throughput mapping
+    int pyr_pair_level;            // k_pyr_pair builds levels pyr_pair_level and +1 in one launch (0: one k_pyr_down per level)
+    int cand_rounds;               // new-feature stereo matching in 1 launch or 2 dense rounds (avb_points.cu)
     int fast_thr;
     int max_iter;
     double min_eig;
@@ -215,7 +217,8 @@ void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, co
                           cudaStream_t st);
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
-int  avb_candidate_rounds(const Geom& g);    // 1: every candidate in one launch; 2: positions < gmin first, the rest on demand
+int  avb_candidate_rounds(const Geom& g);    // default for Geom::cand_rounds. 1: every candidate in one launch; 2: positions < gmin first, the rest on demand
+int  avb_pyramid_pair_level(const Geom& g);  // default for Geom::pyr_pair_level
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st);

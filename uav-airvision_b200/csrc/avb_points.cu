@@ -197,7 +197,7 @@ int avb_candidate_rounds(const Geom& g) {
 
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
-    if (avb_candidate_rounds(g) == 2) {
+    if (g.cand_rounds == 2) {
         launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * g.gmin, 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0,
                  g, d, parity, 0);
         launch_k(k_stereo_candidates<1>, dim3(teams_grid(g.NC * (g.gmax - g.gmin), 1), g.S), dim3(32 * WARPS_PER_BLOCK), 0, st,

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_pyr_pair(const __grid_constant__ CUtens
 // The pair kernel trades redundant halo work for one launch less: right for a few streams (launch-latency bound), wrong
 // when the one-level kernel already fills the GPU at the pair's first level (many streams: it ran at 6 % of the HBM
 // rate there).
-static int pyramid_pair_level(const Geom& g) {
+int avb_pyramid_pair_level(const Geom& g) {
     const int built = g.nlev - 1;                       // levels 1..built
     if (built < 2) return 0;
     const int l = built - 1;
@@ -247,7 +247,7 @@ static int pyramid_pair_level(const Geom& g) {
 
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st) {
     const int built = g.nlev - 1;                       // levels 1..built
-    const int pair_at = pyramid_pair_level(g);          // the pair kernel builds levels pair_at and pair_at + 1 (0: not used)
+    const int pair_at = g.pyr_pair_level;               // the pair kernel builds levels pair_at and pair_at + 1 (0: not used)
     for (int l = 1; l <= built; ++l) {
         if (l == pair_at) {
             dim3 grid((g.lv[l + 1].w + QT_W - 1) / QT_W, (g.lv[l + 1].h + QT_H - 1) / QT_H, 2 * g.S);
@@ -261,5 +261,5 @@ void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int p
 
 int avb_pyramid_launches(const Geom& g) {
     const int built = g.nlev - 1;
-    return pyramid_pair_level(g) ? built - 1 : built;
+    return g.pyr_pair_level ? built - 1 : built;
 }

@@ -1,6 +1,6 @@
 """Config objects shaped like the reference's ConfigEuRoC (/root/reference/src/config.py:19-123) for the BASELINE
 configurations C1/C2/C3.  Only the front-end fields are carried; values are the EuRoC
-calibration.  Plain data: used by bench.py, the tools and (through oracle/configs.py) the tests."""
+calibration.  Plain data: used by bench.py, the tools and the tests."""
 from __future__ import annotations
 
 import numpy as np

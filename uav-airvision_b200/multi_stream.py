@@ -45,17 +45,27 @@ def bind_to_gpu_numa(pci_bus_id: str, local_rank: int = 0, local_world: int = 1,
     result blocks) on the host cores of the NUMA node the GPU hangs off, so the per-frame H2D copy and the result
     block the last kernel writes into mapped host memory do not cross the socket interconnect.  Call it BEFORE the
     context is created.  `pci_bus_id` is 'dddd:bb:dd.f' (cudaDeviceGetPCIBusId).  The node's allowed cores are dealt
-    to the ranks that share the node in contiguous slices.  Returns the cpu set bound to, or None when the topology
-    is unknown (no sysfs entry, node -1, no allowed core on the node): the affinity is then left untouched."""
+    to the ranks that share the node in contiguous slices.  When the topology is unknown (no sysfs entry, node -1 as on
+    single-node or virtualised boxes, no allowed core on the node) and several ranks share the box, the allowed cores
+    are dealt to the local ranks in contiguous slices instead, so that the ranks at least do not migrate over each
+    other; a single rank is left untouched.  Returns the cpu set bound to, or None when the affinity was not changed."""
+    def core_slice():
+        allowed = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(allowed) < local_world:
+            return None
+        share = len(allowed) // local_world
+        mine = allowed[local_rank * share:(local_rank + 1) * share]
+        os.sched_setaffinity(0, mine)
+        return set(mine)
     try:
         dev = os.path.join(sysfs, 'bus', 'pci', 'devices', pci_bus_id.lower())
         node = int(open(os.path.join(dev, 'numa_node')).read())
         if node < 0:
-            return None
+            return core_slice()
         cpus = _parse_cpulist(open(os.path.join(sysfs, 'devices', 'system', 'node', f'node{node}', 'cpulist')).read())
         allowed = sorted(cpus & os.sched_getaffinity(0))
         if not allowed:
-            return None
+            return core_slice()
         # ranks sharing this node: assume GPUs are spread evenly over the nodes that have any
         nodes = set()
         for d in os.listdir(os.path.join(sysfs, 'bus', 'pci', 'devices')):
@@ -73,7 +83,7 @@ def bind_to_gpu_numa(pci_bus_id: str, local_rank: int = 0, local_world: int = 1,
         os.sched_setaffinity(0, mine)
         return set(mine)
     except (OSError, ValueError):
-        return None
+        return core_slice()
 
 
 class MultiStreamFrontEnd:
