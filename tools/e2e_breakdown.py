@@ -6,13 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'uav-airvision_b200')):
     sys.path.insert(0, p)
 import torch
-from bench import make_sequence, workload
+from bench import workload
+from synth_euroc import SlidingTextureStream
 from image_processing import ImageProcessor, _avbhost, FeatureMeasurement
 from synth_euroc import img_msg, stereo_msg
 
 cfg, skw, _ = workload('c2')
 n = 260
-stream = make_sequence(skw, n)
+stream = SlidingTextureStream(n_frames=n, **skw)
 pin = torch.empty((n, 2, stream.h, stream.w), dtype=torch.uint8).pin_memory().numpy()
 evs = []
 k = 0

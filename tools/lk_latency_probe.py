@@ -15,14 +15,15 @@ sys.dont_write_bytecode = True
 
 def run(max_iter, levels, wpf, n=14):
     import torch
-    from bench import make_sequence, rotations_for, workload
+    from bench import rotations_for, workload
+    from synth_euroc import SlidingTextureStream
     from image_processing import _native
     cfg, skw, _ = workload('c2')
     cfg.max_iteration = max_iter
     cfg.pyramid_levels = levels
     cfg.lk_params = dict(cfg.lk_params, maxLevel=levels, criteria=(3, max_iter, 0.01))
     os.environ['AVB_WPF'] = str(wpf)
-    stream = make_sequence(skw, n)
+    stream = SlidingTextureStream(n_frames=n, **skw)
     frames = [stream.frame(k) for k in range(n)]
     stream.frames = lambda: iter(frames)
     Rs = rotations_for(cfg, stream)

@@ -22,12 +22,13 @@ def main():
     ap.add_argument('--workload', default='c2')
     a = ap.parse_args()
     import torch
-    from bench import make_sequence, rotations_for, workload
+    from bench import rotations_for, workload
     from image_processing import _native
+    from synth_euroc import SlidingTextureStream
     cfg, skw, _ = workload(a.workload)
     S, F = a.streams, a.frames
     n = F + 2 * (S - 1)
-    stream = make_sequence(skw, n)
+    stream = SlidingTextureStream(n_frames=n, **skw)
     frames = [stream.frame(k) for k in range(n)]
     stream.frames = lambda: iter(frames)
     Rs = rotations_for(cfg, stream)
