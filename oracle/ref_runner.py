@@ -152,6 +152,35 @@ class _SyncQueue:
                 raise RuntimeError('consumer thread did not drain its queue')
 
 
+def _render_range(job):
+    """Pool worker: frames lo .. hi-1 of the rendered room sequence (tools/ate_parity.make_stream) as uint8 arrays."""
+    n, lo, hi = job
+    for p_ in (PKG, ROOT, os.path.join(ROOT, 'tools')):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    from ate_parity import make_stream
+    st = make_stream(n)
+    return lo, [(f.cam0_image, f.cam1_image) for f in (st.frame(k) for k in range(lo, hi))]
+
+
+def _prerender(stream, n, procs):
+    """Renders the n frames of `stream` on `procs` processes (a frame takes ~0.17 s on one core) and makes
+    stream.frames() replay them."""
+    import multiprocessing as mp
+    from synth_euroc import img_msg, stereo_msg
+    procs = max(1, min(procs, n))
+    step = -(-n // procs)
+    with mp.get_context('spawn').Pool(procs) as pool:
+        parts = pool.map(_render_range, [(n, lo, min(lo + step, n)) for lo in range(0, n, step)])
+    imgs = [im for _, chunk in sorted(parts, key=lambda t: t[0]) for im in chunk]
+
+    def frames():
+        for k, (i0, i1) in enumerate(imgs):
+            ts = stream.t0 + k / stream.rate
+            yield stereo_msg(ts, i0, i1, img_msg(ts, i0), img_msg(ts, i1))
+    stream.frames = frames
+
+
 def vio(a):
     """modules/vio.VIO unchanged, its MSCKF unchanged; `image_processing` = the package under test."""
     import contextlib
@@ -180,6 +209,8 @@ def vio(a):
     cfg.grid_num = cfg.grid_row * cfg.grid_col
     cfg.grid_min_feature_num, cfg.grid_max_feature_num = GRID['grid_min'], GRID['grid_max']
     stream = make_stream(a.frames)
+    if a.render_procs > 1:
+        _prerender(stream, a.frames, a.render_procs)
     os.environ['DATASET_NAME'], os.environ['TIME_OFFSET'] = 'live_vio_' + a.front_end, '0'
     work = tempfile.mkdtemp(prefix='vio_')
     cwd = os.getcwd()
@@ -218,7 +249,7 @@ def vio(a):
                 th.join(timeout=30)
     finally:
         os.chdir(cwd)
-    out = dict(front_end=a.front_end, frames=len(feats), poses=len(rows), wall_s=wall, traj=rows,
+    out = dict(front_end=a.front_end, frames=len(feats), poses=len(rows), wall_s=wall, traj=[] if a.no_traj else rows,
                image_processing=os.path.relpath(image_processing.__file__, ROOT), msckf=os.path.relpath(msckf.__file__, ROOT))
     if a.dump:
         np.savez_compressed(a.dump, traj=np.array(rows), n_frames=np.array([len(feats)]),
@@ -241,5 +272,7 @@ if __name__ == '__main__':
     v_.add_argument('--frames', type=int, default=64)
     v_.add_argument('--front-end', default='b200', choices=['b200', 'ref'])
     v_.add_argument('--dump', default=None)
+    v_.add_argument('--render-procs', type=int, default=1, help='render the sequence ahead on this many processes')
+    v_.add_argument('--no-traj', action='store_true', help='leave the trajectory rows out of the JSON line (use --dump)')
     a = ap.parse_args()
     (bench if a.cmd == 'bench' else vio)(a)

@@ -149,9 +149,58 @@ def compare(args):
     return out
 
 
+def live(args):
+    """Both front ends LIVE on this box (needs oracle/_ref and a GPU): the reference's thread harness modules/vio.py with
+    the reference's MSCKF, once over the reference's own image_processing and once over this repo's CUDA package, on the
+    same rendered sequence (>= 60 s for the BASELINE gate); ATE of both against the rendered ground truth."""
+    import subprocess
+    from metrics import trajectory_metrics
+    n = args.frames
+    gt = list(make_stream(n).groundtruth())
+    t_gt, p_gt = np.array([g.timestamp for g in gt]), np.array([g.p for g in gt])
+    runner = os.path.join(ROOT, 'oracle', 'ref_runner.py')
+    res = {}
+    for fe in ('ref', 'b200'):
+        dump = os.path.join(tempfile.mkdtemp(prefix='ate_live_'), fe + '.npz')
+        r = subprocess.run([sys.executable, runner, 'vio', '--frames', str(n), '--front-end', fe, '--dump', dump,
+                            '--render-procs', str(args.render_procs), '--no-traj'], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SystemExit(f'{fe}: {r.stderr[-2000:]}')
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        z = np.load(dump)
+        traj = z['traj']
+        res[fe] = dict(info=info, z=z, metrics=trajectory_metrics(traj[:, 1], traj[:, 2:5], t_gt, p_gt), traj=traj)
+    a, b = res['ref'], res['b200']
+    same_ids, worst = 0, 0.0
+    for k in range(n):
+        if np.array_equal(a['z'][f'f{k}_ids'], b['z'][f'f{k}_ids']):
+            same_ids += 1
+            if len(a['z'][f'f{k}_ids']):
+                worst = max(worst, float(np.abs(a['z'][f'f{k}_meas'] - b['z'][f'f{k}_meas']).max()))
+    rel = abs(b['metrics']['ate_rmse_m'] - a['metrics']['ate_rmse_m']) / a['metrics']['ate_rmse_m']
+    same_shape = a['traj'].shape == b['traj'].shape
+    out = {'sequence': dict(SEQ, frames=n, seconds=n / SEQ['rate'], kind='RoomSceneStream 752x480, C2 grid 6x10 x max 5'),
+           'harness': 'oracle/_ref modules/vio.py (three threads, two queues) + oracle/_ref msckf.py for both front ends, live on one box',
+           'reference_front_end': a['metrics'], 'b200_front_end': b['metrics'], 'ate_rmse_relative_difference': rel,
+           'max_position_difference_between_trajectories_m': float(np.abs(a['traj'][:, 2:5] - b['traj'][:, 2:5]).max()) if same_shape else None,
+           'frames_with_identical_feature_ids': same_ids, 'frames': n,
+           'worst_normalized_coordinate_difference_on_those_frames': worst,
+           'wall_s': {'reference_front_end': a['info']['wall_s'], 'b200_front_end': b['info']['wall_s']},
+           'gate': 'ATE within 1 % of the reference (BASELINE.json north_star)', 'pass': bool(rel <= 0.01)}
+    print(json.dumps(out, indent=1))
+    if args.out:
+        with open(args.out, 'w') as f:
+            json.dump(out, f, indent=1)
+    return out
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest='cmd', required=True)
+    lv = sub.add_parser('live')
+    lv.add_argument('--frames', type=int, default=1200)
+    lv.add_argument('--render-procs', type=int, default=os.cpu_count() or 1)
+    lv.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'ate_parity_live.json'))
     d = sub.add_parser('dump')
     d.add_argument('--frames', type=int, default=400)
     d.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'ate_gpu_features.npz'))
@@ -159,4 +208,4 @@ if __name__ == '__main__':
     c.add_argument('--features', default=os.path.join(ROOT, 'tests', 'golden', 'ate_gpu_features.npz'))
     c.add_argument('--out', default=os.path.join(ROOT, 'profiles', 'ate_parity.json'))
     a = ap.parse_args()
-    (dump if a.cmd == 'dump' else compare)(a)
+    {'dump': dump, 'compare': compare, 'live': live}[a.cmd](a)

@@ -11,21 +11,27 @@ from collections import OrderedDict, defaultdict
 
 KEY_METRICS = [
     ('gpu__time_duration.sum', 'dur'),
-    ('dram__bytes_read.sum', 'dram_rd'),
-    ('dram__bytes_write.sum', 'dram_wr'),
-    ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct'),
-    ('lts__t_bytes.sum', 'l2_bytes'),
-    ('lts__t_sector_hit_rate.pct', 'l2_hit_pct'),
-    ('l1tex__t_sector_hit_rate.pct', 'l1_hit_pct'),
-    ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct'),
-    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ_pct'),
     ('smsp__inst_executed.sum', 'inst'),
+    ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue_pct'),
+    ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct'),
     ('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'alu_pct'),
-    ('smsp__issue_active.avg.pct', 'issue_pct'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ_pct'),
     ('launch__registers_per_thread', 'regs'),
     ('launch__occupancy_limit_registers', 'occ_lim_regs'),
-    ('smsp__cycles_active.avg', 'cycles'),
+    ('dram__bytes_read.sum', 'dram_rd'),
+    ('dram__bytes_write.sum', 'dram_wr'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct'),
+    ('lts__t_sectors.sum', 'l2_sectors'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2_pct'),
+    ('lts__t_sector_hit_rate.pct', 'l2_hit_pct'),
+    ('l1tex__t_sector_hit_rate.pct', 'l1_hit_pct'),
+    ('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1_pipe_pct'),
 ]
+STALLS = ['barrier', 'branch_resolving', 'dispatch_stall', 'drain', 'lg_throttle', 'long_scoreboard', 'math_pipe_throttle',
+          'membar', 'mio_throttle', 'misc', 'no_instruction', 'not_selected', 'selected', 'short_scoreboard', 'sleeping',
+          'tex_throttle', 'wait']
+UNIT_SCALE = {'byte': 1.0, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9, 'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0,
+              'nsecond': 1e-9, 'usecond': 1e-6, 'msecond': 1e-3, 'second': 1.0, 'sector': 1.0}
 
 
 def short(name):
@@ -51,6 +57,9 @@ def launches(path):
 
 
 def raw(path):
+    """Per kernel (averaged over its launches in the capture): the key metrics of a `--set full` export, the derived
+    DRAM and L2 GB/s (bytes moved / kernel duration; L2 = lts__t_sectors x 32 B) and the three largest warp-stall reasons
+    (warps stalled per issue-active cycle)."""
     with open(path, newline='') as f:
         rd = csv.reader(f)
         hdr = next(rd)
@@ -62,26 +71,34 @@ def raw(path):
                 continue
             name = short(r[col['Kernel Name']]) + ' grid ' + r[col['Grid Size']].replace(' ', '')
             seen.setdefault(name, []).append(r)
-    names = [n for _, n in KEY_METRICS]
+
+    def val(rs, m, scaled=False):
+        if m not in col:
+            return None
+        vals = []
+        for r in rs:
+            try:
+                v = float(r[col[m]].replace(',', ''))
+            except ValueError:
+                continue
+            vals.append(v * (UNIT_SCALE.get(units[col[m]].lower(), 1.0) if scaled else 1.0))
+        return sum(vals) / len(vals) if vals else None
+
+    names = [n for _, n in KEY_METRICS] + ['dram_GBs', 'l2_GBs', 'top stalls (warps / issue-active cycle)']
     print('| kernel (grid) | n | ' + ' | '.join(names) + ' |\n|---|---|' + '---|' * len(names))
     for k, rs in seen.items():
         cells = []
         for m, _ in KEY_METRICS:
-            if m not in col:
-                cells.append('-')
-                continue
-            vals = []
-            for r in rs:
-                try:
-                    vals.append(float(r[col[m]].replace(',', '')))
-                except ValueError:
-                    pass
-            if not vals:
-                cells.append('-')
-                continue
-            v = sum(vals) / len(vals)
-            u = units[col[m]]
-            cells.append(f'{v:.4g} {u}'.strip())
+            v = val(rs, m)
+            cells.append('-' if v is None else f'{v:.4g} {units[col[m]]}'.strip())
+        dur = val(rs, 'gpu__time_duration.sum', True)
+        rdb, wrb = val(rs, 'dram__bytes_read.sum', True), val(rs, 'dram__bytes_write.sum', True)
+        sect = val(rs, 'lts__t_sectors.sum', True)
+        cells.append('-' if not dur or rdb is None else f'{(rdb + wrb) / dur / 1e9:.1f}')
+        cells.append('-' if not dur or sect is None else f'{sect * 32 / dur / 1e9:.1f}')
+        st = [(val(rs, f'smsp__average_warps_issue_stalled_{n}_per_issue_active.ratio') or 0.0, n) for n in STALLS]
+        st = sorted((x for x in st if x[1] != 'selected'), reverse=True)[:3]
+        cells.append(', '.join(f'{n} {v:.2f}' for v, n in st))
         print(f'| {k} | {len(rs)} | ' + ' | '.join(cells) + ' |')
 
 

@@ -16,7 +16,7 @@ import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'lib', 'libavb.so')
+LIB = os.environ.get('AVB_LIB_OUT') or os.path.join(HERE, 'lib', 'libavb.so')      # AVB_LIB_OUT: variant builds (tools/c4_quick.py --lib)
 HOST_EXT = os.path.join(HERE, 'image_processing', '_avbhost' + sysconfig.get_config_var('EXT_SUFFIX'))
 MSCKF_EXT = os.path.join(HERE, '_msckfhost' + sysconfig.get_config_var('EXT_SUFFIX'))
 SOURCES = ['avb_api.cu', 'avb_pyramid.cu', 'avb_fast.cu', 'avb_points.cu', 'avb_grid.cu', 'avb_ransac.cu', 'avb_store.cu']

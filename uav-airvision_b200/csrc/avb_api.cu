@@ -242,6 +242,8 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     g.eps2 = eps * eps;
     g.eps2_lo = (float)(g.eps2 * 0.99999);      // formed here: in the kernels the compiler re-did this FP64 product every iteration
     g.eps2_hi = (float)(g.eps2 * 1.00001);
+    // a threshold <= 0 never takes the shortcut (the float minEig can round below zero)
+    g.eig_accept = g.min_eig > 0.0 ? (float)(2.0 * AVB_WIN * AVB_WIN * (2.0 * g.min_eig + 4e-5)) : INFINITY;
     g.cam0 = {cfg->cam0_intrinsics[0], cfg->cam0_intrinsics[1], cfg->cam0_intrinsics[2], cfg->cam0_intrinsics[3],
               cfg->cam0_distortion[0], cfg->cam0_distortion[1], cfg->cam0_distortion[2], cfg->cam0_distortion[3]};
     g.cam1 = {cfg->cam1_intrinsics[0], cfg->cam1_intrinsics[1], cfg->cam1_intrinsics[2], cfg->cam1_intrinsics[3],
@@ -362,14 +364,24 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     {
         const int built = g.nlev - 1, pair_at = built >= 2 ? built - 1 : 0;
         int r = AVB_OK;
-        for (int p = 0; p < 2 && r == AVB_OK; ++p) {
-            r = make_map(c, enc, &c->maps.l0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 160, 36);
-            if (r == AVB_OK) r = make_map(c, enc, &c->maps.pair0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 44);
-            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 40);
+        int fbw = 0, fbh = 0;
+        avb_fast_box(&fbw, &fbh);
+        for (int v = 0; v < 2 && r == AVB_OK; ++v) {              // k_pyr_down: 16-row and 32-row tiles
+            int pbw = 0, pbh = 0, ptw = 0, pth = 0;
+            avb_pyramid_boxes(v, &pbw, &pbh, &ptw, &pth);
+            for (int p = 0; p < 2 && r == AVB_OK; ++p)
+                r = make_map(c, enc, &c->maps.l0[p][v], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, pbw, pbh);
+            for (int l = 1; l < g.nlev - 1 && r == AVB_OK; ++l)
+                r = make_map(c, enc, &c->maps.lv[l][v], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM,
+                             g.lv[l].pitch, g.slot_bytes, pbw, pbh);
+            for (int l = 1; l < g.nlev && r == AVB_OK; ++l)      // store views: clipped at the level's width and height
+                r = make_map(c, enc, &c->maps.dst[l][v], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM,
+                             g.lv[l].pitch, g.slot_bytes, ptw, pth);
         }
-        for (int l = 1; l < g.nlev - 1 && r == AVB_OK; ++l)
-            r = make_map(c, enc, &c->maps.lv[l], d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,
-                         g.slot_bytes, 160, 36);
+        for (int p = 0; p < 2 && r == AVB_OK; ++p) {
+            r = make_map(c, enc, &c->maps.pair0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 44);
+            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, fbw, fbh);
+        }
         if (pair_at >= 2 && r == AVB_OK) {
             const int l = pair_at - 1;
             r = make_map(c, enc, &c->maps.pair, d.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, g.S * SLOTS_PER_STREAM, g.lv[l].pitch,

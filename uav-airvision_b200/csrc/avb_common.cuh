@@ -54,6 +54,7 @@ struct Geom {
     double min_eig;
     double eps2;                   // (track_precision)^2 in double, like criteria.epsilon
     float eps2_lo, eps2_hi;        // (float)(eps2 * (1 -+ 1e-5)): band outside which the float estimate of |delta|^2 decides
+    float eig_accept;              // 450 * (2 min_eig + 4e-5): D > eig_accept * (A11 + A22) proves minEig >= threshold (avb_lk.cuh)
     CamModel cam0, cam1;
     double R01[9];                 // R_cam0_to_cam1
     double E[9];                   // essential
@@ -157,6 +158,19 @@ __device__ __forceinline__ int refl101(int i, int n) {
     return i >= n ? 2 * n - 2 - i : i;
 }
 
+// floor(t / d) by a host-made reciprocal (magic = ceil(2^32 / d), exact while t * d < 2^32; 0 = divide): tile and cell
+// decompositions run once per tile and per keypoint in every thread, and an emulated integer division is ~20 instructions
+struct FastDiv {
+    unsigned d, magic;
+};
+__device__ __forceinline__ int fdiv(int t, const FastDiv& f) { return f.magic ? (int)__umulhi((unsigned)t, f.magic) : t / (int)f.d; }
+inline FastDiv make_fdiv(int d, long long max_t) {
+    FastDiv f;
+    f.d = (unsigned)d;
+    f.magic = (d > 1 && max_t * d < (1ll << 32)) ? (unsigned)(((1ull << 32) + d - 1) / d) : 0u;
+    return f;
+}
+
 // FAST keypoint key: larger key = earlier in the reference's ranking
 // (response desc, then row-major scan order; stable sorted(..., reverse=True), Appendix B9).
 __host__ __device__ inline unsigned kp_make_key(int resp, int x, int y, int W) {
@@ -200,8 +214,10 @@ extern int g_avb_pdl;              // 1: chain kernels are launched with the pro
 // TMA views (x, y, image).  Level 0: one map per parity over the input block, image = s*2 + cam.
 // Levels >= 1: one map per level over the arena, image = s*4 + slot.  `fast0` has the FAST box shape.
 struct PyrMaps {
-    CUtensorMap l0[2];              // source level 0, box of k_pyr_down
-    CUtensorMap lv[AVB_MAX_LEVELS]; // source level l >= 1, box of k_pyr_down
+    // k_pyr_down, per tile-height variant (0: 16 rows, 1: 32 rows)
+    CUtensorMap l0[2][2];           // [parity][variant] source level 0
+    CUtensorMap lv[AVB_MAX_LEVELS][2];  // source level l >= 1
+    CUtensorMap dst[AVB_MAX_LEVELS][2]; // destination level l >= 1 (store box 64 x rows)
     CUtensorMap pair0[2];           // source level 0, box of k_pyr_pair (used when the pair kernel builds levels 1+2)
     CUtensorMap pair;               // source level nlev-3 >= 1, box of k_pyr_pair
     CUtensorMap fast0[2];
@@ -209,7 +225,9 @@ struct PyrMaps {
 
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
 int  avb_pyramid_launches(const Geom& g);
+void avb_pyramid_boxes(int variant, int* src_w, int* src_h, int* dst_w, int* dst_h);
 void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
+void avb_fast_box(int* w, int* h);
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_ransac(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, const float2* prev, const float2* cur, int n,

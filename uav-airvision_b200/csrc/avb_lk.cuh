@@ -21,6 +21,8 @@
 // In both, row r+1 arrives by shuffle from lane + LPR, so every pixel of image B is fetched once per iteration.
 #pragma once
 
+#include <limits.h>
+
 #include "avb_common.cuh"
 
 #define LK_W_BITS 14
@@ -59,7 +61,8 @@ __device__ __forceinline__ LKStatic lk_static() {
 
 struct LKShared;
 
-// Exact warp sums of N per-lane int32 partials (|v| < 2^31) as int64: split 16/16 warp REDUX.
+// Exact warp sums of N per-lane int32 partials (|v| < 2^31) as int64: split 16/16 warp REDUX.  This is the general path;
+// almost every level takes the one-REDUX path below (see lk_track_warp).
 template <int WPF, int N>
 __device__ __forceinline__ void team_sum_exact(const int (&v)[N], long long (&out)[N], LKShared*, int&) {
     static_assert(WPF == 1, "the 4-warp mapping reduces inline");
@@ -70,6 +73,13 @@ __device__ __forceinline__ void team_sum_exact(const int (&v)[N], long long (&ou
         out[i] = (long long)hi * 65536ll + (long long)lo;
     }
 }
+
+// Largest structure-tensor diagonal sum (integer, before the 2^-20 scale) for which the residual sums b1, b2 of a level
+// are guaranteed to fit in int32, so that ONE 32-bit REDUX per sum is exact (two's-complement wrap-around cancels as long
+// as the true total fits):  |b| = |sum d_k g_k| <= sqrt(sum d_k^2) sqrt(sum g_k^2) <= sqrt(225) * 8160 * sqrt(q)  with
+// |d_k| <= 8160 (template and sample are both (bilinear + 2^8) >> 9 of bytes), q = sum g_k^2 = q11 or q22;
+// 122400 * sqrt(3.0e8) = 2.12e9 < 2^31.  Measured on the bench texture: max q = 6.6e7 (every level narrow).
+#define LK_NARROW_MAX 300000000u
 
 // 2-way dot product of two SIGNED 16-bit values (operand a) with two UNSIGNED bytes (lower / upper half of b) plus c.
 // The fourth bilinear weight is 2^14 minus the other three rounded weights and can come out as -1, hence signed.
@@ -113,6 +123,7 @@ struct LKParams {
     double min_eig;                 // compared in double, as cv2 does (float minEig vs double threshold)
     double eps2;
     float eps2_lo, eps2_hi;         // float band around eps2 outside which the float estimate decides (lk_converged)
+    float eig_accept;               // D > eig_accept * (A11 + A22) proves minEig >= threshold without the sqrt / division
 };
 
 
@@ -221,18 +232,30 @@ __device__ __forceinline__ void lk_template(const uint8_t* __restrict__ img, int
 }
 
 // Structure tensor -> (A11, A12, A22, 1/D); false when cv2 rejects the level (minEig / determinant test).
-__device__ __forceinline__ bool lk_tensor(long long q11, long long q12, long long q22, double min_eig_thr, float& A11,
-                                          float& A12, float& A22, float& Dinv) {
+//   minEig = (A22 + A11 - sqrt((A11 - A22)^2 + 4 A12^2)) / (2 * 15 * 15) = lambda_min / 225, compared with the threshold
+// in double.  lambda_min = D / lambda_max >= D / (A11 + A22), so D > 450 * (2 thr + 4e-5) * (A11 + A22) puts the exact
+// value above twice the threshold; the float rounding of D (<= 6e-8 s^2, s = A11 + A22 <= 7056) and of the minEig
+// formula (<= 5.3e-10 s) cannot bring it back below it.  Only borderline levels evaluate the IEEE sqrt and division.
+__device__ __forceinline__ bool lk_tensor_f(float A11, float A12, float A22, double min_eig_thr, float eig_accept,
+                                            float& Dinv) {
+    const float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    if (D < 1.1920929e-07f) return false;
+    const float s = __fadd_rn(A22, A11);
+    if (!(D > __fmul_rn(eig_accept, s))) {
+        const float dif = __fsub_rn(A11, A22);
+        const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float min_eig = __fdiv_rn(__fsub_rn(s, __fsqrt_rn(rad)), (float)(2 * AVB_WIN * AVB_WIN));
+        if ((double)min_eig < min_eig_thr) return false;
+    }
+    Dinv = __fdiv_rn(1.f, D);
+    return true;
+}
+__device__ __forceinline__ bool lk_tensor(long long q11, long long q12, long long q22, double min_eig_thr, float eig_accept,
+                                          float& A11, float& A12, float& A22, float& Dinv) {
     A11 = __fmul_rn(__ll2float_rn(q11), 9.5367431640625e-07f);
     A12 = __fmul_rn(__ll2float_rn(q12), 9.5367431640625e-07f);
     A22 = __fmul_rn(__ll2float_rn(q22), 9.5367431640625e-07f);
-    const float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-    const float dif = __fsub_rn(A11, A22);
-    const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
-    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * AVB_WIN * AVB_WIN));
-    if ((double)min_eig < min_eig_thr || D < 1.1920929e-07f) return false;
-    Dinv = __fdiv_rn(1.f, D);
-    return true;
+    return lk_tensor_f(A11, A12, A22, min_eig_thr, eig_accept, Dinv);
 }
 
 // cv2's two loop exits, bit for bit, without the double-precision round trip on the common path:
@@ -287,31 +310,55 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
         int sA[3];
         lk_template<NPX, LPR>(pyr_level(A, g, level), cols, rows, pitch, ipx, ipy, w00, w01, w10, w11, L, tI, tIx, tIy, sA[0],
                               sA[1], sA[2]);
-        long long qA[3];
-        team_sum_exact<1, 3>(sA, qA, nullptr, flip);
-        float A11, A12, A22, D;
-        if (!lk_tensor(qA[0], qA[1], qA[2], prm.min_eig, A11, A12, A22, D)) {
+        // Exact sums of the structure tensor.  q11, q22 <= 225 * 4080^2 < 2^32: one unsigned REDUX each (a lane's partial
+        // is < 2^28).  |q12| <= sqrt(q11 q22), so one signed REDUX is exact whenever both diagonals are below 2^31.
+        const unsigned q11 = __reduce_add_sync(0xffffffffu, (unsigned)sA[0]);
+        const unsigned q22 = __reduce_add_sync(0xffffffffu, (unsigned)sA[2]);
+        float A12;
+        if ((q11 | q22) < 0x80000000u) {
+            A12 = __fmul_rn(__int2float_rn(__reduce_add_sync(0xffffffffu, sA[1])), 9.5367431640625e-07f);
+        } else {
+            const int one[1] = {sA[1]};
+            long long q12[1];
+            team_sum_exact<1, 1>(one, q12, nullptr, flip);
+            A12 = __fmul_rn(__ll2float_rn(q12[0]), 9.5367431640625e-07f);
+        }
+        const float A11 = __fmul_rn(__uint2float_rn(q11), 9.5367431640625e-07f);
+        const float A22 = __fmul_rn(__uint2float_rn(q22), 9.5367431640625e-07f);
+        float D;
+        if (!lk_tensor_f(A11, A12, A22, prm.min_eig, prm.eig_accept, D)) {
             if (level == 0) status = false;
             continue;
         }
+        const bool narrow = q11 <= LK_NARROW_MAX && q22 <= LK_NARROW_MAX;     // b1, b2 fit in int32 (see LK_NARROW_MAX)
 
         // ---- iterations on image B ------------------------------------------------------------------
         float cx = __fsub_rn(nx, (float)AVB_HALF), cy = __fsub_rn(ny, (float)AVB_HALF);
         float pdx = 0.f, pdy = 0.f;
         const uint8_t* imgB = pyr_level(B, g, level);
+        // window tests as single unsigned compares: in range <=> -WIN <= inx < cols; footprint (16 rows x 17 columns)
+        // inside the level <=> 0 <= inx <= cols - 17, 0 <= iny <= rows - 16
+        const unsigned x_rng = (unsigned)(cols + AVB_WIN), y_rng = (unsigned)(rows + AVB_WIN);
+        const unsigned x_in = (unsigned)max(cols - 16, 0), y_in = (unsigned)max(rows - 15, 0);
+        const uint8_t* lane_base = imgB + L.row * pitch + L.c0;      // this lane's first sample for a window at (0, 0)
+        // this lane's 9 bytes of row (iny + row) from column inx + c0, packed: P0 = b0..b3, P1 = b4..b7, P2 = b8; N = the
+        // row below (from lane + 2).  Kept across iterations: sub-pixel updates leave the integer window position where
+        // it was on most iterations after the first, and the samples are then still the right ones.
+        unsigned P0 = 0, P1 = 0, P2 = 0, N0 = 0, N1 = 0, N2 = 0;
+        int pinx = INT_MIN, piny = INT_MIN;
         for (int j = 0; j < prm.max_iter; ++j) {
             const int inx = __float2int_rd(cx), iny = __float2int_rd(cy);
-            if (inx < -AVB_WIN || inx >= cols || iny < -AVB_WIN || iny >= rows) {
+            if ((unsigned)(inx + AVB_WIN) >= x_rng || (unsigned)(iny + AVB_WIN) >= y_rng) {
                 if (level == 0) status = false;
                 break;
             }
             lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
-            // this lane's 9 bytes of row (iny + row) from column inx + c0, packed: P0 = b0..b3, P1 = b4..b7, P2 = b8
-            unsigned P0, P1, P2;
-            if (inx >= 0 && inx + 17 <= cols && iny >= 0 && iny + 16 <= rows) {   // warp-uniform: footprint inside the level
+            if (inx == pinx && iny == piny) {                        // warp-uniform
+            } else {
+            if ((unsigned)inx < x_in && (unsigned)iny < y_in) {      // warp-uniform: footprint inside the level
                 // three aligned 32-bit loads + funnel shifts instead of nine byte loads (rows are 16-byte aligned; the
                 // <= 3 bytes read past the footprint stay inside the row pitch / the padded allocation)
-                const uint8_t* a = imgB + (size_t)(iny + L.row) * pitch + (inx + L.c0);
+                const uint8_t* a = lane_base + (iny * pitch + inx);
                 const unsigned sh = ((unsigned)(size_t)a & 3u) * 8u;
                 const unsigned* aw = reinterpret_cast<const unsigned*>((size_t)a & ~(size_t)3);
                 const unsigned W0 = __ldg(aw), W1 = __ldg(aw + 1), W2 = __ldg(aw + 2);
@@ -325,9 +372,12 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
                 P1 = (unsigned)cur[4] | ((unsigned)cur[5] << 8) | ((unsigned)cur[6] << 16) | ((unsigned)cur[7] << 24);
                 P2 = (unsigned)cur[8];
             }
-            const unsigned N0 = __shfl_down_sync(0xffffffffu, P0, LPR);      // the row below, from lane + 2
-            const unsigned N1 = __shfl_down_sync(0xffffffffu, P1, LPR);
-            const unsigned N2 = __shfl_down_sync(0xffffffffu, P2, LPR);
+            N0 = __shfl_down_sync(0xffffffffu, P0, LPR);            // the row below, from lane + 2
+            N1 = __shfl_down_sync(0xffffffffu, P1, LPR);
+            N2 = __shfl_down_sync(0xffffffffu, P2, LPR);
+            pinx = inx;
+            piny = iny;
+            }
             // bilinear sample k = w00 b_k + w01 b_{k+1} + w10 n_k + w11 n_{k+1}: two 2-way 16x8-bit dot products
             // (dp2a) on byte pairs; odd k read the pairs from the words shifted by one byte
             const unsigned Q0 = __funnelshift_r(P0, P1, 8), Q1 = __funnelshift_r(P1, P2, 8);
@@ -351,10 +401,16 @@ __device__ __forceinline__ bool lk_track_warp(const PyrView& A, const PyrView& B
                 sb[0] += diff * (int)tIx[k];            // tIx/tIy are zero for inactive slots
                 sb[1] += diff * (int)tIy[k];
             }
-            long long qb[2];
-            team_sum_exact<1, 2>(sb, qb, nullptr, flip);
-            const float b1 = __fmul_rn(__ll2float_rn(qb[0]), 9.5367431640625e-07f);
-            const float b2 = __fmul_rn(__ll2float_rn(qb[1]), 9.5367431640625e-07f);
+            float b1, b2;
+            if (narrow) {               // one REDUX per sum: the true totals fit in int32
+                b1 = __fmul_rn(__int2float_rn(__reduce_add_sync(0xffffffffu, sb[0])), 9.5367431640625e-07f);
+                b2 = __fmul_rn(__int2float_rn(__reduce_add_sync(0xffffffffu, sb[1])), 9.5367431640625e-07f);
+            } else {
+                long long qb[2];
+                team_sum_exact<1, 2>(sb, qb, nullptr, flip);
+                b1 = __fmul_rn(__ll2float_rn(qb[0]), 9.5367431640625e-07f);
+                b2 = __fmul_rn(__ll2float_rn(qb[1]), 9.5367431640625e-07f);
+            }
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             cx = __fadd_rn(cx, dx);
@@ -391,7 +447,7 @@ struct LKShared {
     short Ix[AVB_MAX_LEVELS][AVB_WIN][16];
     short Iy[AVB_MAX_LEVELS][AVB_WIN][16];
     float A11[AVB_MAX_LEVELS], A12[AVB_MAX_LEVELS], A22[AVB_MAX_LEVELS], Dinv[AVB_MAX_LEVELS];
-    int flag[AVB_MAX_LEVELS];                   // 0 usable, 1 window outside the level, 2 minEig / det reject
+    int flag[AVB_MAX_LEVELS];                   // bits 0-1: 0 usable, 1 window outside the level, 2 minEig / det reject; bit 2: narrow sums
     alignas(16) int red[2][2][4];               // [flip][sum][warp]
 };
 
@@ -428,17 +484,30 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
                     }
                 }
             }
-            long long qA[3];
-            int f0 = 0;
-            team_sum_exact<1, 3>(sA, qA, nullptr, f0);
-            float A11, A12, A22, D = 0.f;
-            const bool ok = lk_tensor(qA[0], qA[1], qA[2], prm.min_eig, A11, A12, A22, D);
+            // exact sums as in lk_track_warp: one REDUX per sum whenever the totals fit in 32 bits
+            const unsigned q11 = __reduce_add_sync(0xffffffffu, (unsigned)sA[0]);
+            const unsigned q22 = __reduce_add_sync(0xffffffffu, (unsigned)sA[2]);
+            float A12;
+            if ((q11 | q22) < 0x80000000u) {
+                A12 = __fmul_rn(__int2float_rn(__reduce_add_sync(0xffffffffu, sA[1])), 9.5367431640625e-07f);
+            } else {
+                const int one[1] = {sA[1]};
+                long long q12[1];
+                int f0 = 0;
+                team_sum_exact<1, 1>(one, q12, nullptr, f0);
+                A12 = __fmul_rn(__ll2float_rn(q12[0]), 9.5367431640625e-07f);
+            }
+            const float A11 = __fmul_rn(__uint2float_rn(q11), 9.5367431640625e-07f);
+            const float A22 = __fmul_rn(__uint2float_rn(q22), 9.5367431640625e-07f);
+            float D = 0.f;
+            const bool ok = lk_tensor_f(A11, A12, A22, prm.min_eig, prm.eig_accept, D);
             if ((threadIdx.x & 31) == 0) {
                 sh->A11[level] = A11;
                 sh->A12[level] = A12;
                 sh->A22[level] = A22;
                 sh->Dinv[level] = D;
-                sh->flag[level] = ok ? 0 : 2;
+                // bit 2: the residual sums of this level fit in int32 (LK_NARROW_MAX)
+                sh->flag[level] = (ok ? 0 : 2) | ((q11 <= LK_NARROW_MAX && q22 <= LK_NARROW_MAX) ? 4 : 0);
             }
         }
     }
@@ -456,10 +525,12 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
             nx = __fmul_rn(nx, 2.f);
             ny = __fmul_rn(ny, 2.f);
         }
-        if (sh->flag[level]) {
+        const int lflag = sh->flag[level];
+        if (lflag & 3) {
             if (level == 0) status = false;
             continue;
         }
+        const bool narrow = (lflag & 4) != 0;
         const int cols = g.lv[level].w, rows = g.lv[level].h, pitch = g.lv[level].pitch;
         const float A11 = sh->A11[level], A12 = sh->A12[level], A22 = sh->A22[level], D = sh->Dinv[level];
         int tI[3] = {0, 0, 0}, tIx[3] = {0, 0, 0}, tIy[3] = {0, 0, 0};
@@ -478,6 +549,8 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
         const unsigned x_rng = (unsigned)(cols + AVB_WIN), y_rng = (unsigned)(rows + AVB_WIN);
         const unsigned x_in = (unsigned)max(cols - 16, 0), y_in = (unsigned)max(rows - 16, 0);
         const uint8_t* lane_base = imgB + L.row * pitch + L.c0;      // this lane's first sample for a window at (0, 0)
+        unsigned P = 0, N = 0;              // this lane's 4 bytes of window row L.row and of the row below it, packed
+        int pinx = INT_MIN, piny = INT_MIN; // integer window position they were fetched for
         for (int j = 0; j < prm.max_iter; ++j) {
             const int inx = __float2int_rd(cx), iny = __float2int_rd(cy);
             if ((unsigned)(inx + AVB_WIN) >= x_rng || (unsigned)(iny + AVB_WIN) >= y_rng) {
@@ -486,9 +559,10 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
             }
             int sb1 = 0, sb2 = 0;
             if (L.npx) {
-                // this lane's 4 bytes of window row L.row and of the row below it, packed little-endian
-                unsigned P, N;
-                if ((unsigned)inx < x_in && (unsigned)iny < y_in) {         // team-uniform: window inside the level
+                // Sub-pixel updates leave the integer window position where it was on most iterations after the first:
+                // the packed samples are then still the right ones (team-uniform test; no address, no load, no latency)
+                if (inx == pinx && iny == piny) {
+                } else if ((unsigned)inx < x_in && (unsigned)iny < y_in) {  // team-uniform: window inside the level
                     // two aligned 32-bit loads per row + one funnel shift (rows are 16-byte aligned, so both rows share
                     // the byte phase; the <= 3 bytes read past the sample stay inside the row pitch / padded allocation)
                     const uint8_t* a = lane_base + iny * pitch + inx;
@@ -509,6 +583,8 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
                     N = (unsigned)__ldg(r1 + c0) | ((unsigned)__ldg(r1 + c1) << 8) | ((unsigned)__ldg(r1 + c2) << 16) |
                         ((unsigned)__ldg(r1 + c3) << 24);
                 }
+                pinx = inx;
+                piny = iny;
                 int w00, w01, w10, w11;
                 lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), w00, w01, w10, w11);
                 // bilinear sample k = w00 b_k + w01 b_{k+1} + w10 n_k + w11 n_{k+1} as two 2-way 16x8-bit dot products
@@ -532,10 +608,16 @@ __device__ __forceinline__ bool lk_track_coop(const PyrView& A, const PyrView& B
             const int4 r1 = *reinterpret_cast<const int4*>(sh->red[flip][0]);
             const int4 r2 = *reinterpret_cast<const int4*>(sh->red[flip][1]);
             flip ^= 1;
-            const long long q1 = ((long long)r1.x + (long long)r1.y) + ((long long)r1.z + (long long)r1.w);
-            const long long q2 = ((long long)r2.x + (long long)r2.y) + ((long long)r2.z + (long long)r2.w);
-            const float b1 = __fmul_rn(__ll2float_rn(q1), 9.5367431640625e-07f);
-            const float b2 = __fmul_rn(__ll2float_rn(q2), 9.5367431640625e-07f);
+            float b1, b2;
+            if (narrow) {               // the totals fit in int32: wrap-around of the partial sums cancels
+                b1 = __fmul_rn(__int2float_rn((r1.x + r1.y) + (r1.z + r1.w)), 9.5367431640625e-07f);
+                b2 = __fmul_rn(__int2float_rn((r2.x + r2.y) + (r2.z + r2.w)), 9.5367431640625e-07f);
+            } else {
+                const long long q1 = ((long long)r1.x + (long long)r1.y) + ((long long)r1.z + (long long)r1.w);
+                const long long q2 = ((long long)r2.x + (long long)r2.y) + ((long long)r2.z + (long long)r2.w);
+                b1 = __fmul_rn(__ll2float_rn(q1), 9.5367431640625e-07f);
+                b2 = __fmul_rn(__ll2float_rn(q2), 9.5367431640625e-07f);
+            }
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             cx = __fadd_rn(cx, dx);
@@ -635,6 +717,7 @@ __device__ __forceinline__ ChainResult feature_chain(const Geom& g, const DevSta
     prm.eps2 = g.eps2;
     prm.eps2_lo = g.eps2_lo;
     prm.eps2_hi = g.eps2_hi;
+    prm.eig_accept = g.eig_accept;
     ChainResult r;
     r.tracked = true;
     r.matched = false;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_klt_points(const __gri
     prm.eps2 = g.eps2;
     prm.eps2_lo = g.eps2_lo;
     prm.eps2_hi = g.eps2_hi;
+    prm.eig_accept = g.eig_accept;
     const PyrView A = pyr_view(d, g, s, slot_from), B = pyr_view(d, g, s, slot_to);
     float ox, oy;
     int flip = 0;
