@@ -191,3 +191,30 @@ def test_per_level_pyramid_kernel_on_every_level(w, h, levels, monkeypatch):
                     assert np.array_equal(c.download_level(slot, lvl), ref[lvl]), (pair, slot, lvl)
         finally:
             c.close()
+
+
+@pytest.mark.parametrize('spec_k', ['0', '2', '16'])
+def test_speculative_candidate_matching_equals_the_port(spec_k, monkeypatch):
+    """Few streams: the candidates' stereo matches run speculatively beside k_track (k_select mode 2 + k_spec_match), and
+    k_select only looks its candidates up.  AVB_SPEC_K=2 keeps the list shorter than grid_max, so that most candidates
+    MISS it and are matched by k_select itself (one warp each); 0 switches speculation off; 16 is the default.
+    All three must publish what the port publishes on 30 lossy frames."""
+    monkeypatch.setenv('AVB_SPEC_K', spec_k)
+    from image_processing import _native
+    cfg = config_c2()
+    n = 30
+    st = SlidingTextureStream(n_frames=n, **LOSSY)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    ctx = _native.Context(cfg, 752, 480, num_streams=1)
+    got = []
+    try:
+        assert ctx.kernels_per_frame() == (8 if spec_k == '0' else 9)
+        for k in range(n):
+            ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
+            got.append(_snapshot(ctx, 0))
+    finally:
+        ctx.close()
+    worst = _assert_equals_port(got, _port_run(cfg, st, 0, n), f'speculation k={spec_k}')
+    print(f'AVB_SPEC_K={spec_k}: 30 lossy frames equal the port (worst {worst:.3g} px), {got[-1]["hdr"][1]} ids handed out')

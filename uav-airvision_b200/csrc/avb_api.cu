@@ -92,7 +92,7 @@ struct avb_ctx {
     DevState d;
     PyrMaps maps;
     cudaStream_t st = nullptr, st_side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     uint8_t* h_in = nullptr;        // pinned: one input block (images + H)
     uint8_t* h_out = nullptr;       // pinned: S result blocks
     bool zc_out = false;            // k_finish writes the result blocks straight into h_out (mapped): no D2H copy node
@@ -261,6 +261,10 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     if (const char* e = getenv("AVB_PYR_PAIR")) g.pyr_pair_level = atoi(e) ? (g.nlev - 1 >= 2 ? g.nlev - 2 : 0) : 0;
     g.cand_rounds = avb_candidate_rounds(g);
     if (const char* e = getenv("AVB_CAND_ROUNDS")) g.cand_rounds = (atoi(e) == 2 && g.wpf == 1 && g.gmin < g.gmax) ? 2 : 1;
+    // Few streams (the 4-warp, latency-bound mapping): the candidates' stereo matches run speculatively beside k_track.
+    // 16 list entries per cell cover gmax candidates unless the mask removes more than 16 - gmax stronger keypoints.
+    g.spec_k = g.wpf == 4 ? std::min(std::max(16, g.gmax), std::min(g.KPC, 32)) : 0;
+    if (const char* e = getenv("AVB_SPEC_K")) g.spec_k = g.wpf == 4 ? std::min(std::max(atoi(e), 0), std::min(g.KPC, 32)) : 0;
     if (g.NMAX > 8192) {
         delete c;
         return fail(nullptr, AVB_E_INVALID, "grid_num*grid_max = %d exceeds 8192", g.NMAX);
@@ -284,6 +288,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&c->st_side, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
     CKC(cudaEventCreate(&c->ev_t0));
     CKC(cudaEventCreate(&c->ev_t1));
     CKC(dalloc(c, &d.in[0], inb));
@@ -311,6 +316,14 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(dalloc(c, &d.c_p1, S * NM));
     CKC(dalloc(c, &d.c_ok, S * NM));
     CKC(dalloc(c, &d.c_count, S * NC));
+    if (g.spec_k > 0) {
+        const size_t SK = S * NC * (size_t)g.spec_k;
+        CKC(dalloc(c, &d.s_key, SK));
+        CKC(dalloc(c, &d.s_p1, SK));
+        CKC(dalloc(c, &d.s_ok, SK));
+        CKC(dalloc(c, &d.s_und, SK));
+        CKC(dalloc(c, &d.s_n, S * NC));
+    }
     CKC(dalloc(c, &d.n_new, S * NC));
     CKC(dalloc(c, &d.next_id, 2 * S));
     CKC(dalloc(c, &d.counters, S * 8));
@@ -364,8 +377,6 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     {
         const int built = g.nlev - 1, pair_at = built >= 2 ? built - 1 : 0;
         int r = AVB_OK;
-        int fbw = 0, fbh = 0;
-        avb_fast_box(&fbw, &fbh);
         for (int v = 0; v < 2 && r == AVB_OK; ++v) {              // k_pyr_down: 16-row and 32-row tiles
             int pbw = 0, pbh = 0, ptw = 0, pth = 0;
             avb_pyramid_boxes(v, &pbw, &pbh, &ptw, &pth);
@@ -380,7 +391,11 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
         }
         for (int p = 0; p < 2 && r == AVB_OK; ++p) {
             r = make_map(c, enc, &c->maps.pair0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, 96, 44);
-            if (r == AVB_OK) r = make_map(c, enc, &c->maps.fast0[p], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, fbw, fbh);
+            for (int v = 0; v < 2 && r == AVB_OK; ++v) {
+                int fbw = 0, fbh = 0;
+                avb_fast_box(v, &fbw, &fbh);
+                r = make_map(c, enc, &c->maps.fast0[p][v], d.in[p], g.W, g.H, g.S * 2, g.W, img_bytes, fbw, fbh);
+            }
         }
         if (pair_at >= 2 && r == AVB_OK) {
             const int l = pair_at - 1;
@@ -422,6 +437,7 @@ extern "C" void avb_destroy(avb_ctx* c) {
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -467,8 +483,16 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
     cudaStreamWaitEvent(c->st_side, c->ev_fork, 0);
     launch_clear_frame(g, d, c->st_side);
     launch_fast(g, d, c->maps, p, c->st_side);
-    cudaEventRecord(c->ev_join, c->st_side);
+    const bool spec = g.spec_k > 0 && !first;
+    if (spec) launch_spec_select(g, d, c->st_side);
+    if (!spec) cudaEventRecord(c->ev_join, c->st_side);
     launch_pyramid(g, d, c->maps, p, c->st);
+    if (spec) {                         // the speculative matches read this frame's pyramids of both cameras
+        cudaEventRecord(c->ev_pyr, c->st);
+        cudaStreamWaitEvent(c->st_side, c->ev_pyr, 0);
+        launch_spec_match(g, d, p, c->st_side);
+        cudaEventRecord(c->ev_join, c->st_side);
+    }
     if (first) {
         cudaStreamWaitEvent(c->st, c->ev_join, 0);
         launch_stereo_buckets(g, d, p, c->st);
@@ -478,14 +502,15 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
         if (g.ransac) launch_ransac(g, d, p, c->st);
         cudaStreamWaitEvent(c->st, c->ev_join, 0);
         launch_select(g, d, p, 0, c->st);
-        launch_stereo_candidates(g, d, p, c->st);
+        if (!spec) launch_stereo_candidates(g, d, p, c->st);    // with speculation k_select itself matches what the list misses
     }
     launch_finish(g, d, p, first ? 1 : 0, c->st);
 }
 
 // Serialised, instrumented variant of the steady-state chain: one event after every stage on c->st.
-// Stage order: 0 input copy | 1 clear+FAST | 2 pyramid | 3 track | 4 select | 5 stereo(new) | 6 finish (grid update +
-// publish) | 7 (unused, 0) | 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
+// Stage order: 0 input copy | 1 clear+FAST (+ speculative list) | 2 pyramid | 3 track | 4 select | 5 stereo(new) |
+// 6 finish (grid update + publish) | 7 speculative stereo matches (beside k_track in the real chain; 0 when off) |
+// 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
 extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, float* stage_ms /*[9]*/) {
     if (!c || !d_block || !stage_ms) return AVB_E_INVALID;
     if (c->first_frame) return fail(c, AVB_E_STATE, "profile the steady state: process frame 0 first");
@@ -493,7 +518,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     const Geom& g = c->g;
     const DevState& d = c->d;
     const int p = c->parity ^ 1;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[11];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaEventRecord(c->ev_t0, c->st));
@@ -502,15 +527,18 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     CK(cudaEventRecord(ev[1], c->st));
     launch_clear_frame(g, d, c->st);
     launch_fast(g, d, c->maps, p, c->st);
+    if (g.spec_k > 0) launch_spec_select(g, d, c->st);
     CK(cudaEventRecord(ev[2], c->st));
     launch_pyramid(g, d, c->maps, p, c->st);
     CK(cudaEventRecord(ev[3], c->st));
+    if (g.spec_k > 0) launch_spec_match(g, d, p, c->st);
+    CK(cudaEventRecord(ev[10], c->st));
     launch_track(g, d, p, c->st);
     if (g.ransac) launch_ransac(g, d, p, c->st);       // counted with the track stage
     CK(cudaEventRecord(ev[4], c->st));
     launch_select(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[5], c->st));
-    launch_stereo_candidates(g, d, p, c->st);
+    if (g.spec_k == 0) launch_stereo_candidates(g, d, p, c->st);
     CK(cudaEventRecord(ev[6], c->st));
     launch_finish(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[7], c->st));
@@ -520,7 +548,8 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     CK(cudaEventRecord(c->ev_t1, c->st));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
-    for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+    static const int from[9] = {0, 1, 2, 10, 4, 5, 6, 3, 8}, to[9] = {1, 2, 3, 4, 5, 6, 7, 10, 9};
+    for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&stage_ms[i], ev[from[i]], ev[to[i]]);
     for (auto& e : ev) cudaEventDestroy(e);
     c->parity = p;
     return AVB_OK;
@@ -528,9 +557,9 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
 
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
-    // clear, fast, pyramid launches (the last two levels share one), track, select, stereo_candidates, finish
-    // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish
-    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (c->g.cand_rounds == 2 ? 1 : 0);
+    // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish;
+    // with speculation: + the speculative list and its matches, - stereo_candidates
+    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (c->g.cand_rounds == 2 ? 1 : 0) + (c->g.spec_k > 0 ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {

@@ -49,6 +49,8 @@ struct Geom {
     int wpf;                       // warps per feature in the LK kernels: 4 = latency mapping, 1 = throughput mapping
     int pyr_pair_level;            // k_pyr_pair builds levels pyr_pair_level and +1 in one launch (0: one k_pyr_down per level)
     int cand_rounds;               // new-feature stereo matching in 1 launch or 2 dense rounds (avb_points.cu)
+    int spec_k;                    // > 0 (few streams): the spec_k strongest FAST keypoints of every cell are stereo-matched
+                                   // SPECULATIVELY beside k_track; k_select then only looks its candidates up (avb_points.cu)
     int fast_thr;
     int max_iter;
     double min_eig;
@@ -115,6 +117,12 @@ struct DevState {
     uint8_t* c_ok;                 // [S][NMAX]
     double4* c_und;                // [S][NMAX] normalized coordinates of the candidate (valid when c_ok)
     int* c_count;                  // [S][NC]
+    // speculative matches (Geom::spec_k > 0): the spec_k largest keys of each cell's FAST bucket, unmasked, and their stereo result
+    unsigned* s_key;               // [S][NC][spec_k], descending
+    float2* s_p1;                  // [S][NC][spec_k]
+    uint8_t* s_ok;                 // [S][NC][spec_k]
+    double4* s_und;                // [S][NC][spec_k]
+    int* s_n;                      // [S][NC]
     int* n_new;                    // [S][NC]  new features given ids this frame (before pruning)
     long long* next_id;            // [2 parities][S]: read from the previous frame's parity, written to this frame's
     int* counters;                 // [S][8]: before_tracking, after_tracking, after_matching, n_fast, n_cand, after_ransac
@@ -220,14 +228,14 @@ struct PyrMaps {
     CUtensorMap dst[AVB_MAX_LEVELS][2]; // destination level l >= 1 (store box 64 x rows)
     CUtensorMap pair0[2];           // source level 0, box of k_pyr_pair (used when the pair kernel builds levels 1+2)
     CUtensorMap pair;               // source level nlev-3 >= 1, box of k_pyr_pair
-    CUtensorMap fast0[2];
+    CUtensorMap fast0[2][2];        // [parity][k_fast variant]
 };
 
 void launch_pyramid(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
 int  avb_pyramid_launches(const Geom& g);
 void avb_pyramid_boxes(int variant, int* src_w, int* src_h, int* dst_w, int* dst_h);
 void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st);
-void avb_fast_box(int* w, int* h);
+void avb_fast_box(int variant, int* w, int* h);
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_ransac(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, const float2* prev, const float2* cur, int n,
@@ -235,6 +243,8 @@ void launch_ransac_points(const Geom& g, const CamModel& cm, const double* R, co
                           cudaStream_t st);
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cudaStream_t st);
+void launch_spec_select(const Geom& g, const DevState& d, cudaStream_t st);
+void launch_spec_match(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 int  avb_candidate_rounds(const Geom& g);    // default for Geom::cand_rounds. 1: every candidate in one launch; 2: positions < gmin first, the rest on demand
 int  avb_pyramid_pair_level(const Geom& g);  // default for Geom::pyr_pair_level
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);

@@ -13,17 +13,14 @@
 #include "avb_common.cuh"
 
 #define FT_W 64
-#ifndef FT_H
-#define FT_H 26                     // (26 + 2) rows x 9 eight-pixel groups = 252 items = four full rounds of 64 threads
-#endif
-#ifndef FAST_NT
-#define FAST_NT 64                  // threads per CTA: small CTAs = many independent barrier domains per SM (measured at 64
-                                    // streams: 256 threads x 32 rows 212 us, 128 x 26 181 us, 64 x 26 175 us, 64 x 12 198 us)
-#endif
+// Tile height TH and threads per CTA NT are template parameters of k_fast:
+//   <64, 26>   many streams: (26 + 2) rows x 9 eight-pixel groups = 252 items = four full rounds of 64 threads; small CTAs =
+//              many independent barrier domains per SM (measured at 64 streams: 256 threads x 32 rows 212 us, 128 x 26
+//              181 us, 64 x 26 175 us, 64 x 12 198 us)
+//   <256, 16>  a few streams: every CTA's corner test is ONE round ((16 + 2) x 9 = 162 items of 256 threads) and one
+//              752x480 image makes 360 CTAs = one wave; the halo overhead does not matter when the GPU is mostly idle
 #define FB_W 96                     // TMA box: 16 left halo (TMA start column must be a 16-byte multiple) + FT_W + 16
 #define FB_X 16
-#define FB_H (FT_H + 8)
-#define FB_HP ((FB_H + 3) & ~3)      // rows per shared stage: FB_W * FB_HP is a multiple of 128 bytes
 #define SC_PITCH 68
 
 __device__ __forceinline__ void f_mbar_init(uint64_t* bar, int count) {
@@ -110,27 +107,26 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pol) {
     return best - 1;                // best > thr for a corner, so this is >= thr
 }
 
-#define FAST_POS ((FT_H + 2) * (FT_W + 2))
 #define FG 9                        // 8-pixel groups per tile row: tile columns 12 .. 83 cover px = -1 .. 64
-#define FAST_ITEMS (FG * (FT_H + 2))
 
-#ifndef AVB_FAST_CTAS_PER_SM
-#define AVB_FAST_CTAS_PER_SM 12     // persistent grid = min(tiles, 148 x this)
-#endif
-#define FAST_MAXK ((FT_W / 2) * (FT_H / 2))     // strict 3x3 NMS: no two keypoints are 8-neighbours
 
 struct FastDivs {
     FastDiv per_img, tiles_x, gw, gh;
 };
 
-// Persistent: a CTA walks over 64x32 tiles (tile t, t + grid, ...), the TMA copy of the next tile in flight while this
+// Persistent: a CTA walks over 64 x TH tiles (tile t, t + grid, ...), the TMA copy of the next tile in flight while this
 // one is processed.  Passes per tile: (A) the corner test on every pixel of the tile + 1-pixel ring, four pixels per
 // word, corners compacted into a shared list (one shared atomic per warp and round); (B) the exact score only for listed
 // corners, one per thread (no lane idles through someone else's score); (C1) strict 3x3 non-maximum suppression, the
 // keypoints compacted again; (C2) bucketing by grid cell, every lane busy.
-__global__ void __launch_bounds__(FAST_NT, AVB_FAST_CTAS_PER_SM) k_fast(const __grid_constant__ CUtensorMap map0, const __grid_constant__ Geom g,
-                                                                  const __grid_constant__ DevState d, const __grid_constant__ FastDivs dv,
-                                                                  int tiles_x, int tiles_y, int n_tiles) {
+template <int FAST_NT, int FT_H>
+__global__ void __launch_bounds__(FAST_NT, FAST_NT == 64 ? 12 : 3) k_fast(const __grid_constant__ CUtensorMap map0, const __grid_constant__ Geom g,
+                                                                       const __grid_constant__ DevState d, const __grid_constant__ FastDivs dv,
+                                                                       int tiles_x, int tiles_y, int n_tiles) {
+    constexpr int FB_H = FT_H + 8;                                  // TMA box height
+    constexpr int FB_HP = (FB_H + 3) & ~3;                          // rows per shared stage: FB_W * FB_HP is a multiple of 128 bytes
+    constexpr int FAST_POS = (FT_H + 2) * (FT_W + 2), FAST_ITEMS = FG * (FT_H + 2);
+    constexpr int FAST_MAXK = (FT_W / 2) * (FT_H / 2);              // strict 3x3 NMS: no two keypoints are 8-neighbours
     __shared__ __align__(128) uint8_t tile[2][FB_HP][FB_W];        // FB_HP: every stage starts on a 128-byte boundary (TMA)
     __shared__ __align__(16) uint8_t sc[2][FT_H + 2][SC_PITCH];
     __shared__ unsigned short clist[FAST_POS];
@@ -297,17 +293,23 @@ __global__ void __launch_bounds__(FAST_NT, AVB_FAST_CTAS_PER_SM) k_fast(const __
     }
 }
 
-void avb_fast_box(int* w, int* h) {              // shape of the TMA box the fast0 descriptors must be encoded with
+void avb_fast_box(int variant, int* w, int* h) {      // shape of the TMA box the fast0 descriptors of a variant need
     *w = FB_W;
-    *h = FB_H;
+    *h = (variant ? 16 : 26) + 8;
 }
 
 void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int parity, cudaStream_t st) {
-    const int tx = (g.W + FT_W - 1) / FT_W, ty = (g.H + FT_H - 1) / FT_H, nt = tx * ty * g.S;
+    const int tx = (g.W + FT_W - 1) / FT_W;
+    // many streams (every SM gets a dozen small tiles' worth): 64 threads x 26 rows; else 256 threads x 16 rows
+    const int v = (long)tx * ((g.H + 25) / 26) * g.S >= 148 * 12 ? 0 : 1;
+    const int th = v ? 16 : 26, ty = (g.H + th - 1) / th, nt = tx * ty * g.S;
     FastDivs dv;
     dv.per_img = make_fdiv(tx * ty, nt);
     dv.tiles_x = make_fdiv(tx, tx * ty);
     dv.gw = make_fdiv(g.gw, g.W);
     dv.gh = make_fdiv(g.gh, g.H);
-    k_fast<<<std::min(nt, 148 * AVB_FAST_CTAS_PER_SM), FAST_NT, 0, st>>>(maps.fast0[parity], g, d, dv, tx, ty, nt);
+    if (v)
+        k_fast<256, 16><<<std::min(nt, 148 * 3), 256, 0, st>>>(maps.fast0[parity][v], g, d, dv, tx, ty, nt);
+    else
+        k_fast<64, 26><<<std::min(nt, 148 * 12), 64, 0, st>>>(maps.fast0[parity][v], g, d, dv, tx, ty, nt);
 }

@@ -38,68 +38,146 @@ __global__ void k_finish(const __grid_constant__ Geom g, const __grid_constant__
 //   2. top-k by key: every warp extracts the k largest keys of its strided share with warp-max rounds (no block
 //      barrier), then warp 0 extracts the k largest of the 8k finalists.  A key packs (response, inverted scan
 //      index), the low word of a finalist is its bucket index, so ties cannot occur.
+// mode 0: steady state (FeatureAdder); 1: first frame (FeatureInitializer ranking of the stereo inliers);
+// mode 2: SPECULATIVE list (few streams, Geom::spec_k): the spec_k strongest keypoints of the cell, unmasked -- whatever
+//         the mask removes later, the adder's candidates are the first unmasked ones of this order, so they are in this
+//         list unless more than spec_k - gmax keypoints above them get masked.  Their stereo match (k_spec_match) runs
+//         BESIDE k_track instead of behind it; mode 0 then copies the result of every candidate it finds in the list
+//         and marks the others (c_ok = 2) for k_stereo_candidates, which matches only those.
 #define SEL_WARPS 8
 #define SEL_MAXF 128               // live features that can touch one cell: gmax per cell x the 9 cells around, generously
+template <bool SPEC>                // SPEC: the speculative look-up + in-kernel matching of the misses is compiled in (115 registers
+                                    // against 32: the many-stream launches, which never speculate, keep the small kernel)
 __global__ void __launch_bounds__(32 * SEL_WARPS) k_select(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
-                                                          int parity, int first_frame) {
+                                                          int parity, int mode) {
     extern __shared__ unsigned smem_u32[];
     unsigned* keys = smem_u32;
     __shared__ unsigned feat[SEL_MAXF];
     __shared__ int n_feat;
     __shared__ unsigned long long fin[SEL_WARPS * AVB_MAX_CAP];
+    __shared__ unsigned skeys[32 * SEL_WARPS];
+    __shared__ unsigned miss_key[AVB_MAX_CAP];  // candidates the speculative list does not hold: matched here, one warp each
+    __shared__ int miss_slot[AVB_MAX_CAP];
+    __shared__ int n_miss;
 
-    pdl_wait();
-    pdl_launch_dependents();
+    if (mode != 2) {                // the speculative list depends on FAST alone and is not a link of the PDL chain
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+    const bool first_frame = mode == 1;
     const int cell = blockIdx.x, s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t kbase = ((size_t)s * g.NC + cell) * g.KPC;
-    const int n = min(d.kp_count[s * g.NC + cell], g.KPC);
-    const int k = first_frame ? g.gmin : g.gmax;
+    // every global load that does not depend on another one is issued here, together: the kernel is a chain of memory
+    // round trips otherwise (it ran 9.4 us for a few hundred bytes of work)
+    const int n_raw = d.kp_count[s * g.NC + cell];
+    const unsigned key_raw = tid < g.KPC ? d.kp_key[kbase + tid] : 0u;          // valid when tid < n
+    const uint8_t ok_raw = (first_frame && tid < g.KPC) ? d.kp_ok[kbase + tid] : (uint8_t)1;
+    const int k = mode == 2 ? g.spec_k : (first_frame ? g.gmin : g.gmax);
 
-    if (tid == 0) n_feat = 0;
+    if (tid == 0) n_feat = n_miss = 0;
     __syncthreads();
-    if (!first_frame) {
+    if (mode == 0) {
         const int cx0 = (cell % g.cols) * g.gw, cy0 = (cell / g.cols) * g.gh;
-        for (int i = tid; i < g.NMAX; i += 32 * SEL_WARPS) {
-            if (d.t_cell[(size_t)s * g.NMAX + i] >= 0) {
-                const float2 p = d.t_p0[(size_t)s * g.NMAX + i];
-                const int fx = (int)p.x, fy = (int)p.y;             // int() truncation (B7)
-                // mask[y-3:y+4, x-3:x+4] = 0 with a negative slice start selects nothing (B7)
-                if (fx >= 3 && fy >= 3 && fx >= cx0 - 3 && fx < cx0 + g.gw + 3 && fy >= cy0 - 3 && fy < cy0 + g.gh + 3) {
-                    const int pos = atomicAdd(&n_feat, 1);
-                    if (pos < SEL_MAXF) feat[pos] = ((unsigned)fy << 16) | (unsigned)fx;
+        for (int i0 = 0; i0 < g.NMAX; i0 += 2 * 32 * SEL_WARPS) {
+            const int ia = i0 + tid, ib = ia + 32 * SEL_WARPS;
+            const size_t fb = (size_t)s * g.NMAX;
+            const int ca = ia < g.NMAX ? d.t_cell[fb + ia] : -1, cb = ib < g.NMAX ? d.t_cell[fb + ib] : -1;
+            const float2 pa = ia < g.NMAX ? d.t_p0[fb + ia] : make_float2(0.f, 0.f);
+            const float2 pb = ib < g.NMAX ? d.t_p0[fb + ib] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = h ? cb : ca;
+                const float2 p = h ? pb : pa;
+                if (c >= 0) {
+                    const int fx = (int)p.x, fy = (int)p.y;         // int() truncation (B7)
+                    // mask[y-3:y+4, x-3:x+4] = 0 with a negative slice start selects nothing (B7)
+                    if (fx >= 3 && fy >= 3 && fx >= cx0 - 3 && fx < cx0 + g.gw + 3 && fy >= cy0 - 3 && fy < cy0 + g.gh + 3) {
+                        const int pos = atomicAdd(&n_feat, 1);
+                        if (pos < SEL_MAXF) feat[pos] = ((unsigned)fy << 16) | (unsigned)fx;
+                    }
                 }
             }
         }
     }
     __syncthreads();
+    const int n = min(n_raw, g.KPC);
     const int nf_all = n_feat, nf = min(nf_all, SEL_MAXF);
-    for (int i = tid; i < n; i += 32 * SEL_WARPS) {
-        unsigned key = d.kp_key[kbase + i];
-        if (first_frame) {
-            if (!d.kp_ok[kbase + i]) key = 0;
-        } else {
-            int resp, x, y;
-            kp_decode(key, g.W, resp, x, y);
-            bool masked = false;
-            for (int j = 0; j < nf; ++j) {
-                const int fx = (int)(feat[j] & 0xffffu), fy = (int)(feat[j] >> 16);
-                masked |= (abs(x - fx) <= 3) && (abs(y - fy) <= 3);
+    auto masked_key = [&](unsigned key, uint8_t ok) -> unsigned {
+        if (first_frame) return ok ? key : 0u;
+        if (mode != 0) return key;
+        int resp, x, y;
+        kp_decode(key, g.W, resp, x, y);
+        bool masked = false;
+        for (int j = 0; j < nf; ++j) {
+            const int fx = (int)(feat[j] & 0xffffu), fy = (int)(feat[j] >> 16);
+            masked |= (abs(x - fx) <= 3) && (abs(y - fy) <= 3);
+        }
+        if (nf_all > SEL_MAXF) {                                    // overflow of the local list: fall back to the full table
+            for (int j = 0; j < g.NMAX && !masked; ++j) {
+                if (d.t_cell[(size_t)s * g.NMAX + j] < 0) continue;
+                const float2 p = d.t_p0[(size_t)s * g.NMAX + j];
+                const int fx = (int)p.x, fy = (int)p.y;
+                masked = fx >= 3 && fy >= 3 && (abs(x - fx) <= 3) && (abs(y - fy) <= 3);
             }
-            if (nf_all > SEL_MAXF) {                                // overflow of the local list: fall back to the full table
-                for (int j = 0; j < g.NMAX && !masked; ++j) {
-                    if (d.t_cell[(size_t)s * g.NMAX + j] < 0) continue;
-                    const float2 p = d.t_p0[(size_t)s * g.NMAX + j];
-                    const int fx = (int)p.x, fy = (int)p.y;
-                    masked = fx >= 3 && fy >= 3 && (abs(x - fx) <= 3) && (abs(y - fy) <= 3);
+        }
+        return masked ? 0u : key;
+    };
+    const size_t sbase = ((size_t)s * g.NC + cell) * (size_t)max(g.spec_k, 1);
+    const bool lookup = SPEC && mode == 0 && g.spec_k > 0;
+    const int sn = lookup ? d.s_n[s * g.NC + cell] : 0;
+
+    if (n <= 32 * SEL_WARPS) {
+        // The usual case: one key per thread.  Rank = number of larger keys (keys of distinct keypoints are distinct: a
+        // key holds the scan position), read from shared memory: no reduction rounds, no serial tail; the thread that
+        // owns rank r writes list entry r and does its own look-up in the speculative list.
+        const unsigned key = tid < n ? masked_key(key_raw, ok_raw) : 0u;
+        skeys[tid] = key;
+        const int live = __syncthreads_count(key != 0u);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += skeys[j] > key;
+        if (key != 0u && rank < k) {
+            if (mode == 2) {
+                d.s_key[sbase + rank] = key;
+            } else {
+                const size_t o = (size_t)s * g.NMAX + cell * g.gmax + rank;
+                d.c_key[o] = key;
+                d.c_src[o] = tid;
+                if (first_frame) {
+                    d.c_p1[o] = d.kp_p1[kbase + tid];
+                    d.c_ok[o] = 1;
+                } else if (lookup) {
+                    int hit = -1;
+                    for (int j = 0; j < sn; ++j)
+                        if (d.s_key[sbase + j] == key) hit = j;
+                    if (hit >= 0) {                                 // matched speculatively: take the result
+                        const uint8_t ok = d.s_ok[sbase + hit];
+                        d.c_p1[o] = d.s_p1[sbase + hit];
+                        d.c_ok[o] = ok;
+                        if (ok) d.c_und[o] = d.s_und[sbase + hit];
+                    } else {                                        // not in the list: matched below
+                        const int m = atomicAdd(&n_miss, 1);
+                        miss_key[m] = key;
+                        miss_slot[m] = rank;
+                    }
                 }
             }
-            if (masked) key = 0;
         }
-        keys[i] = key;
-    }
-    __syncthreads();
+        if (tid == 0) {
+            const int found = min(live, k);
+            if (mode == 2) {
+                d.s_n[s * g.NC + cell] = found;
+            } else {
+                d.c_count[s * g.NC + cell] = found;
+                atomicAdd(&d.counters[s * 8 + 3], n);
+                atomicAdd(&d.counters[s * 8 + 4], found);
+            }
+        }
+    } else {
 
-    // per-warp top-k of the keys i = warp*32 + lane (mod 256); an exhausted warp reports zeros
+    // More keypoints in the cell than threads (dense noise): top-k by reduction rounds.  Every warp extracts the k largest
+    // keys of its strided share with warp-max rounds, then warp 0 extracts the k largest of the 8k finalists.
+    for (int i = tid; i < n; i += 32 * SEL_WARPS) keys[i] = masked_key(d.kp_key[kbase + i], first_frame ? d.kp_ok[kbase + i] : (uint8_t)1);
+    __syncthreads();
     {
         unsigned long long last = ~0ull;
         for (int r = 0; r < k; ++r) {
@@ -116,6 +194,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) k_select(const __grid_constant
     }
     __syncthreads();
     if (warp == 0) {
+        const unsigned skey = (lookup && lane < sn) ? d.s_key[sbase + lane] : 0u;  // the speculative list: one entry per lane
         unsigned long long last = ~0ull;
         int found = 0;
         for (int r = 0; r < k; ++r) {
@@ -127,30 +206,72 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) k_select(const __grid_constant
             best = warp_max_u64(best);
             if ((best >> 32) == 0) break;
             last = best;
+            const unsigned key = (unsigned)(best >> 32);
+            const unsigned hit = lookup ? __ballot_sync(0xffffffffu, skey == key) : 0u;
             if (lane == 0) {
-                const size_t o = (size_t)s * g.NMAX + cell * g.gmax + r;
-                const int src = (int)(best & 0xffffffffu);
-                d.c_key[o] = (unsigned)(best >> 32);
-                d.c_src[o] = src;
-                if (first_frame) {
-                    d.c_p1[o] = d.kp_p1[kbase + src];
-                    d.c_ok[o] = 1;
+                if (mode == 2) {
+                    d.s_key[sbase + r] = key;
+                } else {
+                    const size_t o = (size_t)s * g.NMAX + cell * g.gmax + r;
+                    const int src = (int)(best & 0xffffffffu);
+                    d.c_key[o] = key;
+                    d.c_src[o] = src;
+                    if (first_frame) {
+                        d.c_p1[o] = d.kp_p1[kbase + src];
+                        d.c_ok[o] = 1;
+                    } else if (lookup) {
+                        if (hit) {
+                            const size_t si = sbase + (__ffs(hit) - 1);
+                            const uint8_t ok = d.s_ok[si];
+                            d.c_p1[o] = d.s_p1[si];
+                            d.c_ok[o] = ok;
+                            if (ok) d.c_und[o] = d.s_und[si];
+                        } else {
+                            const int m = atomicAdd(&n_miss, 1);
+                            miss_key[m] = key;
+                            miss_slot[m] = r;
+                        }
+                    }
                 }
             }
             ++found;
         }
         if (lane == 0) {
-            d.c_count[s * g.NC + cell] = found;
-            atomicAdd(&d.counters[s * 8 + 3], n);
-            atomicAdd(&d.counters[s * 8 + 4], found);
+            if (mode == 2) {
+                d.s_n[s * g.NC + cell] = found;
+            } else {
+                d.c_count[s * g.NC + cell] = found;
+                atomicAdd(&d.counters[s * 8 + 3], n);
+                atomicAdd(&d.counters[s * 8 + 4], found);
+            }
+        }
+    }
+    }
+    if (!SPEC || !lookup) return;
+    // Candidates the speculative list did not hold (more than spec_k - gmax stronger keypoints were masked: rare) are
+    // stereo-matched here, one warp each (stereo_matcher.py:33-115 through the one-warp mapping)
+    __syncthreads();
+    if constexpr (SPEC) {
+        for (int m = warp; m < n_miss; m += SEL_WARPS) {
+            int resp, x, y;
+            kp_decode(miss_key[m], g.W, resp, x, y);
+            const ChainResult r = feature_chain<1>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, nullptr);
+            if (lane == 0) {
+                const size_t o = (size_t)s * g.NMAX + cell * g.gmax + miss_slot[m];
+                d.c_p1[o] = make_float2(r.x1, r.y1);
+                d.c_ok[o] = r.matched ? 1 : 0;
+                if (r.matched) d.c_und[o] = make_double4(r.u0, r.v0, r.u1, r.v1);
+            }
         }
     }
 }
 
 int avb_set_smem_limits(size_t select_bytes, size_t grid_bytes) {
     cudaError_t e = cudaSuccess;
-    if (select_bytes > 48 * 1024)
-        e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_bytes);
+    if (select_bytes > 44 * 1024)      // the kernels also hold ~4 KB of static shared memory
+        e = cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_bytes);
+    if (e == cudaSuccess && select_bytes > 44 * 1024)
+        e = cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_bytes);
     if (e == cudaSuccess && grid_bytes > 16 * 1024)      // k_finish also holds ~29 KB of static shared memory
         e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_bytes);
     return e == cudaSuccess ? 0 : -1;
@@ -158,7 +279,14 @@ int avb_set_smem_limits(size_t select_bytes, size_t grid_bytes) {
 
 void launch_select(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st) {
     const size_t smem = (size_t)g.KPC * sizeof(unsigned);
-    launch_k(k_select, dim3(g.NC, g.S), dim3(32 * SEL_WARPS), smem, st, g_avb_pdl && !first_frame, g, d, parity, first_frame);
+    if (g.spec_k > 0 && !first_frame)
+        launch_k(k_select<true>, dim3(g.NC, g.S), dim3(32 * SEL_WARPS), smem, st, g_avb_pdl != 0, g, d, parity, 0);
+    else
+        launch_k(k_select<false>, dim3(g.NC, g.S), dim3(32 * SEL_WARPS), smem, st, g_avb_pdl && !first_frame, g, d, parity, first_frame ? 1 : 0);
+}
+void launch_spec_select(const Geom& g, const DevState& d, cudaStream_t st) {
+    const size_t smem = (size_t)g.KPC * sizeof(unsigned);
+    launch_k(k_select<false>, dim3(g.NC, g.S), dim3(32 * SEL_WARPS), smem, st, false, g, d, 0, 2);
 }
 
 // k_finish: one 1024-thread CTA per stream closes the frame.

@@ -99,6 +99,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOC
     }
 }
 
+// Speculative stereo_match of the spec_k strongest keypoints of every cell (k_select mode 2), one warp each, on the side
+// stream beside k_track.  Same arithmetic as k_stereo_candidates (both lane mappings give bit-identical results).
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, AVB_WPF1_BLOCKS) k_spec_match(const __grid_constant__ Geom g,
+                                                                                    const __grid_constant__ DevState d, int parity) {
+    const int s = blockIdx.y;
+    const int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (t >= g.NC * g.spec_k) return;
+    const int cell = t / g.spec_k, j = t - cell * g.spec_k;
+    if (j >= d.s_n[s * g.NC + cell]) return;
+    const size_t idx = ((size_t)s * g.NC + cell) * g.spec_k + j;
+    int resp, x, y;
+    kp_decode(d.s_key[idx], g.W, resp, x, y);
+    const ChainResult r = feature_chain<1>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, nullptr);
+    if ((threadIdx.x & 31) == 0) {
+        d.s_p1[idx] = make_float2(r.x1, r.y1);
+        d.s_ok[idx] = r.matched ? 1 : 0;
+        if (r.matched) d.s_und[idx] = make_double4(r.u0, r.v0, r.u1, r.v1);
+    }
+}
+
 // frame 0: stereo_match of EVERY FAST keypoint before ranking (feature_initializer.py:52-55, B15)
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 8) k_stereo_buckets(const __grid_constant__ Geom g,
                                                                          const __grid_constant__ DevState d, int parity) {
@@ -208,6 +228,9 @@ void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cuda
     } else {
         launch_k(k_stereo_candidates<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity, -1);
     }
+}
+void launch_spec_match(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
+    k_spec_match<<<dim3(teams_grid(g.NC * g.spec_k, 1), g.S), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
 }
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid((g.KPC + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.NC, g.S);
