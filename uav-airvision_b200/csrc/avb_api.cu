@@ -103,6 +103,10 @@ struct avb_ctx {
     bool rot_copy_pending = false;  // an enqueued (not waited-for) gather frame's rotation copy may not have run yet
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // steady-state frame, per parity, host-input variant
     cudaGraphExec_t graph_dev[2] = {nullptr, nullptr}; // same, device-input variant (no H2D of images)
+    // host-image path (avb_process_frame): the cam0-only work (clear, FAST, speculative list) as a graph of its own, launched
+    // as soon as the cam0 images have arrived, while the cam1 images are still on the bus; and the rest of the chain
+    cudaGraphExec_t graph_cam0[2] = {nullptr, nullptr}, graph_rest[2] = {nullptr, nullptr};
+    cudaEvent_t ev_cam0 = nullptr, ev_rot = nullptr, ev_side_done = nullptr;
     std::vector<void*> allocs;
     // scratch for the per-stage entry points
     float2 *s_a = nullptr, *s_b = nullptr, *s_c = nullptr;
@@ -289,6 +293,9 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_cam0, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_rot, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
     CKC(cudaEventCreate(&c->ev_t0));
     CKC(cudaEventCreate(&c->ev_t1));
     CKC(dalloc(c, &d.in[0], inb));
@@ -410,6 +417,10 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     }
     CKC(cudaStreamSynchronize(c->st));
     CKC(cudaDeviceSynchronize());
+    if (avb_preload_fast() || avb_preload_grid() || avb_preload_points() || avb_preload_pyramid()) {
+        avb_destroy(c);
+        return fail(nullptr, AVB_E_CUDA, "loading the kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     if (cfg->use_graph) {
         int r = build_graphs(c);
         if (r != AVB_OK) {
@@ -429,6 +440,8 @@ extern "C" void avb_destroy(avb_ctx* c) {
     for (int p = 0; p < 2; ++p) {
         if (c->graph[p]) cudaGraphExecDestroy(c->graph[p]);
         if (c->graph_dev[p]) cudaGraphExecDestroy(c->graph_dev[p]);
+        if (c->graph_cam0[p]) cudaGraphExecDestroy(c->graph_cam0[p]);
+        if (c->graph_rest[p]) cudaGraphExecDestroy(c->graph_rest[p]);
     }
     for (void* p : c->allocs) cudaFree(p);
     for (void* p : {(void*)c->s_a, (void*)c->s_b, (void*)c->s_c, (void*)c->s_st, (void*)c->s_da, (void*)c->s_db, (void*)c->s_R})
@@ -438,6 +451,8 @@ extern "C" void avb_destroy(avb_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
+    for (cudaEvent_t e : {c->ev_cam0, c->ev_rot, c->ev_side_done})
+        if (e) cudaEventDestroy(e);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -465,6 +480,7 @@ extern "C" int avb_reset(avb_ctx* c) {
     for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(c->d.grid[p].count, 0, (size_t)g.S * g.NC * sizeof(int), c->st));
     CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)2 * g.S * sizeof(long long), c->st));
     CK(cudaMemsetAsync(c->d.frame_index, 0, (size_t)g.S * sizeof(int), c->st));
+    CK(cudaMemsetAsync(c->d.counters, 0, (size_t)g.S * 8 * sizeof(int), c->st));
     CK(cudaStreamSynchronize(c->st));
     c->parity = 1;
     c->first_frame = true;
@@ -473,6 +489,33 @@ extern "C" int avb_reset(avb_ctx* c) {
 }
 
 // ---- the frame ------------------------------------------------------------------------------------
+
+// The steady-state chain in two parts for the host-image path.  Part 1 needs the cam0 images only.
+static void enqueue_cam0_part(avb_ctx* c, int p, cudaStream_t st) {
+    launch_clear_frame(c->g, c->d, st);
+    launch_fast(c->g, c->d, c->maps, p, st);
+    if (c->g.spec_k > 0) launch_spec_select(c->g, c->d, st);
+}
+// Part 2 (captured on c->st): everything else.  It meets part 1 through ev_side_done, an event OUTSIDE the graph (recorded
+// on the side stream behind part 1, before this graph is launched): first where the speculative matches start, else
+// where k_select reads the FAST buckets.
+static void enqueue_rest_part(avb_ctx* c, int p) {
+    const Geom& g = c->g;
+    const DevState& d = c->d;
+    const bool spec = g.spec_k > 0;
+    launch_pyramid(g, d, c->maps, p, c->st);
+    cudaEventRecord(c->ev_fork, c->st);
+    cudaStreamWaitEvent(c->st_side, c->ev_fork, 0);                            // the side stream joins the capture
+    cudaStreamWaitEvent(c->st_side, c->ev_side_done, cudaEventWaitExternal);
+    if (spec) launch_spec_match(g, d, p, c->st_side);
+    cudaEventRecord(c->ev_join, c->st_side);
+    launch_track(g, d, p, c->st);
+    if (g.ransac) launch_ransac(g, d, p, c->st);
+    cudaStreamWaitEvent(c->st, c->ev_join, 0);
+    launch_select(g, d, p, 0, c->st);
+    if (!spec) launch_stereo_candidates(g, d, p, c->st);
+    launch_finish(g, d, p, 0, c->st);
+}
 
 // Enqueues the kernel chain of one frame on c->st (FAST runs on a forked branch).  Inputs of parity p must
 // already be (or be ordered before this on c->st) in d.in[p].
@@ -579,6 +622,23 @@ static int build_graphs(avb_ctx* c) {
             CK(cudaGraphDestroy(graph));
             (variant == 0 ? c->graph : c->graph_dev)[p] = exec;
         }
+    }
+    for (int p = 0; p < 2; ++p) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        CK(cudaStreamBeginCapture(c->st_side, cudaStreamCaptureModeThreadLocal));
+        enqueue_cam0_part(c, p, c->st_side);
+        CK(cudaStreamEndCapture(c->st_side, &graph));
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        c->graph_cam0[p] = exec;
+        CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+        enqueue_rest_part(c, p);
+        if (!c->zc_out) cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
+        CK(cudaStreamEndCapture(c->st, &graph));
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        c->graph_rest[p] = exec;
     }
     return AVB_OK;
 }
@@ -709,6 +769,50 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
     const size_t ro = in_images_bytes(g);
     avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     CK(cudaEventRecord(c->ev_t0, c->st));
+    if (g.S == 1 && !c->first_frame && c->cfg.use_graph && c->graph_cam0[p]) {
+        // One stream, steady state: the cam0-only part of the chain (clear, FAST, speculative list) starts as soon as the
+        // cam0 image has arrived, while the cam1 image is still on the bus (7 us at 752x480); the rest of the chain
+        // follows the cam1 copy and meets that part through ev_side_done.
+        const uint8_t *src0 = img0[0], *src1 = img1[0];
+        if (!src0 || !src1) return fail(c, AVB_E_INVALID, "null image pointer (stream 0)");
+        const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
+        if (!pin1) c->copier.post(c->h_in + ib, src1, g.W, g.H, stride);       // the helper stages cam1 meanwhile
+        int rc = AVB_OK;
+        auto ck = [&](cudaError_t e, const char* what) {
+            if (e != cudaSuccess && rc == AVB_OK) rc = fail(c, AVB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        };
+        if (pin0) {
+            ck(cudaMemcpyAsync(c->d.in[p], src0, ib, cudaMemcpyHostToDevice, c->st), "H2D cam0");
+        } else {
+            CopyWorker::copy(c->h_in, src0, g.W, g.H, stride);
+            ck(cudaMemcpyAsync(c->d.in[p], c->h_in, ib, cudaMemcpyHostToDevice, c->st), "H2D cam0");
+        }
+        ck(cudaEventRecord(c->ev_cam0, c->st), "event");
+        ck(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0), "wait");               // not before the previous frame is done with d.in[p]
+        ck(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side), "H2D rotations");
+        ck(cudaEventRecord(c->ev_rot, c->st_side), "event");
+        ck(cudaStreamWaitEvent(c->st_side, c->ev_cam0, 0), "wait");
+        ck(cudaGraphLaunch(c->graph_cam0[p], c->st_side), "graph (cam0 part)");
+        ck(cudaEventRecord(c->ev_side_done, c->st_side), "event");
+        if (pin1) {
+            ck(cudaMemcpyAsync(c->d.in[p] + ib, src1, ib, cudaMemcpyHostToDevice, c->st), "H2D cam1");
+        } else {
+            c->copier.wait();
+            ck(cudaMemcpyAsync(c->d.in[p] + ib, c->h_in + ib, ib, cudaMemcpyHostToDevice, c->st), "H2D cam1");
+        }
+        ck(cudaStreamWaitEvent(c->st, c->ev_rot, 0), "wait");
+        ck(cudaGraphLaunch(c->graph_rest[p], c->st), "graph (rest)");
+        ck(cudaEventRecord(c->ev_t1, c->st), "event");
+        if (rc != AVB_OK) {
+            cudaStreamSynchronize(c->st_side);
+            cudaStreamSynchronize(c->st);
+            return rc;
+        }
+        c->parity = p;
+        c->have_frame = true;
+        CK(cudaStreamSynchronize(c->st));
+        return AVB_OK;
+    }
     bool rot_sent = false;
     auto send_rotations = [&]() -> int {
         CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));      // not before the previous frame is done with d.in[p]

@@ -250,7 +250,11 @@ int  avb_pyramid_pair_level(const Geom& g);  // default for Geom::pyr_pair_level
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st);
 void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame, cudaStream_t st);
 void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st);
-int  avb_set_smem_limits(size_t select_bytes, size_t grid_bytes);   // opt in to > 48 KB dynamic shared memory
+int  avb_set_smem_limits(size_t select_bytes, size_t grid_bytes);
+int  avb_preload_fast();
+int  avb_preload_grid();
+int  avb_preload_points();
+int  avb_preload_pyramid();   // opt in to > 48 KB dynamic shared memory
 // flat point lists (per-stage entry points)
 void launch_klt_points(const Geom& g, const DevState& d, int s, int slot_from, int slot_to,
                        const float2* prev, const float2* guess, int n, float2* out, uint8_t* status,

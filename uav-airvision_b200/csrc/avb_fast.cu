@@ -313,3 +313,13 @@ void launch_fast(const Geom& g, const DevState& d, const PyrMaps& maps, int pari
     else
         k_fast<64, 26><<<std::min(nt, 148 * 12), 64, 0, st>>>(maps.fast0[parity][v], g, d, dv, tx, ty, nt);
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch: ~0.2 ms each, which frame 0 of a stream
+// would pay for the kernels only it uses.  cudaFuncGetAttributes loads the function now (called from avb_create).
+int avb_preload_fast() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_fast<64, 26>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_fast<256, 16>);
+    return e == cudaSuccess ? 0 : -1;
+}

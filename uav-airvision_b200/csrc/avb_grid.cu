@@ -10,14 +10,15 @@
 
 #include "avb_lk.cuh"
 
+// FAST bucket counts of the frame.  (The per-frame counters are zeroed by k_finish once it has published them: k_track
+// adds to them on the main branch, which is not ordered against this kernel on the FAST branch.)
 __global__ void k_clear_frame(Geom g, DevState d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < g.S * g.NC) d.kp_count[i] = 0;
-    if (i < g.S * 8) d.counters[i] = 0;
 }
 
 void launch_clear_frame(const Geom& g, const DevState& d, cudaStream_t st) {
-    const int n = g.S * (g.NC > 8 ? g.NC : 8);
+    const int n = g.S * g.NC;
     k_clear_frame<<<(n + 255) / 256, 256, 0, st>>>(g, d);
 }
 
@@ -576,6 +577,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
 #endif
         d.next_id[parity * g.S + s] = next_id + total_new;
         d.frame_index[s] += 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d.counters[s * 8 + i] = 0;     // published: zero for the next frame's kernels
     }
 }
 
@@ -583,4 +586,16 @@ void launch_finish(const Geom& g, const DevState& d, int parity, int first_frame
     const int per_cta = FIN_THREADS / 32;
     const int nct = std::min((g.NC + per_cta - 1) / per_cta, 8);
     launch_k(k_finish, dim3(g.S, nct), dim3(FIN_THREADS), (size_t)g.NMAX * 3 * sizeof(int), st, g_avb_pdl != 0, g, d, parity, first_frame);
+}
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch: ~0.2 ms each, which frame 0 of a stream
+// would pay for the kernels only it uses.  cudaFuncGetAttributes loads the function now (called from avb_create).
+int avb_preload_grid() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_clear_frame);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_select<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_select<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_finish);
+    return e == cudaSuccess ? 0 : -1;
 }

@@ -256,3 +256,17 @@ void launch_undistort(const CamModel& cam, const double* xy, int n, const double
     if (n <= 0) return;
     k_undistort<<<(n + 127) / 128, 128, 0, st>>>(cam, xy, n, R, has_R, f32_io, distort, out);
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch: ~0.2 ms each, which frame 0 of a stream
+// would pay for the kernels only it uses.  cudaFuncGetAttributes loads the function now (called from avb_create).
+int avb_preload_points() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<4>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<4>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_spec_match);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_buckets);
+    return e == cudaSuccess ? 0 : -1;
+}

@@ -376,3 +376,14 @@ int avb_pyramid_launches(const Geom& g) {
     const int built = g.nlev - 1;
     return g.pyr_pair_level ? built - 1 : built;
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch: ~0.2 ms each, which frame 0 of a stream
+// would pay for the kernels only it uses.  cudaFuncGetAttributes loads the function now (called from avb_create).
+int avb_preload_pyramid() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_pyr_down<16>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_pyr_down<32>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_pyr_pair);
+    return e == cudaSuccess ? 0 : -1;
+}
