@@ -39,7 +39,8 @@
 extern "C" {
 #endif
 
-#define AVB_ABI_VERSION 3   /* 3: + avb_store_*, avb_process_frame_gather, avb_enqueue_frame_gather (structs unchanged since 2) */
+#define AVB_ABI_VERSION 4   /* 3: + avb_store_*, avb_process_frame_gather, avb_enqueue_frame_gather; 4: + avb_get_result_prev
+                             * (result blocks double-buffered by frame parity); structs unchanged since 2 */
 
 #define AVB_OK              0
 #define AVB_E_INVALID      -1   /* bad argument / unsupported configuration */
@@ -162,10 +163,16 @@ int  avb_enqueue_frame_gather(avb_ctx* ctx, const uint8_t* const* d_images, cons
                               const double* R_p_c1);
 
 /* Results of the last frame for stream s (pointers into pinned host memory, valid until the
- * next avb_process_frame): ids[n], meas[n*4] = u0 v0 u1 v1 (normalized coords; u0,v0 carry the
+ * frame after next: two blocks, alternating by frame parity): ids[n], meas[n*4] = u0 v0 u1 v1 (normalized coords; u0,v0 carry the
  * f64 result, u1,v1 the f32-rounded one, as the reference publishes them). */
 int  avb_get_result(avb_ctx* ctx, int s, const avb_frame_header** hdr,
                     const int64_t** ids, const double** meas);
+/* The same for the frame BEFORE the last one enqueued.  The result blocks are double-buffered by frame parity, so a
+ * sweep driver may enqueue step k+1 (avb_enqueue_frame_gather) as soon as step k has completed (avb_sync) and read
+ * step k's results here while k+1 runs (the reference's runs have no such coupling: every run is a process of its
+ * own, run.bat:4-12).  Valid until the frame after next is enqueued. */
+int  avb_get_result_prev(avb_ctx* ctx, int s, const avb_frame_header** hdr,
+                         const int64_t** ids, const double** meas);
 
 /* State read-back for stream s in grid order (pipeline.prev_features after the roll):
  * cell[n], lifetime[n], cam0_xy[n*2], cam1_xy[n*2] (pixels, f32). Any pointer may be NULL. */

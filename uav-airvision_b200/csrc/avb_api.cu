@@ -94,7 +94,9 @@ struct avb_ctx {
     cudaStream_t st = nullptr, st_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     uint8_t* h_in = nullptr;        // pinned: one input block (images + H)
-    uint8_t* h_out = nullptr;       // pinned: S result blocks
+    uint8_t* h_out[2] = {nullptr, nullptr};   // pinned: S result blocks per frame parity (the results of frame k stay
+                                    // readable while frame k+1 runs: a driver launches k+1 first and reads k behind it)
+    uint8_t* d_out[2] = {nullptr, nullptr};   // what k_finish of a parity writes: the mapped host block (zc_out) or the device mirror
     bool zc_out = false;            // k_finish writes the result blocks straight into h_out (mapped): no D2H copy node
     size_t out_stride = 0;
     int parity = 1;                 // parity of the current frame; the first frame lands in parity 0
@@ -347,15 +349,20 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     // disappears from the frame.  Many streams: one bulk DMA of the device mirror is cheaper than scattered stores.
     c->zc_out = S * c->out_stride <= (size_t)64 * 1024;
     if (const char* e = getenv("AVB_ZC_OUT")) c->zc_out = atoi(e) != 0;
-    CKC(cudaHostAlloc((void**)&c->h_out, S * c->out_stride, cudaHostAllocMapped));
-    memset(c->h_out, 0, S * c->out_stride);
-    if (c->zc_out) {
-        void* dp = nullptr;
-        CKC(cudaHostGetDevicePointer(&dp, c->h_out, 0));
-        d.out = static_cast<uint8_t*>(dp);
-    } else {
-        CKC(dalloc(c, &d.out, S * c->out_stride));
+    for (int q = 0; q < 2; ++q) {
+        CKC(cudaHostAlloc((void**)&c->h_out[q], S * c->out_stride, cudaHostAllocMapped));
+        memset(c->h_out[q], 0, S * c->out_stride);
+        if (c->zc_out) {
+            void* dp = nullptr;
+            CKC(cudaHostGetDevicePointer(&dp, c->h_out[q], 0));
+            c->d_out[q] = static_cast<uint8_t*>(dp);
+        } else if (q == 0) {
+            CKC(dalloc(c, &c->d_out[0], S * c->out_stride));   // one device mirror: its D2H copy is stream-ordered before the next k_finish
+        } else {
+            c->d_out[1] = c->d_out[0];
+        }
     }
+    d.out = c->d_out[0];
     CKC(cudaHostAlloc((void**)&c->h_in, inb, cudaHostAllocDefault));
     memset(c->h_in, 0, inb);
     avb_fill_rotations(c, c->h_in, nullptr, nullptr);      // identity until the caller provides rotations
@@ -447,7 +454,8 @@ extern "C" void avb_destroy(avb_ctx* c) {
     for (void* p : {(void*)c->s_a, (void*)c->s_b, (void*)c->s_c, (void*)c->s_st, (void*)c->s_da, (void*)c->s_db, (void*)c->s_R})
         if (p) cudaFree(p);
     if (c->h_in) cudaFreeHost(c->h_in);
-    if (c->h_out) cudaFreeHost(c->h_out);
+    for (uint8_t* h : c->h_out)
+        if (h) cudaFreeHost(h);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
@@ -491,6 +499,13 @@ extern "C" int avb_reset(avb_ctx* c) {
 // ---- the frame ------------------------------------------------------------------------------------
 
 // The steady-state chain in two parts for the host-image path.  Part 1 needs the cam0 images only.
+// DevState as the kernels of parity p see it (k_finish writes that parity's result block)
+static DevState dev_state(const avb_ctx* c, int p) {
+    DevState d = c->d;
+    d.out = c->d_out[p];
+    return d;
+}
+
 static void enqueue_cam0_part(avb_ctx* c, int p, cudaStream_t st) {
     launch_clear_frame(c->g, c->d, st);
     launch_fast(c->g, c->d, c->maps, p, st);
@@ -501,7 +516,7 @@ static void enqueue_cam0_part(avb_ctx* c, int p, cudaStream_t st) {
 // where k_select reads the FAST buckets.
 static void enqueue_rest_part(avb_ctx* c, int p) {
     const Geom& g = c->g;
-    const DevState& d = c->d;
+    const DevState d = dev_state(c, p);
     const bool spec = g.spec_k > 0;
     launch_pyramid(g, d, c->maps, p, c->st);
     cudaEventRecord(c->ev_fork, c->st);
@@ -521,7 +536,7 @@ static void enqueue_rest_part(avb_ctx* c, int p) {
 // already be (or be ordered before this on c->st) in d.in[p].
 static void enqueue_chain(avb_ctx* c, int p, bool first) {
     const Geom& g = c->g;
-    const DevState& d = c->d;
+    const DevState d = dev_state(c, p);
     cudaEventRecord(c->ev_fork, c->st);
     cudaStreamWaitEvent(c->st_side, c->ev_fork, 0);
     launch_clear_frame(g, d, c->st_side);
@@ -559,8 +574,8 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     if (c->first_frame) return fail(c, AVB_E_STATE, "profile the steady state: process frame 0 first");
     CK(cudaSetDevice(c->cfg.device));
     const Geom& g = c->g;
-    const DevState& d = c->d;
     const int p = c->parity ^ 1;
+    const DevState d = dev_state(c, p);
     cudaEvent_t ev[11];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(c->st));
@@ -586,7 +601,7 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     launch_finish(g, d, p, 0, c->st);
     CK(cudaEventRecord(ev[7], c->st));
     CK(cudaEventRecord(ev[8], c->st));
-    if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+    if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out[p], c->d_out[p], (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev[9], c->st));
     CK(cudaEventRecord(c->ev_t1, c->st));
     CK(cudaGetLastError());
@@ -615,7 +630,7 @@ static int build_graphs(avb_ctx* c) {
             if (variant == 0)   // device variant: the block was placed by a D2D copy ordered before the launch
                 cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st);
             enqueue_chain(c, p, false);
-            if (!c->zc_out) cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
+            if (!c->zc_out) cudaMemcpyAsync(c->h_out[p], c->d_out[p], (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
             CK(cudaStreamEndCapture(c->st, &graph));
             cudaGraphExec_t exec = nullptr;
             CK(cudaGraphInstantiate(&exec, graph, 0));
@@ -634,7 +649,7 @@ static int build_graphs(avb_ctx* c) {
         c->graph_cam0[p] = exec;
         CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
         enqueue_rest_part(c, p);
-        if (!c->zc_out) cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
+        if (!c->zc_out) cudaMemcpyAsync(c->h_out[p], c->d_out[p], (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st);
         CK(cudaStreamEndCapture(c->st, &graph));
         CK(cudaGraphInstantiate(&exec, graph, 0));
         CK(cudaGraphDestroy(graph));
@@ -695,7 +710,7 @@ static int run_frame(avb_ctx* c, int variant, bool wait) {
     } else {
         if (variant == 0) CK(cudaMemcpyAsync(c->d.in[p], c->h_in, inb, cudaMemcpyHostToDevice, c->st));
         enqueue_chain(c, p, c->first_frame);
-        if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out, c->d.out, (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
+        if (!c->zc_out) CK(cudaMemcpyAsync(c->h_out[p], c->d_out[p], (size_t)g.S * c->out_stride, cudaMemcpyDeviceToHost, c->st));
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev_t1, c->st));
@@ -925,20 +940,26 @@ extern "C" int avb_last_frame_ms(avb_ctx* c, float* ms) {
     return AVB_OK;
 }
 
-extern "C" int avb_get_result(avb_ctx* c, int s, const avb_frame_header** hdr, const int64_t** ids, const double** meas) {
+static int result_at(avb_ctx* c, int s, int parity, const avb_frame_header** hdr, const int64_t** ids, const double** meas) {
     if (!c || s < 0 || s >= c->g.S) return AVB_E_INVALID;
     if (!c->have_frame) return fail(c, AVB_E_STATE, "no frame processed yet");
-    uint8_t* b = c->h_out + (size_t)s * c->out_stride;
+    uint8_t* b = c->h_out[parity] + (size_t)s * c->out_stride;
     if (hdr) *hdr = reinterpret_cast<const avb_frame_header*>(b);
     if (ids) *ids = reinterpret_cast<const int64_t*>(out_ids(b));
     if (meas) *meas = out_meas(b, c->g.NMAX);
     return AVB_OK;
 }
+extern "C" int avb_get_result(avb_ctx* c, int s, const avb_frame_header** hdr, const int64_t** ids, const double** meas) {
+    return result_at(c, s, c ? c->parity : 0, hdr, ids, meas);
+}
+extern "C" int avb_get_result_prev(avb_ctx* c, int s, const avb_frame_header** hdr, const int64_t** ids, const double** meas) {
+    return result_at(c, s, c ? c->parity ^ 1 : 0, hdr, ids, meas);
+}
 
 extern "C" int avb_get_features(avb_ctx* c, int s, int32_t* cell, int32_t* lifetime, float* cam0_xy, float* cam1_xy) {
     if (!c || s < 0 || s >= c->g.S) return AVB_E_INVALID;
     if (!c->have_frame) return fail(c, AVB_E_STATE, "no frame processed yet");
-    uint8_t* b = c->h_out + (size_t)s * c->out_stride;
+    uint8_t* b = c->h_out[c->parity] + (size_t)s * c->out_stride;
     const size_t n = (size_t) reinterpret_cast<const avb_frame_header*>(b)->n_features;
     const int nm = c->g.NMAX;
     if (cell) memcpy(cell, out_cell(b, nm), n * 4);

@@ -15,7 +15,7 @@ EXPORTS = (
     'avb_reset', 'avb_input_staging', 'avb_input_block_bytes', 'avb_input_rotation_offset',
     'avb_input_rotation_stride',
     'avb_fill_rotations', 'avb_process_frame', 'avb_process_frame_device', 'avb_enqueue_frame_device',
-    'avb_sync', 'avb_get_result', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
+    'avb_sync', 'avb_get_result', 'avb_get_result_prev', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
     'avb_undistort_points', 'avb_distort_points', 'avb_two_point_ransac', 'avb_last_frame_ms', 'avb_kernels_per_frame',
     'avb_cuda_stream', 'avb_time_pyramid', 'avb_profile_frame_device', 'avb_get_geometry',
@@ -89,6 +89,7 @@ def load():
     lib.avb_process_frame_device.argtypes = [vp, vp]
     lib.avb_enqueue_frame_device.argtypes = [vp, vp]
     lib.avb_get_result.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.avb_get_result_prev.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.avb_get_features.argtypes = [vp, ip, i32p, i32p, f32p, f32p]
     lib.avb_upload_stereo.argtypes = [vp, ip, u8p, u8p, ip]
     lib.avb_download_level.argtypes = [vp, ip, ip, ip, u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -114,7 +115,7 @@ def load():
     lib.avb_store_image.restype = C.c_void_p
     lib.avb_process_frame_gather.argtypes = [vp, vp, f64p, f64p]
     lib.avb_enqueue_frame_gather.argtypes = [vp, vp, f64p, f64p]
-    if lib.avb_abi_version() != 3:
+    if lib.avb_abi_version() != 4:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
     return lib
@@ -233,6 +234,7 @@ class Context:
         self.staging = self._staging_block[:img_bytes].reshape(self.S, 2, self.height, self.width)
         self._ident = np.tile(np.eye(3).reshape(-1), self.S)
         self._views = {}
+        self._blocks = {}
         self.stereo_threshold = float(ac.stereo_threshold)
         self._staged_frames = 0          # frames made current through begin_frame (stage-class flow)
         self._cur0 = None
@@ -297,35 +299,40 @@ class Context:
         self._ck(self._lib.avb_sync(self._h))
 
     def result(self, s=0):
-        """(header record, ids int64[n], meas float64[n,4]) -- views into pinned memory, valid until the
-        next frame."""
-        v = self._views.get(s)
+        """(header record, ids int64[n], meas float64[n,4]) of the last frame -- views into pinned memory, valid until the
+        frame after next (the result blocks alternate by frame parity)."""
+        hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.avb_get_result(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
+        v = self._views.get(hp.value)
         if v is None:
-            hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            self._ck(self._lib.avb_get_result(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
             hdr = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(48,)).view(HEADER_DTYPE)
             ids = np.ctypeslib.as_array(C.cast(ip_, C.POINTER(C.c_int64)), shape=(self.capacity,))
             meas = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_double)), shape=(self.capacity, 4))
             v = (hdr, ids, meas)
-            self._views[s] = v
+            self._views[hp.value] = v
         hdr, ids, meas = v
         n = int(hdr['n_features'][0])
         return hdr[0], ids[:n], meas[:n]
 
-    def result_block(self):
-        """The result blocks of all S streams as one array: (block uint8[S, stride] -- a view of the pinned memory,
-        valid until the next frame --, ids offset, meas offset).  Stream s: header at block[s, :48] (HEADER_DTYPE), ids
-        int64[capacity] at the ids offset, meas float64[capacity, 4] at the meas offset."""
-        if getattr(self, '_block', None) is None:
-            def ptrs(s):
-                hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
-                self._ck(self._lib.avb_get_result(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
-                return hp.value, ip_.value, mp.value
-            h0, i0, m0 = ptrs(0)
+    def result_block(self, prev=False):
+        """The result blocks of all S streams as one array: (block uint8[S, stride] -- a view of the pinned memory --,
+        ids offset, meas offset).  Stream s: header at block[s, :48] (HEADER_DTYPE), ids int64[capacity] at the ids
+        offset, meas float64[capacity, 4] at the meas offset.  prev=True: the frame before the last one enqueued (what a
+        driver reads while the next frame runs, avb_get_result_prev)."""
+        fn = self._lib.avb_get_result_prev if prev else self._lib.avb_get_result
+
+        def ptrs(s):
+            hp, ip_, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self._ck(fn(self._h, s, C.byref(hp), C.byref(ip_), C.byref(mp)))
+            return hp.value, ip_.value, mp.value
+        h0, i0, m0 = ptrs(0)
+        blk = self._blocks.get(h0)
+        if blk is None:
             stride = (ptrs(1)[0] - h0) if self.S > 1 else (m0 - h0) + self.capacity * 32
-            blk = np.ctypeslib.as_array(C.cast(C.c_void_p(h0), C.POINTER(C.c_uint8)), shape=(self.S * stride,))
-            self._block = (blk.reshape(self.S, stride), i0 - h0, m0 - h0)
-        return self._block
+            a = np.ctypeslib.as_array(C.cast(C.c_void_p(h0), C.POINTER(C.c_uint8)), shape=(self.S * stride,))
+            blk = (a.reshape(self.S, stride), i0 - h0, m0 - h0)
+            self._blocks[h0] = blk
+        return blk
 
     def features(self, s=0):
         """Grid-ordered state of stream s: (cell, lifetime, cam0_xy, cam1_xy)."""

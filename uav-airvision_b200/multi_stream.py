@@ -99,7 +99,7 @@ class MultiStreamFrontEnd:
         self.next_feature_id = [0] * self.S
         self.num_features = [defaultdict(int) for _ in range(self.S)]
         self._R = np.empty((2, self.S, 3, 3))          # [cam][stream]; cam 1 is passed on only with RANSAC on
-        self._steps_prepared, self._prepared, self._in_flight = 0, None, None     # store-fed steps (sweep.py)
+        self._steps_prepared, self._prepared, self._in_flight, self._done = 0, None, None, None   # store-fed steps (sweep.py)
 
     def close(self):
         self.ctx.close()
@@ -169,12 +169,21 @@ class MultiStreamFrontEnd:
         self._in_flight = msgs
 
     def end_step_from_store(self):
-        """Waits for the step begun last and returns its results (see step_from_store).  The S result blocks leave the
-        pinned memory in ONE copy (the next step may be launched right after this returns); the per-stream arrays are
-        views into that copy."""
-        msgs, self._in_flight = self._in_flight, None
+        """Waits for the step begun last and returns its results (see step_from_store)."""
+        self.wait_step()
+        return self.take_results(prev=False)
+
+    def wait_step(self):
+        """Blocks until the step begun last has completed (its result block is in host memory)."""
+        self._done, self._in_flight = self._in_flight, None
         self.ctx.sync()
-        blk, ids_off, meas_off = self.ctx.result_block()
+
+    def take_results(self, prev):
+        """Results of the step completed last.  `prev=True`: the NEXT step has already been begun (its chain runs while
+        this reads): libavb keeps the result blocks of two consecutive frames (avb_get_result_prev).  The S result
+        blocks leave the pinned memory in ONE copy; the per-stream arrays are views into that copy."""
+        msgs, self._done = self._done, None
+        blk, ids_off, meas_off = self.ctx.result_block(prev=prev)
         cap = self.ctx.capacity
         blk = blk.copy()
         hdr = blk[:, :_native.HEADER_DTYPE.itemsize].view(_native.HEADER_DTYPE)[:, 0]

@@ -141,10 +141,13 @@ def run_sweep(config, sequences, offsets_s, device=0, n_steps=None, estimator_wo
                 t_mark = time.perf_counter()
             nxt = host_side(k + 1) if k + 1 < steps else None
             t0 = time.perf_counter()
-            out = fe.end_step_from_store()
+            fe.wait_step()
             fe_s += time.perf_counter() - t0 if k >= warmup_steps else 0.0
+            # step k+1 goes to the GPU BEFORE step k's results are taken apart: the result blocks of two consecutive
+            # frames are both kept (avb_get_result_prev), so the GPU does not idle through the host's copy and loops
             if nxt is not None:
                 fe.begin_step_from_store(nxt[0])
+            out = fe.take_results(prev=nxt is not None)
             for s, (ts, ids, meas) in enumerate(out):
                 n_feat[s, k] = len(ids)
             if pool is not None:
