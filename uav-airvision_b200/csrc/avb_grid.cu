@@ -331,19 +331,27 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
     const GridTable prev = d.grid[parity ^ 1], cur = d.grid[parity];
     const size_t base = (size_t)s * g.NMAX;
 
+    // Every global load of phase 1 is issued before anything waits on one (the kernel is a chain of memory round trips:
+    // the first slice of the table and of the candidate lists -- all there is for up to 1024 slots / 32 cells per CTA --
+    // the id counter and the frame index travel together)
+    const long long next_id = d.next_id[(parity ^ 1) * g.S + s];
+    const int c_first = (!first_frame && tid < g.NMAX) ? d.t_cell[base + tid] : -1;
+    const int li_first = (!first_frame && tid < g.NMAX) ? prev.life[base + tid] : 0;
+    const int nc_first = warp < g.NC ? d.c_count[s * g.NC + warp] : 0;
+    const uint8_t ok_first = (warp < g.NC && lane < g.gmax) ? d.c_ok[base + warp * g.gmax + lane] : (uint8_t)0;
     for (int c = tid; c <= g.NC; c += FIN_THREADS) cnt[c] = 0;
     if (tid == 0) s_fresh = 0;
     __syncthreads();
     for (int i = tid; i < g.NMAX; i += FIN_THREADS) {
-        const int c = first_frame ? -1 : d.t_cell[base + i];
-        const int li = first_frame ? 0 : prev.life[base + i];
+        const int c = i == tid ? c_first : (first_frame ? -1 : d.t_cell[base + i]);
+        const int li = i == tid ? li_first : (first_frame ? 0 : prev.life[base + i]);
         cellof[i] = c;
         slife[i] = li;
         if (c >= 0) atomicAdd(&cnt[c], 1);
     }
     for (int c = warp; c < g.NC; c += FIN_THREADS / 32) {       // new features per cell
-        const int nc = d.c_count[s * g.NC + c];                 // both loads in flight together: c_ok past the count is
-        const uint8_t okv = lane < g.gmax ? d.c_ok[base + c * g.gmax + lane] : 0;     // stale but masked
+        const int nc = c == warp ? nc_first : d.c_count[s * g.NC + c];          // c_ok past the count is stale but masked
+        const uint8_t okv = c == warp ? ok_first : (lane < g.gmax ? d.c_ok[base + c * g.gmax + lane] : (uint8_t)0);
         const unsigned bn = __ballot_sync(0xffffffffu, lane < nc && okv);
         if (lane == 0) {
             nnew[c] = min(__popc(bn), g.gmin);
@@ -392,7 +400,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(const __grid_constant__ 
     __syncthreads();
     const int total = off_cnt[g.NC], total_new = off_new[g.NC], has_new = s_fresh;
     uint8_t* ob = d.out + (size_t)s * out_stride_bytes(g.NMAX);
-    const long long next_id = d.next_id[(parity ^ 1) * g.S + s];
 #ifdef AVB_DEBUG_CLOCKS
     dbg_t[2] = clock64();
 #endif
