@@ -87,7 +87,7 @@ def stage_bytes(w, h, max_level, S):
         lw, lh = (lw + 1) // 2, (lh + 1) // 2
         px.append(lw * lh)
     return {'input_copy': 2 * S * 2 * px[0], 'pyramid': 2 * S * sum(px[l - 1] + px[l] for l in range(1, max_level + 1)),
-            'clear+fast': S * px[0]}
+            'fast': S * px[0]}
 
 
 def algorithmic_bytes_per_frame(w, h, max_level, n_feat):

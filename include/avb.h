@@ -224,7 +224,7 @@ int  avb_kernels_per_frame(const avb_ctx* ctx);
 /* Raw CUDA stream handle (cudaStream_t) so callers can bracket work with their own events. */
 void* avb_cuda_stream(avb_ctx* ctx);
 /* Instrumented steady-state frame from a device-resident input block: kernels run serialised with a CUDA
- * event after every stage.  stage_ms[9] = input copy, clear+FAST, pyramid (all levels), track, select,
+ * event after every stage.  stage_ms[9] = input copy, FAST, pyramid (all levels), track, select,
  * stereo match of new candidates, finish (grid update + publish), 0 (reserved), result copy.  Advances the stream
  * like a frame. */
 int  avb_profile_frame_device(avb_ctx* ctx, const uint8_t* d_block, float* stage_ms);

@@ -79,10 +79,10 @@ def _offset_runs(cfg, S, n_steps, stride, skw, width=752, height=480):
     return multi, single, frames, Rs, kernels
 
 
-def _port_run(cfg, st, first, n_steps):
+def _port_run(cfg, st, first, n_steps, backend='cv2'):
     """The oracle port on frames first .. first + n_steps - 1 of the sequence (IMU samples older than the run's first
     frame never reach a window: imu_processor.py:28-48 starts at t_prev - 0.01)."""
-    fe = FrontEndPort(cfg, backend='cv2')
+    fe = FrontEndPort(cfg, backend=backend)
     out, k = [], 0
     for kind, msg in st.events():
         if kind == 'imu':
@@ -140,7 +140,7 @@ def test_offset_runs_in_one_context_equal_single_contexts_and_the_port(S):
           f'0, {S // 2}, {S - 1} equal the port (worst {worst:.3g} px); {lost} features lost in stereo matching, {new_ids} ids handed out')
     assert lost > 0
     if S == 64:
-        assert kernels == 10            # clear, fast, 3 x k_pyr_down, track, select, 2 candidate rounds, finish
+        assert kernels == 9             # fast, 3 x k_pyr_down, track, select, 2 candidate rounds, finish
 
 
 def test_forced_two_round_candidates_and_bulk_result_copy_on_a_small_context(monkeypatch):
@@ -159,7 +159,7 @@ def test_forced_two_round_candidates_and_bulk_result_copy_on_a_small_context(mon
     ctx = _native.Context(cfg, 752, 480, num_streams=1)
     got = []
     try:
-        assert ctx.kernels_per_frame() == 2 + 3 + 1 + 1 + 2 + 1
+        assert ctx.kernels_per_frame() == 1 + 3 + 1 + 1 + 2 + 1
         for k in range(n):
             ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
             got.append(_snapshot(ctx, 0))
@@ -193,13 +193,15 @@ def test_per_level_pyramid_kernel_on_every_level(w, h, levels, monkeypatch):
             c.close()
 
 
-@pytest.mark.parametrize('spec_k', ['0', '2', '16'])
-def test_speculative_candidate_matching_equals_the_port(spec_k, monkeypatch):
+@pytest.mark.parametrize('spec_k,spec_wpf', [('0', '1'), ('2', '1'), ('16', '1'), ('16', '4')])
+def test_speculative_candidate_matching_equals_the_port(spec_k, spec_wpf, monkeypatch):
     """Few streams: the candidates' stereo matches run speculatively beside k_track (k_select mode 2 + k_spec_match), and
     k_select only looks its candidates up.  AVB_SPEC_K=2 keeps the list shorter than grid_max, so that most candidates
     MISS it and are matched by k_select itself (one warp each); 0 switches speculation off; 16 is the default.
-    All three must publish what the port publishes on 30 lossy frames."""
+    AVB_SPEC_WPF=4 gives every speculative candidate four warps (measured slower at 16 per cell: 56 us against 46 us, the
+    launch no longer fits the GPU at once).  All must publish what the port publishes on 30 lossy frames."""
     monkeypatch.setenv('AVB_SPEC_K', spec_k)
+    monkeypatch.setenv('AVB_SPEC_WPF', spec_wpf)
     from image_processing import _native
     cfg = config_c2()
     n = 30
@@ -210,11 +212,55 @@ def test_speculative_candidate_matching_equals_the_port(spec_k, monkeypatch):
     ctx = _native.Context(cfg, 752, 480, num_streams=1)
     got = []
     try:
-        assert ctx.kernels_per_frame() == (8 if spec_k == '0' else 9)
+        assert ctx.kernels_per_frame() == (7 if spec_k == '0' else 8)
         for k in range(n):
             ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
             got.append(_snapshot(ctx, 0))
     finally:
         ctx.close()
     worst = _assert_equals_port(got, _port_run(cfg, st, 0, n), f'speculation k={spec_k}')
-    print(f'AVB_SPEC_K={spec_k}: 30 lossy frames equal the port (worst {worst:.3g} px), {got[-1]["hdr"][1]} ids handed out')
+    print(f'AVB_SPEC_K={spec_k} AVB_SPEC_WPF={spec_wpf}: 30 lossy frames equal the port (worst {worst:.3g} px), {got[-1]["hdr"][1]} ids handed out')
+
+
+_PORT_CACHE = {}
+
+
+@pytest.mark.parametrize('wpf', ['4', '1'])
+def test_black_and_white_sequence_takes_the_wide_sum_path_and_equals_the_port(wpf, monkeypatch):
+    """Black/white blobs with sharp edges: the structure-tensor sums of nearly every window exceed LK_NARROW_MAX, so the
+    LK kernels of the frame chain (four warps per feature and one warp per feature) reduce their sums in two exact
+    halves instead of one 32-bit REDUX (avb_lk.cuh).  6 frames against the port on its numpy backend (oracle/cv_semantics:
+    the same exact-sum arithmetic -> identical features, positions bit for bit).  cv2 itself sums these large products
+    in float32 in SIMD-lane order and loses ONE of the 298 features of frame 2 that exact sums keep (status agreement
+    99.7 %, inside BASELINE's 99.5 % bar); ids are sequential, so the feature sets differ from there on and the cv2
+    backend can only be compared up to that frame."""
+    monkeypatch.setenv('AVB_WPF', wpf)
+    from image_processing import _native
+    cfg = config_c2()
+    n = 6
+    st = SlidingTextureStream(n_frames=n, seed=11, sigma=1.5, drift=(2.0, 1.0), gyro=(0.01, -0.02, 0.02))
+    st._tex = np.where(st._tex > 127.5, 255.0, 0.0)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    ix, _ = cs.scharr(frames[0].cam0_image)
+    sq = np.pad(ix.astype(np.int64) ** 2, ((8, 7), (8, 7))).cumsum(0).cumsum(1)
+    win = sq[15:, 15:] - sq[:-15, 15:] - sq[15:, :-15] + sq[:-15, :-15]
+    assert np.mean(win > 3.0e8) > 0.9
+    Rs = _rotations(cfg, st)
+    ctx = _native.Context(cfg, 752, 480, num_streams=1)
+    got = []
+    try:
+        for k in range(n):
+            ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
+            got.append(_snapshot(ctx, 0))
+    finally:
+        ctx.close()
+    if 'bw' not in _PORT_CACHE:                               # the same reference for both lane mappings
+        _PORT_CACHE['bw'] = _port_run(cfg, st, 0, n, backend='numpy')
+    worst = _assert_equals_port(got, _PORT_CACHE['bw'], f'black/white wpf={wpf}')
+    assert worst == 0.0, worst
+    cv = _port_run(cfg, st, 0, 2, backend='cv2')
+    worst_cv = _assert_equals_port(got[:2], cv, f'black/white wpf={wpf} vs cv2')
+    print(f'AVB_WPF={wpf}: {n} black/white frames identical to the exact-sum port, first 2 within {worst_cv:.3g} px of the cv2 '
+          f'port; {got[-1]["hdr"][0]} features, {got[-1]["hdr"][1]} ids handed out')
+    assert got[-1]['hdr'][0] > 100

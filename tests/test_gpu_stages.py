@@ -194,6 +194,72 @@ def test_klt_c3_five_levels_textureless_offframe():
     assert np.mean(d <= 0.01) >= 0.995               # random points include ill-conditioned windows
 
 
+def _box_sum(a, r=7):
+    """Sum over the (2r+1)^2 window around every pixel (zero outside)."""
+    c = np.pad(a, ((r + 1, r), (r + 1, r))).cumsum(0).cumsum(1)
+    n = 2 * r + 1
+    return c[n:, n:] - c[:-n, n:] - c[n:, :-n] + c[:-n, :-n]
+
+
+def _contrast_frames(kind):
+    """Two 752x480 frames outside the range of the bench texture.  'binary': black/white blobs with sharp edges (structure
+    tensor sums above LK_NARROW_MAX = 3e8 -> the wide, two-half exact reduction of avb_lk.cuh); 'faint': mid-grey with
+    one or two grey levels of texture, in bands of rising amplitude (minimum eigenvalue around cv2's 1e-4 threshold ->
+    the exact sqrt/division branch of lk_tensor_f instead of its band test)."""
+    st = SlidingTextureStream(n_frames=2, seed=11, sigma=1.5, drift=(2.0, 1.0))
+    if kind == 'binary':
+        st._tex = np.where(st._tex > 127.5, 255.0, 0.0)
+    else:
+        amp = np.linspace(0.2, 12.0, st._tex.shape[1])[None, :]
+        st._tex = 128.0 + (st._tex - 127.5) / 127.5 * amp
+    return st.frame(0), st.frame(1)
+
+
+@pytest.mark.parametrize('kind', ['binary', 'faint'])
+def test_klt_outside_the_bench_texture_range(ctx752, kind):
+    """The LK shortcuts (narrow sums, eigenvalue band test) have an exact path behind them for the inputs they do not
+    cover; these images take it.  Against the numpy oracle: identical; against cv2: the BASELINE tolerance."""
+    f0, f1 = _contrast_frames(kind)
+    ix, iy = cs.scharr(f0.cam0_image)
+    q11 = _box_sum(ix.astype(np.int64) ** 2)
+    if kind == 'binary':
+        assert q11.max() > 3.0e8, q11.max()                # integer template sums are on the same scale as Scharr^2
+    else:
+        lam = q11[20:-20, 20:-20] / 2.0 ** 20 / 225.0 / 2
+        assert lam.min() < 1e-4 < lam.max()
+    ctx752.upload(f0.cam0_image, f0.cam1_image)
+    ctx752.build_pyramids()
+    ctx752.advance()
+    ctx752.upload(f1.cam0_image, f1.cam1_image)
+    ctx752.build_pyramids()
+    g = np.random.default_rng(3)
+    if kind == 'binary':                                    # windows on the strongest structure first
+        ys, xs = np.unravel_index(np.argsort(q11[10:-10, 10:-10], axis=None)[::-1][:4000:40], q11[10:-10, 10:-10].shape)
+        strong = np.stack([xs + 10, ys + 10], 1).astype(np.float32)
+    else:
+        strong = np.zeros((0, 2), np.float32)
+    pts = np.vstack([strong, g.uniform([8, 8], [744, 472], (2000, 2)).astype(np.float32)])
+    pts += g.uniform(0, 1, pts.shape).astype(np.float32)
+    guess = pts + np.float32([-1.5, -0.7]) + g.normal(0, 0.5, pts.shape).astype(np.float32)
+    q, st = ctx752.klt_track(2, 0, pts, guess)
+    n = 160
+    q_ref, st_ref = cs.lk_track(cs.build_pyramid(f0.cam0_image, 3), cs.build_pyramid(f1.cam0_image, 3), pts[:n], guess[:n])
+    assert np.array_equal(st[:n], st_ref) and np.array_equal(q[:n][st_ref == 1], q_ref[st_ref == 1]), kind
+    assert 0 < st.sum()
+    if kind == 'faint':
+        assert st.sum() < len(st)                           # the faint end of the image is below the threshold
+    if cv2 is not None:
+        lk = dict(winSize=(15, 15), maxLevel=3, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01),
+                  flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        q_cv, st_cv, _ = cv2.calcOpticalFlowPyrLK(f0.cam0_image, f1.cam0_image, pts, guess.copy(), **lk)
+        st_cv = st_cv.reshape(-1)
+        both = (st == 1) & (st_cv == 1)
+        d = np.abs(q - q_cv)[both].max(axis=1)
+        print(f'{kind}: status agreement {(st == st_cv).mean():.4f}, within 0.01 px {np.mean(d <= 0.01):.4f}, '
+              f'max {d.max():.3g}, tracked {both.sum()}')
+        assert (st == st_cv).mean() >= 0.995 and np.mean(d <= 0.01) >= 0.995
+
+
 @pytest.mark.skipif(cv2 is None, reason='cv2 not importable')
 def test_stereo_match_vs_port(ctx752, frames752):
     f0, _ = frames752

@@ -47,7 +47,7 @@ def run(max_iter, levels, wpf, n=14):
     ctx.close()
     med = {a: float(np.median(b)) * 1e3 for a, b in acc.items()}
     print(f'max_iter={max_iter:2d} levels={levels + 1} wpf={wpf}: track {med["track"]:6.1f} us  stereo_new {med["stereo_new"]:6.1f} us  '
-          f'select {med["select"]:5.1f}  pyramid {med["pyramid"]:5.1f}  fast {med["clear+fast"]:5.1f}  features {nfeat}')
+          f'select {med["select"]:5.1f}  pyramid {med["pyramid"]:5.1f}  fast {med["fast"]:5.1f}  features {nfeat}')
 
 
 if __name__ == '__main__':

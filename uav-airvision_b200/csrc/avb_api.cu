@@ -271,6 +271,8 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     // 16 list entries per cell cover gmax candidates unless the mask removes more than 16 - gmax stronger keypoints.
     g.spec_k = g.wpf == 4 ? std::min(std::max(16, g.gmax), std::min(g.KPC, 32)) : 0;
     if (const char* e = getenv("AVB_SPEC_K")) g.spec_k = g.wpf == 4 ? std::min(std::max(atoi(e), 0), std::min(g.KPC, 32)) : 0;
+    g.spec_wpf = 1;
+    if (const char* e = getenv("AVB_SPEC_WPF")) g.spec_wpf = atoi(e) == 4 ? 4 : 1;
     if (g.NMAX > 8192) {
         delete c;
         return fail(nullptr, AVB_E_INVALID, "grid_num*grid_max = %d exceeds 8192", g.NMAX);
@@ -489,6 +491,7 @@ extern "C" int avb_reset(avb_ctx* c) {
     CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)2 * g.S * sizeof(long long), c->st));
     CK(cudaMemsetAsync(c->d.frame_index, 0, (size_t)g.S * sizeof(int), c->st));
     CK(cudaMemsetAsync(c->d.counters, 0, (size_t)g.S * 8 * sizeof(int), c->st));
+    CK(cudaMemsetAsync(c->d.kp_count, 0, (size_t)g.S * g.NC * sizeof(int), c->st));
     CK(cudaStreamSynchronize(c->st));
     c->parity = 1;
     c->first_frame = true;
@@ -507,7 +510,6 @@ static DevState dev_state(const avb_ctx* c, int p) {
 }
 
 static void enqueue_cam0_part(avb_ctx* c, int p, cudaStream_t st) {
-    launch_clear_frame(c->g, c->d, st);
     launch_fast(c->g, c->d, c->maps, p, st);
     if (c->g.spec_k > 0) launch_spec_select(c->g, c->d, st);
 }
@@ -539,8 +541,7 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
     const DevState d = dev_state(c, p);
     cudaEventRecord(c->ev_fork, c->st);
     cudaStreamWaitEvent(c->st_side, c->ev_fork, 0);
-    launch_clear_frame(g, d, c->st_side);
-    launch_fast(g, d, c->maps, p, c->st_side);
+    launch_fast(g, d, c->maps, p, c->st_side);          // the buckets are empty: k_select left them so (avb_grid.cu)
     const bool spec = g.spec_k > 0 && !first;
     if (spec) launch_spec_select(g, d, c->st_side);
     if (!spec) cudaEventRecord(c->ev_join, c->st_side);
@@ -566,7 +567,7 @@ static void enqueue_chain(avb_ctx* c, int p, bool first) {
 }
 
 // Serialised, instrumented variant of the steady-state chain: one event after every stage on c->st.
-// Stage order: 0 input copy | 1 clear+FAST (+ speculative list) | 2 pyramid | 3 track | 4 select | 5 stereo(new) |
+// Stage order: 0 input copy | 1 FAST (+ speculative list) | 2 pyramid | 3 track | 4 select | 5 stereo(new) |
 // 6 finish (grid update + publish) | 7 speculative stereo matches (beside k_track in the real chain; 0 when off) |
 // 8 result copy.  Used by bench.py for the per-kernel roofline; never by the hot path.
 extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, float* stage_ms /*[9]*/) {
@@ -583,7 +584,6 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
     CK(cudaEventRecord(ev[0], c->st));
     CK(cudaMemcpyAsync(c->d.in[p], d_block, in_block_bytes(g), cudaMemcpyDeviceToDevice, c->st));
     CK(cudaEventRecord(ev[1], c->st));
-    launch_clear_frame(g, d, c->st);
     launch_fast(g, d, c->maps, p, c->st);
     if (g.spec_k > 0) launch_spec_select(g, d, c->st);
     CK(cudaEventRecord(ev[2], c->st));
@@ -615,9 +615,9 @@ extern "C" int avb_profile_frame_device(avb_ctx* c, const uint8_t* d_block, floa
 
 extern "C" int avb_kernels_per_frame(const avb_ctx* c) {
     if (!c) return 0;
-    // clear, fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish;
+    // fast, pyramid launches, track, [ransac], select, stereo_candidates (two rounds in throughput mode), finish;
     // with speculation: + the speculative list and its matches, - stereo_candidates
-    return 2 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (c->g.cand_rounds == 2 ? 1 : 0) + (c->g.spec_k > 0 ? 1 : 0);
+    return 1 + avb_pyramid_launches(c->g) + 4 + (c->g.ransac ? 1 : 0) + (c->g.cand_rounds == 2 ? 1 : 0) + (c->g.spec_k > 0 ? 1 : 0);
 }
 
 static int build_graphs(avb_ctx* c) {
@@ -1031,6 +1031,7 @@ extern "C" int avb_fast_detect(avb_ctx* c, int s, const uint8_t* mask, int32_t* 
     std::vector<unsigned> keys((size_t)g.NC * g.KPC);
     CK(cudaMemcpyAsync(counts.data(), c->d.kp_count + (size_t)s * g.NC, g.NC * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(keys.data(), c->d.kp_key + (size_t)s * g.NC * g.KPC, keys.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+    launch_clear_frame(g, c->d, c->st);    // the frame chain expects empty buckets
     CK(cudaStreamSynchronize(c->st));
     std::vector<unsigned long long> all;   // (scan index << 8) | response
     for (int cell = 0; cell < g.NC; ++cell) {

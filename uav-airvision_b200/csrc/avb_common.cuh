@@ -51,6 +51,7 @@ struct Geom {
     int cand_rounds;               // new-feature stereo matching in 1 launch or 2 dense rounds (avb_points.cu)
     int spec_k;                    // > 0 (few streams): the spec_k strongest FAST keypoints of every cell are stereo-matched
                                    // SPECULATIVELY beside k_track; k_select then only looks its candidates up (avb_points.cu)
+    int spec_wpf;                  // warps per speculative candidate (1 or 4)
     int fast_thr;
     int max_iter;
     double min_eig;

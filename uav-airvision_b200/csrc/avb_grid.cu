@@ -10,8 +10,9 @@
 
 #include "avb_lk.cuh"
 
-// FAST bucket counts of the frame.  (The per-frame counters are zeroed by k_finish once it has published them: k_track
-// adds to them on the main branch, which is not ordered against this kernel on the FAST branch.)
+// FAST bucket counts.  Not part of the frame chain: between frames the counts ARE zero -- the last reader of a cell's count
+// (k_select in mode 0 / 1, one CTA per cell) zeroes it, as k_finish does with the per-frame counters -- so k_fast appends
+// without a clearing launch ahead of it.  This kernel serves the stage API (avb_fast_detect), which has no k_select.
 __global__ void k_clear_frame(Geom g, DevState d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < g.S * g.NC) d.kp_count[i] = 0;
@@ -77,6 +78,9 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) k_select(const __grid_constant
 
     if (tid == 0) n_feat = n_miss = 0;
     __syncthreads();
+    // every thread's load of the count is behind the barrier: the final selection of the frame (not the speculative list,
+    // which runs first) leaves the bucket empty for the next frame's k_fast
+    if (mode != 2 && tid == 0) d.kp_count[s * g.NC + cell] = 0;
     if (mode == 0) {
         const int cx0 = (cell % g.cols) * g.gw, cy0 = (cell / g.cols) * g.gh;
         for (int i0 = 0; i0 < g.NMAX; i0 += 2 * 32 * SEL_WARPS) {

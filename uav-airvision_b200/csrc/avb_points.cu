@@ -99,20 +99,27 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOC
     }
 }
 
-// Speculative stereo_match of the spec_k strongest keypoints of every cell (k_select mode 2), one warp each, on the side
-// stream beside k_track.  Same arithmetic as k_stereo_candidates (both lane mappings give bit-identical results).
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, AVB_WPF1_BLOCKS) k_spec_match(const __grid_constant__ Geom g,
+// Speculative stereo_match of the spec_k strongest keypoints of every cell (k_select mode 2) on the side stream beside
+// k_track.  Same arithmetic as k_stereo_candidates (both lane mappings give bit-identical results).  WPF = 4: the chain of
+// one candidate is what this branch's length is made of (all candidates are resident at once), and four warps walk it
+// faster than one.
+template <int WPF>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOCKS : 4) k_spec_match(const __grid_constant__ Geom g,
                                                                                     const __grid_constant__ DevState d, int parity) {
+    __shared__ LKShared sh;
     const int s = blockIdx.y;
-    const int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int t = team_index<WPF>(blockIdx.x);
+    const bool lead = WPF == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0;
     if (t >= g.NC * g.spec_k) return;
-    const int cell = t / g.spec_k, j = t - cell * g.spec_k;
+    // rank-major: the teams of every cell's strongest candidate come first, so that if the launch does not fit the GPU at
+    // once, the candidates most likely to be adopted are not the ones left waiting
+    const int j = t / g.NC, cell = t - j * g.NC;
     if (j >= d.s_n[s * g.NC + cell]) return;
     const size_t idx = ((size_t)s * g.NC + cell) * g.spec_k + j;
     int resp, x, y;
     kp_decode(d.s_key[idx], g.W, resp, x, y);
-    const ChainResult r = feature_chain<1>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, nullptr);
-    if ((threadIdx.x & 31) == 0) {
+    const ChainResult r = feature_chain<WPF>(g, d, s, parity, false, (float)x, (float)y, 0.f, 0.f, &sh);
+    if (lead) {
         d.s_p1[idx] = make_float2(r.x1, r.y1);
         d.s_ok[idx] = r.matched ? 1 : 0;
         if (r.matched) d.s_und[idx] = make_double4(r.u0, r.v0, r.u1, r.v1);
@@ -230,7 +237,10 @@ void launch_stereo_candidates(const Geom& g, const DevState& d, int parity, cuda
     }
 }
 void launch_spec_match(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
-    k_spec_match<<<dim3(teams_grid(g.NC * g.spec_k, 1), g.S), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    if (g.spec_wpf == 4)
+        k_spec_match<4><<<dim3(teams_grid(g.NC * g.spec_k, 4), g.S), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
+    else
+        k_spec_match<1><<<dim3(teams_grid(g.NC * g.spec_k, 1), g.S), 32 * WARPS_PER_BLOCK, 0, st>>>(g, d, parity);
 }
 void launch_stereo_buckets(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid((g.KPC + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, g.NC, g.S);
@@ -266,7 +276,8 @@ int avb_preload_points() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<4>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<4>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_spec_match);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_spec_match<1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_spec_match<4>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_buckets);
     return e == cudaSuccess ? 0 : -1;
 }

@@ -355,7 +355,7 @@ class Context:
     def cuda_stream(self):
         return self._lib.avb_cuda_stream(self._h)
 
-    STAGES = ('input_copy', 'clear+fast', 'pyramid', 'track', 'select', 'stereo_new', 'finish', 'spec_match',
+    STAGES = ('input_copy', 'fast', 'pyramid', 'track', 'select', 'stereo_new', 'finish', 'spec_match',
               'result_copy')
 
     def profile_frame_device(self, d_block_ptr: int):
