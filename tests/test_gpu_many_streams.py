@@ -264,3 +264,24 @@ def test_black_and_white_sequence_takes_the_wide_sum_path_and_equals_the_port(wp
     print(f'AVB_WPF={wpf}: {n} black/white frames identical to the exact-sum port, first 2 within {worst_cv:.3g} px of the cv2 '
           f'port; {got[-1]["hdr"][0]} features, {got[-1]["hdr"][1]} ids handed out')
     assert got[-1]['hdr'][0] > 100
+
+
+def test_ragged_streams_some_dark_some_full_in_one_launch():
+    """Eight offset runs of a sequence whose frames 6 and 7 are flat grey and whose frame 8 is half flat: in the same
+    launch some streams hold 300 features, some none at all (empty tables, empty FAST buckets, empty result blocks),
+    some are refilling an empty grid.  Every stream equals its single-stream context bit for bit and the port."""
+    cfg = config_c2()
+    S, n_steps, stride = 8, 8, 1
+    skw = dict(seed=4, gyro=(0.01, 0.0, -0.02), blackout={6: 1.0, 7: 1.0, 8: 0.53})
+    multi, single, frames, Rs, kernels = _offset_runs(cfg, S, n_steps, stride, skw)
+    for s in range(S):
+        _assert_equal_runs(multi[s], single[s], f'ragged stream {s}')
+    st = SlidingTextureStream(n_frames=len(frames), **skw)
+    st.frames = lambda: iter(frames)
+    worst = 0.0
+    for s in (0, 3, 6, 7):                          # stream 6 STARTS on a dark frame, stream 7 too (frame 7)
+        worst = max(worst, _assert_equals_port(multi[s], _port_run(cfg, st, stride * s, n_steps), f'ragged stream {s}'))
+    counts = [[f['hdr'][0] for f in multi[s]] for s in range(S)]
+    print(f'ragged: features per step, stream 0 {counts[0]}, stream 3 {counts[3]}, stream 6 {counts[6]}; worst {worst:.3g} px')
+    assert any(0 in c and 300 in c for c in counts)
+    assert any(counts[a][k] == 0 and counts[b][k] >= 299 for k in range(n_steps) for a in range(S) for b in range(S))

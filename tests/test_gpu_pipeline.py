@@ -154,7 +154,7 @@ def test_multi_stream_context_equals_single_streams():
     c.close()
 
 
-@pytest.mark.parametrize('name', ['ref_default_s0', 'ref_c1_gyro_s2'])
+@pytest.mark.parametrize('name', ['ref_default_s0', 'ref_c1_gyro_s2', 'ref_c2_dark_s4'])
 def test_staged_pipeline_matches_reference_golden(name, golden_dir):
     """mode='staged' = the reference's own orchestration over this package's stage classes (PyramidBuilder,
     StereoMatcher, FeatureInitializer, FeatureTracker, FeatureAdder, FeaturePruner, FeaturePublisher), every stage a
@@ -262,12 +262,12 @@ def test_multi_stream_front_end_replay_equals_single_pipelines():
     fe.close()
 
 
+@pytest.mark.parametrize('name', ['ref_c2_s1', 'ref_c2_dark_s4'])
 @pytest.mark.parametrize('wpf', ['1', '4'])
-def test_both_lk_lane_mappings_match_reference_golden(wpf, golden_dir, monkeypatch):
+def test_both_lk_lane_mappings_match_reference_golden(wpf, name, golden_dir, monkeypatch):
     """The throughput mapping (one warp per feature, packed loads + dp2a) and the latency mapping (four warps per
     feature, parallel per-level templates) are the same arithmetic: both must reproduce the reference's dumps."""
     monkeypatch.setenv('AVB_WPF', wpf)
-    name = 'ref_c2_s1'
     g = np.load(os.path.join(golden_dir, name + '.npz'))
     gr, gc, gmin, gmax, skw = CASES[name]
     cfg = FrontEndConfig(grid_row=gr, grid_col=gc, grid_min=gmin, grid_max=gmax)
@@ -276,7 +276,7 @@ def test_both_lk_lane_mappings_match_reference_golden(wpf, golden_dir, monkeypat
     ref = [dict(ids=g[f'f{k}_ids'], cell=g[f'f{k}_cell'], life=g[f'f{k}_life'], p0=g[f'f{k}_p0'],
                 p1=g[f'f{k}_p1'], pub=g[f'f{k}_pub']) for k in range(n)]
     worst = _compare(frames, ref)
-    print(f'AVB_WPF={wpf}: worst position deviation {worst:.3g} px')
+    print(f'AVB_WPF={wpf} {name}: worst position deviation {worst:.3g} px')
     assert nid == int(g['next_feature_id'][0])
 
 

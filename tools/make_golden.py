@@ -33,6 +33,9 @@ CASES = {
     'ref_c1_gyro_s2': (5, 6, 3, 5, dict(n_frames=8, seed=2, sigma=3.0, drift=(-1.1, 0.9),
                                          gyro=(0.02, -0.03, 0.05), noise=1.5)),
     'ref_sparse_s3': (4, 5, 3, 5, dict(n_frames=6, seed=3, sigma=5.0, drift=(0.4, 0.2))),
+    # frames 4 and 5 are flat grey (every feature lost, empty feature messages), frame 6 is flat in its left half: the
+    # stream refills an EMPTY grid through the adder (not the first-frame initialiser)
+    'ref_c2_dark_s4': (6, 10, 3, 5, dict(n_frames=10, seed=4, gyro=(0.01, 0.0, -0.02), blackout={4: 1.0, 5: 1.0, 6: 0.53})),
 }
 
 
@@ -89,5 +92,7 @@ if __name__ == '__main__':
     _reference_first()
     import cv2
     print('reference run with cv2', cv2.__version__, 'numpy', np.__version__)
+    only = sys.argv[1:]                                 # optional: names of the cases to (re)write
     for name, spec in CASES.items():
-        dump_case(name, spec)
+        if not only or name in only:
+            dump_case(name, spec)

@@ -73,7 +73,7 @@ class SlidingTextureStream:
 
     def __init__(self, width=752, height=480, n_frames=20, seed=0, sigma=2.5,
                  disparity=12.0, drift=(1.3, 0.6), rate=20.0, imu_rate=200.0,
-                 gyro=(0.0, 0.0, 0.0), t0=1000.0, noise=0.0, movers=()):
+                 gyro=(0.0, 0.0, 0.0), t0=1000.0, noise=0.0, movers=(), blackout=None):
         self.w, self.h, self.n = int(width), int(height), int(n_frames)
         self.seed, self.sigma = int(seed), float(sigma)
         self.disparity = float(disparity)
@@ -82,6 +82,10 @@ class SlidingTextureStream:
         self.gyro = np.asarray(gyro, dtype=np.float64)
         self.t0 = float(t0)
         self.noise = float(noise)
+        # {frame index: fraction of the image width}: the leftmost columns of both cameras are a flat grey in that frame
+        # (1.0 = the whole frame: every feature is lost, the stream restarts from an empty grid without the first-frame
+        # initialiser)
+        self.blackout = {int(k): float(v) for k, v in (blackout or {}).items()}
         margin_x = int(abs(self.drift[0]) * self.n + abs(self.disparity)) + 8
         margin_y = int(abs(self.drift[1]) * self.n) + 8
         self._mx, self._my = margin_x, margin_y
@@ -124,6 +128,11 @@ class SlidingTextureStream:
             n1 = rng.normal(0.0, self.noise, size=img1.shape)
             img0 = np.clip(np.rint(img0 + n0), 0, 255).astype(np.uint8)
             img1 = np.clip(np.rint(img1 + n1), 0, 255).astype(np.uint8)
+        if k in self.blackout:
+            cols = int(round(self.blackout[k] * self.w))
+            img0, img1 = img0.copy(), img1.copy()
+            img0[:, :cols] = 90
+            img1[:, :cols] = 90
         m0, m1 = img_msg(ts, img0), img_msg(ts, img1)
         return stereo_msg(ts, img0, img1, m0, m1)
 
