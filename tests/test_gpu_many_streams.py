@@ -285,3 +285,29 @@ def test_ragged_streams_some_dark_some_full_in_one_launch():
     print(f'ragged: features per step, stream 0 {counts[0]}, stream 3 {counts[3]}, stream 6 {counts[6]}; worst {worst:.3g} px')
     assert any(0 in c and 300 in c for c in counts)
     assert any(counts[a][k] == 0 and counts[b][k] >= 299 for k in range(n_steps) for a in range(S) for b in range(S))
+
+
+@pytest.mark.parametrize('wpf', ['4', '1'])
+def test_four_huge_cells_take_the_reduction_path_of_the_selection(wpf, monkeypatch):
+    """2 x 2 cells of 376 x 240 px, up to 32 features each: every FAST bucket holds ~1300 keys, far beyond the 256 that
+    k_select ranks by counting, so the per-cell top-k (speculative list of 32, masked final list) runs its reduction
+    rounds; the mask sieve sees 32 live features per cell.  6 frames against the port."""
+    monkeypatch.setenv('AVB_WPF', wpf)
+    from image_processing import _native
+    cfg = FrontEndConfig(grid_row=2, grid_col=2, grid_min=20, grid_max=32)
+    n = 6
+    st = SlidingTextureStream(n_frames=n, **LOSSY)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    ctx = _native.Context(cfg, 752, 480, num_streams=1)
+    got = []
+    try:
+        for k in range(n):
+            ctx.process([frames[k].cam0_image], [frames[k].cam1_image], None if k == 0 else Rs[k][0], None if k == 0 else Rs[k][1])
+            got.append(_snapshot(ctx, 0))
+    finally:
+        ctx.close()
+    worst = _assert_equals_port(got, _port_run(cfg, st, 0, n), f'2x2 cells wpf={wpf}')
+    print(f'AVB_WPF={wpf}: 2 x 2 cells, n_fast {got[-1]["hdr"][7]}, features {[f["hdr"][0] for f in got]}, worst {worst:.3g} px')
+    assert got[-1]['hdr'][7] > 4 * 256 and got[-1]['hdr'][0] > 100

@@ -99,6 +99,49 @@ def test_fast_dense_noise_and_flat_images():
         c.close()
 
 
+def test_maximum_image_size():
+    """The largest image the library accepts (4096 wide, W * H < 2^24: the scan index of a FAST key has 24 bits): pyramid
+    bit-exact on all 5 levels, FAST exact incl. order at the far corner of the index range, LK against the numpy oracle."""
+    from image_processing import _native
+    from synth_euroc import make_texture
+    w, h, levels = 4096, 4095, 5
+    # 16 x 16 cells of 256 x 255 px: a cell's FAST bucket must fit the selection kernel's shared memory (cell area <= ~200 k px)
+    cfg = FrontEndConfig(grid_row=16, grid_col=16, pyramid_levels=levels, width=w, height=h)
+    a = np.clip(np.rint(make_texture(h + 8, w + 8, 21, 2.0)), 0, 255).astype(np.uint8)
+    img0, img1 = np.ascontiguousarray(a[2:h + 2, 3:w + 3]), np.ascontiguousarray(a[:h, :w])
+    c = _native.Context(cfg, w, h, use_graph=False)
+    try:
+        c.upload(img0, img0)
+        c.build_pyramids()
+        ref0 = cs.build_pyramid(img0, levels)
+        for lvl in range(levels + 1):
+            assert np.array_equal(c.download_level(0, lvl), ref0[lvl]), lvl
+        xs, ys, rs = c.fast_detect()
+        if cv2 is not None:
+            kps = cv2.FastFeatureDetector_create(cfg.fast_threshold).detect(img0)
+            rx = np.array([int(k.pt[0]) for k in kps]); ry = np.array([int(k.pt[1]) for k in kps])
+            rr = np.array([int(k.response) for k in kps])
+        else:
+            rx, ry, rr = cs.fast_detect(img0, cfg.fast_threshold)
+        assert len(xs) == len(rx) > 100000
+        assert np.array_equal(xs, rx) and np.array_equal(ys, ry) and np.array_equal(rs, rr)
+        assert ys.max() >= h - 8 and xs.max() >= w - 8            # keypoints next to the last rows / columns
+        c.advance()
+        c.upload(img1, img1)
+        c.build_pyramids()
+        g = np.random.default_rng(2)
+        far = np.stack([xs[-60:], ys[-60:]], 1).astype(np.float32)          # the bottom rows of the image
+        pts = np.vstack([far, g.uniform([10, 10], [w - 10, h - 10], (60, 2)).astype(np.float32)])
+        guess = pts + np.float32([2.0, 1.5])
+        q, st = c.klt_track(2, 0, pts, guess)
+    finally:
+        c.close()
+    q_ref, st_ref = cs.lk_track(ref0, cs.build_pyramid(img1, levels), pts, guess)
+    assert np.array_equal(st, st_ref) and np.array_equal(q[st_ref == 1], q_ref[st_ref == 1])
+    assert st.sum() > 60
+    print(f'4096x4095: {len(xs)} keypoints exact, 6 pyramid levels exact, {int(st.sum())} of {len(st)} tracks identical to the oracle')
+
+
 def _points(img, n, seed):
     xs, ys, _ = cs.fast_detect(img, 15)
     idx = np.random.default_rng(seed).choice(len(xs), n, replace=False)
