@@ -105,7 +105,7 @@ struct avb_ctx {
     bool rot_copy_pending = false;  // an enqueued (not waited-for) gather frame's rotation copy may not have run yet
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // steady-state frame, per parity, host-input variant
     cudaGraphExec_t graph_dev[2] = {nullptr, nullptr}; // same, device-input variant (no H2D of images)
-    // host-image path (avb_process_frame): the cam0-only work (clear, FAST, speculative list) as a graph of its own, launched
+    // host-image path (avb_process_frame): the cam0-only work (FAST, speculative list) as a graph of its own, launched
     // as soon as the cam0 images have arrived, while the cam1 images are still on the bus; and the rest of the chain
     cudaGraphExec_t graph_cam0[2] = {nullptr, nullptr}, graph_rest[2] = {nullptr, nullptr};
     cudaEvent_t ev_cam0 = nullptr, ev_rot = nullptr, ev_side_done = nullptr;
@@ -785,7 +785,7 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
     avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     CK(cudaEventRecord(c->ev_t0, c->st));
     if (g.S == 1 && !c->first_frame && c->cfg.use_graph && c->graph_cam0[p]) {
-        // One stream, steady state: the cam0-only part of the chain (clear, FAST, speculative list) starts as soon as the
+        // One stream, steady state: the cam0-only part of the chain (FAST, speculative list) starts as soon as the
         // cam0 image has arrived, while the cam1 image is still on the bus (7 us at 752x480); the rest of the chain
         // follows the cam1 copy and meets that part through ev_side_done.
         const uint8_t *src0 = img0[0], *src1 = img1[0];
