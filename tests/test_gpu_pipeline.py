@@ -474,3 +474,45 @@ def test_run_sweep_cli_on_euroc_directories(tmp_path):
             assert int(r['frames']) == 28 and len(lines) >= 5 and float(r['ate_rmse_m']) < 0.05
             cols = lines[0].split()
             assert len(cols) == 8 and abs(sum(float(c) ** 2 for c in cols[4:]) - 1.0) < 1e-6
+
+
+def test_page_locked_strided_and_pageable_host_images_give_the_same_messages():
+    """The three intake paths of avb_process_frame (page-locked dense images: DMA straight from the caller's memory;
+    pageable images: staged through the library's pinned block by two threads; strided views: row-wise staging), each
+    through the split-graph steady state (cam0-only work under the cam1 copy): identical feature messages, 14 lossy frames."""
+    import torch
+    from image_processing import ImageProcessor
+    from synth_euroc import img_msg, stereo_msg
+    cfg = FrontEndConfig(grid_row=6, grid_col=10)
+    kw = dict(n_frames=14, seed=8, sigma=2.0, drift=(1.9, -1.1), gyro=(0.02, 0.0, -0.02), noise=2.0)
+    base = SlidingTextureStream(**kw)
+    frames = [base.frame(k) for k in range(base.n)]
+
+    def variant(kind):
+        out = []
+        for f in frames:
+            if kind == 'pinned':
+                a = torch.empty((2, 480, 752), dtype=torch.uint8).pin_memory().numpy()
+                a[0], a[1] = f.cam0_image, f.cam1_image
+                i0, i1 = a[0], a[1]
+            elif kind == 'strided':
+                a = np.zeros((2, 480, 800), np.uint8)
+                a[0, :, 16:768], a[1, :, 16:768] = f.cam0_image, f.cam1_image
+                i0, i1 = a[0, :, 16:768], a[1, :, 16:768]
+                assert i0.strides == (800, 1)
+            else:
+                i0, i1 = f.cam0_image.copy(), f.cam1_image.copy()
+            out.append(stereo_msg(f.timestamp, i0, i1, img_msg(f.timestamp, i0), img_msg(f.timestamp, i1)))
+        return out
+
+    got = {}
+    for kind in ('pageable', 'pinned', 'strided'):
+        st = SlidingTextureStream(**kw)
+        msgs_in = variant(kind)
+        st.frames = lambda m=msgs_in: iter(m)
+        ip = ImageProcessor(cfg)
+        msgs = run_stream(ip, st)
+        got[kind] = [(m.timestamp, [(f.id, f.u0, f.v0, f.u1, f.v1) for f in m.features]) for m in msgs]
+        ip.context.close()
+    assert len(got['pageable']) == 14 and len(got['pageable'][-1][1]) > 250
+    assert got['pinned'] == got['pageable'] and got['strided'] == got['pageable']
