@@ -925,6 +925,11 @@ def main():
         }
         if multi is not None:
             multi['roofline_frac'] = multi['hbm_gbs'] / peak
+            # the image-scan kernels are the HBM-shaped part of the path: their own algorithmic bytes / stage time at the
+            # many-stream launch shape, against the same measured peak (the LK kernels work out of L1/L2: DESIGN.md section 5)
+            line['roofline']['hbm_shaped_stages'] = {
+                k_: {'achieved': v, 'unit': 'GB/s', 'frac': round(v / peak, 4), 'streams_per_launch': multi['streams_per_gpu']}
+                for k_, v in multi['stage_hbm_gbs'].items()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
