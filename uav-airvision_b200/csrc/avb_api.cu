@@ -344,6 +344,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
         CKC(dalloc(c, &d.r_und, 2 * S * NM));
         CKC(dalloc(c, &d.r_raw, 2 * S * NM));
         CKC(dalloc(c, &d.r_bits, 2 * S * NM));
+        CKC(dalloc(c, &d.r_prev, S * NM));
     }
     c->out_stride = out_stride_bytes(g.NMAX);
     // A small result (one or a few streams) is written by k_finish directly into mapped pinned host memory: the posted

@@ -130,6 +130,7 @@ struct DevState {
     // two-point RANSAC scratch, [2 cams][S][NMAX] (allocated only when Geom::ransac)
     int* r_idx;
     float4* r_und;
+    float4* r_prev;                // [S][NMAX] previous positions, gyro-rotated and undistorted (cam0 xy, cam1 zw): written by k_track
     int* r_raw;
     uint8_t* r_bits;
     uint8_t* out;                  // [S][out_stride] device mirror of the result block

@@ -21,7 +21,7 @@ __device__ __forceinline__ int team_index(int bx) {
 
 // FeatureTracker.track_features, steps 3-8 (feature_tracker.py:85-133) for every previous feature:
 // gyro prediction (K R K^-1) -> temporal LK -> image-bounds cull (> W-1 rule, B6) -> stereo match.
-template <int WPF>
+template <int WPF, bool RANSAC>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOCKS : 4) k_track(const __grid_constant__ Geom g, const __grid_constant__ DevState d,
                                                                 int parity) {
     __shared__ LKShared sh;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOC
     const float gx = (float)(hx / hz), gy = (float)(hy / hz);
 
     const ChainResult r = feature_chain<WPF>(g, d, s, parity, true, p.x, p.y, gx, gy, &sh);
+    const bool matched = r.matched;
     if (lead) {
         int* cnt = d.counters + s * 8;
         int new_cell = -1;
@@ -59,6 +60,28 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, WPF == 1 ? AVB_WPF1_BLOC
         d.t_p1[base + wi] = make_float2(r.x1, r.y1);
         d.t_cell[base + wi] = new_cell;
         if (new_cell >= 0) d.t_und[base + wi] = make_double4(r.u0, r.v0, r.u1, r.v1);
+    }
+    if (RANSAC && matched && (WPF == 1 || threadIdx.x < 32)) {      // a template flag: the plain instantiation keeps its 96 registers without spills
+        // k_ransac's inputs that do not depend on other features are made here, where the work is spread over the GPU
+        // (that kernel runs one CTA per stream: at 2000 points the FP64 undistortions were half of its 41 us): the
+        // previous position of each camera, undistorted and rotated by the gyro prediction of that camera
+        // (oracle/ransac.py: undistort(prev, R_p_c)).  Lane 0 cam0, lane 1 cam1; the current positions are t_und.
+        const int l = threadIdx.x & 31;
+        const bool c1 = l == 1;
+        CamModel cm;
+        cm.fx = c1 ? g.cam1.fx : g.cam0.fx;
+        cm.fy = c1 ? g.cam1.fy : g.cam0.fy;
+        cm.cx = c1 ? g.cam1.cx : g.cam0.cx;
+        cm.cy = c1 ? g.cam1.cy : g.cam0.cy;
+        cm.k1 = c1 ? g.cam1.k1 : g.cam0.k1;
+        cm.k2 = c1 ? g.cam1.k2 : g.cam0.k2;
+        cm.p1 = c1 ? g.cam1.p1 : g.cam0.p1;
+        cm.p2 = c1 ? g.cam1.p2 : g.cam0.p2;
+        const float2 q = c1 ? prev.p1[base + wi] : p;
+        double ux, uy;
+        undistort_pt(cm, (double)q.x, (double)q.y, H + 9 + (c1 ? 9 : 0), ux, uy);
+        const float x1u = __shfl_sync(0xffffffffu, (float)ux, 1), y1u = __shfl_sync(0xffffffffu, (float)uy, 1);
+        if (l == 0) d.r_prev[base + wi] = make_float4((float)ux, (float)uy, x1u, y1u);
     }
 }
 
@@ -212,10 +235,13 @@ static inline int teams_grid(int n, int wpf) { return wpf == 1 ? (n + WARPS_PER_
 
 void launch_track(const Geom& g, const DevState& d, int parity, cudaStream_t st) {
     dim3 grid(teams_grid(g.NMAX, g.wpf), g.S);
-    if (g.wpf == 1)
-        launch_k(k_track<1>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
-    else
-        launch_k(k_track<4>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+    if (g.wpf == 1) {
+        if (g.ransac) launch_k(k_track<1, true>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+        else launch_k(k_track<1, false>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+    } else {
+        if (g.ransac) launch_k(k_track<4, true>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+        else launch_k(k_track<4, false>, grid, dim3(32 * WARPS_PER_BLOCK), 0, st, g_avb_pdl != 0, g, d, parity);
+    }
 }
 // Two rounds save ~40 % of the matching work but cost a second chain of latency: worth it only when the candidates
 // fill the GPU several times over (throughput-bound), not when they fit in a wave or two.
@@ -272,8 +298,10 @@ void launch_undistort(const CamModel& cam, const double* xy, int n, const double
 int avb_preload_points() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<1>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<4>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<1, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<4, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<1, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_track<4, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_stereo_candidates<4>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_spec_match<1>);

@@ -107,20 +107,16 @@ struct RansacParams {
     int iters, seed, frame_index, cam_key;
 };
 
-template <typename Fetch>
-__device__ __forceinline__ void ransac_camera(const CamModel& cm, const double* R, int n, Fetch fetch, float4* und, int* raw_idx,
+// und_of(k): point k undistorted, f32: (previous position rotated by R_p_c, current position).
+template <typename UndOf>
+__device__ __forceinline__ void ransac_camera(const CamModel& cm, int n, UndOf und_of, float4* und, int* raw_idx,
                                               uint8_t* bits, RsShared& sh, int bar, int t, const RansacParams& prm) {
     const int lane = t & 31, wq = t >> 5;
     if (n <= 0) return;
-    // 2. undistort (f64 inside, f32 results), partial sums of the point norms
+    // 2. undistorted points (f64 inside, f32 results), partial sums of the point norms
     double part = 0.0;
     for (int k = t; k < n; k += RS_HALF) {
-        float2 a, b;
-        fetch(k, a, b);
-        double ax, ay, bx, by;
-        undistort_pt(cm, (double)a.x, (double)a.y, R, ax, ay);
-        undistort_pt(cm, (double)b.x, (double)b.y, nullptr, bx, by);
-        const float4 u = make_float4((float)ax, (float)ay, (float)bx, (float)by);
+        const float4 u = und_of(k);
         und[k] = u;
         const double n1 = __dsqrt_rn(__dadd_rn(__dmul_rn((double)u.x, (double)u.x), __dmul_rn((double)u.y, (double)u.y)));
         const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn((double)u.z, (double)u.z), __dmul_rn((double)u.w, (double)u.w)));
@@ -247,8 +243,6 @@ __global__ void __launch_bounds__(2 * RS_HALF) k_ransac(const __grid_constant__ 
     const size_t base = (size_t)s * g.NMAX;
     const RansacScratch sc = cam ? sc1 : sc0;
     int* idx = sc.idx + base;
-    const GridTable prev = d.grid[parity ^ 1];
-    const double* R = frame_H(d, g, s, parity) + 9 + 9 * cam;       // R_p_c of this camera
 
     // 1. the point list: stereo-matched survivors in table order
     const int* tc = d.t_cell + base;
@@ -256,19 +250,23 @@ __global__ void __launch_bounds__(2 * RS_HALF) k_ransac(const __grid_constant__ 
     if (t == 0) n_pts[cam] = n;
     bar_half(cam);
 
-    const float2* pa = (cam ? prev.p1 : prev.p0) + base;
-    const float2* pb = (cam ? d.t_p1 : d.t_p0) + base;
     RansacParams prm;
     prm.thr_px = g.ransac_thr;
     prm.iters = g.ransac_iters;
     prm.seed = g.ransac_seed;
     prm.frame_index = d.frame_index[s];
     prm.cam_key = cam;
-    ransac_camera(cam ? g.cam1 : g.cam0, R, n,
-                  [&](int k, float2& a, float2& b) {
+    // the undistortions themselves were made by k_track at the end of every feature's LK chain (r_prev: previous
+    // positions through R_p_c; t_und: the current ones, the values the publisher uses), rounded to f32 here as
+    // cv2.undistortPoints rounds them for float32 input
+    const float4* rp = d.r_prev + base;
+    const double4* tu = d.t_und + base;
+    ransac_camera(cam ? g.cam1 : g.cam0, n,
+                  [&](int k) {
                       const int wi = idx[k];
-                      a = pa[wi];
-                      b = pb[wi];
+                      const float4 pr = rp[wi];
+                      const double4 cu = tu[wi];
+                      return cam ? make_float4(pr.z, pr.w, (float)cu.z, (float)cu.w) : make_float4(pr.x, pr.y, (float)cu.x, (float)cu.y);
                   },
                   sc.und + base, sc.raw_idx + base, sc.bits + base, sh, cam, t, prm);
     __syncthreads();
@@ -289,10 +287,13 @@ __global__ void __launch_bounds__(2 * RS_HALF) k_ransac(const __grid_constant__ 
 __global__ void __launch_bounds__(RS_HALF) k_ransac_points(CamModel cm, const double* R, const float2* prev, const float2* cur, int n,
                                                            float4* und, int* raw_idx, uint8_t* bits, RansacParams prm) {
     __shared__ RsShared sh;
-    ransac_camera(cm, R, n,
-                  [&](int k, float2& a, float2& b) {
-                      a = prev[k];
-                      b = cur[k];
+    ransac_camera(cm, n,
+                  [&](int k) {
+                      const float2 a = prev[k], b = cur[k];
+                      double ax, ay, bx, by;
+                      undistort_pt(cm, (double)a.x, (double)a.y, R, ax, ay);
+                      undistort_pt(cm, (double)b.x, (double)b.y, nullptr, bx, by);
+                      return make_float4((float)ax, (float)ay, (float)bx, (float)by);
                   },
                   und, raw_idx, bits, sh, 0, threadIdx.x, prm);
 }
