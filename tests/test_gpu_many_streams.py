@@ -311,3 +311,92 @@ def test_four_huge_cells_take_the_reduction_path_of_the_selection(wpf, monkeypat
     worst = _assert_equals_port(got, _port_run(cfg, st, 0, n), f'2x2 cells wpf={wpf}')
     print(f'AVB_WPF={wpf}: 2 x 2 cells, n_fast {got[-1]["hdr"][7]}, features {[f["hdr"][0] for f in got]}, worst {worst:.3g} px')
     assert got[-1]['hdr'][7] > 4 * 256 and got[-1]['hdr'][0] > 100
+
+
+def test_soak_3000_frames_speculative_split_graph_path_equals_the_plain_chain(monkeypatch):
+    """A timing-dependent fault (a race between the FAST branch's speculative table and the main branch, a stale
+    double-buffered result block, a bucket count not left at zero) would not show in a 30-frame parity test every time.
+    3000 frames (120 lossy frames walked forth and back) through two contexts fed the same host images: the default
+    single-stream shape (speculative matches on the side stream, cam0 part of the chain as a graph of its own) and the
+    plain chain (AVB_SPEC_K=0: candidates matched behind k_select).  Every frame's ids, cells, lifetimes, positions and
+    published coordinates must be identical."""
+    from image_processing import _native
+    cfg = config_c2()
+    n = 120
+    st = SlidingTextureStream(n_frames=n, **LOSSY)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    order = list(range(n)) + list(range(n - 2, 0, -1))
+    a = _native.Context(cfg, 752, 480, num_streams=1)
+    monkeypatch.setenv('AVB_SPEC_K', '0')
+    b = _native.Context(cfg, 752, 480, num_streams=1)
+    try:
+        assert a.kernels_per_frame() == 8 and b.kernels_per_frame() == 7
+        total = 0
+        for step in range(3000):
+            k = order[step % len(order)]
+            R0, R1 = (None, None) if step == 0 else Rs[k]
+            for ctx in (a, b):
+                ctx.process([frames[k].cam0_image], [frames[k].cam1_image], R0, R1)
+            x, y = _snapshot(a, 0), _snapshot(b, 0)
+            assert x['hdr'] == y['hdr'], f'step {step}: {x["hdr"]} vs {y["hdr"]}'
+            for key in ('ids', 'cell', 'life', 'p0', 'p1', 'meas'):
+                assert np.array_equal(x[key], y[key]), f'step {step}: {key} differ'
+            total += x['hdr'][0]
+    finally:
+        a.close()
+        b.close()
+    print(f'soak: 3000 frames, {total} published features, both launch shapes identical on every frame')
+    assert total > 3000 * 250
+
+
+def test_soak_pipelined_enqueue_with_previous_result_blocks_equals_synchronous_steps():
+    """The sweep driver's overlap (enqueue step k+1, THEN take step k's results from the other parity's result block,
+    avb_get_result_prev) against plain synchronous steps: 8 streams x 400 steps from device-resident input blocks (bulk D2H
+    result path), every result block identical byte for byte."""
+    import torch
+    from image_processing import _native
+    cfg = config_c2()
+    S, n_base, steps = 8, 40, 400
+    n = n_base + 2 * (S - 1)
+    st = SlidingTextureStream(n_frames=n, **LOSSY)
+    frames = [st.frame(k) for k in range(n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    a = _native.Context(cfg, 752, 480, num_streams=S)
+    b = _native.Context(cfg, 752, 480, num_streams=S)
+    try:
+        bb, ib = a.block_bytes, 752 * 480
+        host = np.zeros((n_base, bb), np.uint8)
+        for k in range(n_base):
+            for s in range(S):
+                f = frames[k + 2 * s]
+                host[k, (2 * s) * ib:(2 * s + 1) * ib] = f.cam0_image.reshape(-1)
+                host[k, (2 * s + 1) * ib:(2 * s + 2) * ib] = f.cam1_image.reshape(-1)
+            a.fill_rotations(host[k], np.stack([Rs[k + 2 * s][0] for s in range(S)]), np.stack([Rs[k + 2 * s][1] for s in range(S)]))
+        dev = torch.from_numpy(host).cuda()
+        order = list(range(n_base)) + list(range(n_base - 2, 0, -1))
+        ptr = lambda step: dev.data_ptr() + order[step % len(order)] * bb
+        want = []
+        for step in range(steps):                                   # synchronous: process, read
+            b.process_device(ptr(step))
+            want.append(b.result_block()[0].copy())
+        got = []
+        a.enqueue_device(ptr(0))
+        for step in range(steps):                                   # pipelined: sync k, enqueue k+1, read k
+            a.sync()
+            if step + 1 < steps:
+                a.enqueue_device(ptr(step + 1))
+                got.append(a.result_block(prev=True)[0].copy())
+            else:
+                got.append(a.result_block()[0].copy())
+        feats = 0
+        for step in range(steps):
+            assert np.array_equal(got[step], want[step]), f'step {step}: result blocks differ'
+            feats += int(want[step][:, :48].view(_native.HEADER_DTYPE)['n_features'].sum())
+    finally:
+        a.close()
+        b.close()
+    print(f'soak: {S} streams x {steps} steps, {feats} published features, pipelined == synchronous')
+    assert feats > S * steps * 250
