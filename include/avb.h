@@ -39,8 +39,9 @@
 extern "C" {
 #endif
 
-#define AVB_ABI_VERSION 4   /* 3: + avb_store_*, avb_process_frame_gather, avb_enqueue_frame_gather; 4: + avb_get_result_prev
-                             * (result blocks double-buffered by frame parity); structs unchanged since 2 */
+#define AVB_ABI_VERSION 5   /* 3: + avb_store_*, avb_process_frame_gather, avb_enqueue_frame_gather; 4: + avb_get_result_prev
+                             * (result blocks double-buffered by frame parity); 5: + avb_submit_images /
+                             * avb_process_submitted; structs unchanged since 2 */
 
 #define AVB_OK              0
 #define AVB_E_INVALID      -1   /* bad argument / unsupported configuration */
@@ -126,6 +127,16 @@ int      avb_fill_rotations(const avb_ctx* ctx, uint8_t* block, const double* R_
  * host memory. */
 int  avb_process_frame(avb_ctx* ctx, const uint8_t* const* img0, const uint8_t* const* img1,
                        int stride, const double* R_p_c0, const double* R_p_c1);
+
+/* avb_process_frame in two halves.  avb_submit_images starts the intake (host staging, H2D copies and, for a single
+ * stream, the cam0-only kernels: FAST and the speculative candidate list); nothing in it needs the frame's gyro
+ * rotations, so the caller can integrate the IMU window (IMUProcessor.integrate_imu_data, imu_processor.py:28-67;
+ * pipeline.py:52-55 does it at the top of stereo_callback) while the images are on the bus.  avb_process_submitted
+ * then takes the rotations, runs the rest of the frame and blocks until the results are in host memory.  The image
+ * buffers must stay valid until it returns.  AVB_E_STATE: submit twice, finish without submit, or any other frame
+ * entry point in between. */
+int  avb_submit_images(avb_ctx* ctx, const uint8_t* const* img0, const uint8_t* const* img1, int stride);
+int  avb_process_submitted(avb_ctx* ctx, const double* R_p_c0, const double* R_p_c1);
 
 /* Same, the whole input block already resident in device memory (layout above). */
 int  avb_process_frame_device(avb_ctx* ctx, const uint8_t* d_block);

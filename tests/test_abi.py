@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert set(names) == set(_native.EXPORTS)
-    assert lib.avb_abi_version() == 4
+    assert lib.avb_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):

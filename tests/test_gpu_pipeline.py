@@ -516,3 +516,45 @@ def test_page_locked_strided_and_pageable_host_images_give_the_same_messages():
         ip.context.close()
     assert len(got['pageable']) == 14 and len(got['pageable'][-1][1]) > 250
     assert got['pinned'] == got['pageable'] and got['strided'] == got['pageable']
+
+
+def test_submit_images_then_process_submitted_equals_process_frame():
+    """avb_submit_images + avb_process_submitted (the frame in two halves, so that the caller integrates the gyro window
+    while the images are on the bus) against the one-call path, 3 streams x 8 frames incl. frame 0 (the general intake) and
+    1 stream x 8 frames (the split-graph intake); and the call-order errors."""
+    from image_processing import _native
+    from test_gpu_many_streams import _rotations, _snapshot
+    cfg = FrontEndConfig(grid_row=6, grid_col=10)
+    kw = dict(n_frames=12, seed=9, sigma=2.0, drift=(1.6, 0.9), gyro=(0.02, -0.01, 0.02), noise=1.5)
+    st = SlidingTextureStream(**kw)
+    frames = [st.frame(k) for k in range(st.n)]
+    st.frames = lambda: iter(frames)
+    Rs = _rotations(cfg, st)
+    for S in (3, 1):
+        a = _native.Context(cfg, 752, 480, num_streams=S)
+        b = _native.Context(cfg, 752, 480, num_streams=S)
+        try:
+            for k in range(8):
+                idx = [k + s for s in range(S)]
+                i0, i1 = [frames[i].cam0_image for i in idx], [frames[i].cam1_image for i in idx]
+                R0 = None if k == 0 else np.stack([Rs[i][0] for i in idx])
+                R1 = None if k == 0 else np.stack([Rs[i][1] for i in idx])
+                a.submit_images(i0, i1)
+                if k == 3:                                  # call order: nothing else may start a frame in between
+                    with pytest.raises(RuntimeError, match='submitted'):
+                        a.submit_images(i0, i1)
+                    with pytest.raises(RuntimeError, match='submitted'):
+                        a.process_staged(R0, R1)
+                a.process_submitted(R0, R1)
+                b.process(i0, i1, R0, R1)
+                for s in range(S):
+                    x, y = _snapshot(a, s), _snapshot(b, s)
+                    assert x['hdr'] == y['hdr'], (S, k, s)
+                    for key in ('ids', 'cell', 'life', 'p0', 'p1', 'meas'):
+                        assert np.array_equal(x[key], y[key]), (S, k, s, key)
+            with pytest.raises(RuntimeError, match='no images submitted'):
+                a.process_submitted(None, None)
+            assert _snapshot(a, 0)['hdr'][0] > 250
+        finally:
+            a.close()
+            b.close()

@@ -29,13 +29,22 @@ orig = ip.imu_processor.integrate_imu_data
 def timed_imu():
     t0 = time.perf_counter(); r = orig(); t_imu.append(time.perf_counter() - t0); return r
 ip.imu_processor.integrate_imu_data = timed_imu
-orig_pf = _avbhost.process_frame
-t_pf = []
+t_pf, t_sub, t_fin = [], [], []
 import image_processing.pipeline as pl
-class _H:
-    @staticmethod
-    def process_frame(*a):
-        t0 = time.perf_counter(); r = orig_pf(*a); t_pf.append(time.perf_counter() - t0); return r
+
+
+def _timed(fn, acc):
+    def f(*a):
+        t0 = time.perf_counter(); r = fn(*a); acc.append(time.perf_counter() - t0); return r
+    return f
+
+
+class _H:                               # the C driver calls of stereo_callback, timed
+    process_frame = staticmethod(_timed(_avbhost.process_frame, t_pf))
+    submit_images = staticmethod(_timed(_avbhost.submit_images, t_sub))
+    finish_frame = staticmethod(_timed(_avbhost.finish_frame, t_fin))
+
+
 pl._avbhost = _H
 for kind, msg in evs:
     if kind == 'imu':
@@ -44,5 +53,5 @@ for kind, msg in evs:
         t0 = time.perf_counter(); fm = ip.stereo_callback(msg); t_cb.append(time.perf_counter() - t0)
         dev.append(ip.context.last_frame_ms() if hasattr(ip.context, 'last_frame_ms') else float('nan'))
 med = lambda a: 1e6 * float(np.median(a[20:]))
-print(f'stereo_callback {med(t_cb):.1f} us | _avbhost.process_frame {med(t_pf):.1f} us | integrate_imu {med(t_imu):.1f} us | '
+print(f'stereo_callback {med(t_cb):.1f} us | _avbhost.submit_images {med(t_sub):.1f} us + finish_frame {med(t_fin):.1f} us | integrate_imu {med(t_imu):.1f} us (between the two) | '
       f'device (events, H2D..results) {1e3 * float(np.median(dev[20:])):.1f} us | features {len(fm.features)}')

@@ -91,7 +91,8 @@ struct avb_ctx {
     Geom g;
     DevState d;
     PyrMaps maps;
-    cudaStream_t st = nullptr, st_side = nullptr;
+    cudaStream_t st = nullptr, st_side = nullptr, st_rot = nullptr;   // st_rot: the rotation section's copy (avb_process_submitted)
+    int submitted = 0;              // avb_submit_images done, avb_process_submitted due: 1 split-graph path, 2 general path
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     uint8_t* h_in = nullptr;        // pinned: one input block (images + H)
     uint8_t* h_out[2] = {nullptr, nullptr};   // pinned: S result blocks per frame parity (the results of frame k stay
@@ -294,6 +295,7 @@ extern "C" int avb_create(const avb_config* cfg, avb_ctx** out) {
     const size_t inb = in_block_bytes(g);
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->st_side, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->st_rot, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
@@ -468,6 +470,7 @@ extern "C" void avb_destroy(avb_ctx* c) {
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_side) cudaStreamDestroy(c->st_side);
+    if (c->st_rot) cudaStreamDestroy(c->st_rot);
     delete c;
 }
 
@@ -486,7 +489,10 @@ extern "C" void* avb_cuda_stream(avb_ctx* c) { return c ? (void*)c->st : nullptr
 extern "C" int avb_reset(avb_ctx* c) {
     if (!c) return AVB_E_INVALID;
     CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->st_side));
+    CK(cudaStreamSynchronize(c->st_rot));
     CK(cudaStreamSynchronize(c->st));
+    c->submitted = 0;                   // a submitted, unfinished frame is dropped with the rest of the state
     const Geom& g = c->g;
     for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(c->d.grid[p].count, 0, (size_t)g.S * g.NC * sizeof(int), c->st));
     CK(cudaMemsetAsync(c->d.next_id, 0, (size_t)2 * g.S * sizeof(long long), c->st));
@@ -703,6 +709,7 @@ extern "C" int avb_fill_rotations(const avb_ctx* c, uint8_t* block, const double
 // d.in[p] by copies ordered before this on c->st; 2: like 1, and ev_t0 was already recorded before those copies.
 static int run_frame(avb_ctx* c, int variant, bool wait) {
     const Geom& g = c->g;
+    if (c->submitted) return fail(c, AVB_E_STATE, "images submitted: avb_process_submitted must finish that frame first");
     const int p = c->parity ^ 1;
     const size_t inb = in_block_bytes(g);
     if (variant != 2) CK(cudaEventRecord(c->ev_t0, c->st));
@@ -764,31 +771,24 @@ static bool is_page_locked(avb_ctx* c, const void* p, size_t n) {
     return yes;
 }
 
-extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
-                                 const double* R_p_c0, const double* R_p_c1) {
-    if (!c) return AVB_E_INVALID;
+// Intake of one frame's host images (pipelined: each image is staged into pinned memory -- or, when the caller's buffer
+// is itself page-locked and dense, taken from where it lies -- and its H2D copy is enqueued before the next image is
+// touched, so the PCIe transfer of one image overlaps the host copy of the next).  The cam0 copy goes out before anything
+// else: the GPU is idle until it arrives and every host call ahead of it is on the frame's critical path.  Nothing here
+// needs the frame's gyro rotations, so a caller may compute them (IMUProcessor.integrate_imu_data) while the copies
+// fly: avb_submit_images, then avb_process_submitted(R).
+static int submit_images(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride) {
     const Geom& g = c->g;
-    CK(cudaSetDevice(c->cfg.device));
-    if (!(img0 && img1)) {              // the caller filled the pinned staging block in place
-        avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
-        return run_frame(c, 0, true);
-    }
+    if (c->submitted) return fail(c, AVB_E_STATE, "images already submitted: call avb_process_submitted first");
+    if (!(img0 && img1)) return fail(c, AVB_E_INVALID, "null image arrays");
     if (stride < g.W) return fail(c, AVB_E_INVALID, "stride %d < width %d", stride, g.W);
-    // Pipelined intake: each image is staged into pinned memory (or, when the caller's buffer is itself page-locked
-    // and dense, taken from where it lies) and its H2D copy is enqueued before the next image is touched, so the PCIe
-    // transfer of one image overlaps the host copy of the next.  The kernels then run from the graph variant that has
-    // no H2D node.  Order of submission: the first image copy goes out before anything else (the GPU is idle until it
-    // arrives; every host call ahead of it is on the frame's critical path), then the 216-byte rotation section on the
-    // side stream (a copy this small is all latency; in line it would add ~2.5 us), then the remaining images.
     const int p = c->parity ^ 1;
     const size_t ib = (size_t)g.W * g.H;
-    const size_t ro = in_images_bytes(g);
-    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
     CK(cudaEventRecord(c->ev_t0, c->st));
     if (g.S == 1 && !c->first_frame && c->cfg.use_graph && c->graph_cam0[p]) {
-        // One stream, steady state: the cam0-only part of the chain (FAST, speculative list) starts as soon as the
-        // cam0 image has arrived, while the cam1 image is still on the bus (7 us at 752x480); the rest of the chain
-        // follows the cam1 copy and meets that part through ev_side_done.
+        // One stream, steady state: the cam0-only part of the chain (FAST, speculative list) starts as soon as the cam0
+        // image has arrived, while the cam1 image is still on the bus (7 us at 752x480); the rest of the chain follows
+        // the cam1 copy and meets that part through ev_side_done.
         const uint8_t *src0 = img0[0], *src1 = img1[0];
         if (!src0 || !src1) return fail(c, AVB_E_INVALID, "null image pointer (stream 0)");
         const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
@@ -804,9 +804,7 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
             ck(cudaMemcpyAsync(c->d.in[p], c->h_in, ib, cudaMemcpyHostToDevice, c->st), "H2D cam0");
         }
         ck(cudaEventRecord(c->ev_cam0, c->st), "event");
-        ck(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0), "wait");               // not before the previous frame is done with d.in[p]
-        ck(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side), "H2D rotations");
-        ck(cudaEventRecord(c->ev_rot, c->st_side), "event");
+        ck(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0), "wait");               // not before the previous frame is done with its tables
         ck(cudaStreamWaitEvent(c->st_side, c->ev_cam0, 0), "wait");
         ck(cudaGraphLaunch(c->graph_cam0[p], c->st_side), "graph (cam0 part)");
         ck(cudaEventRecord(c->ev_side_done, c->st_side), "event");
@@ -816,56 +814,99 @@ extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const u
             c->copier.wait();
             ck(cudaMemcpyAsync(c->d.in[p] + ib, c->h_in + ib, ib, cudaMemcpyHostToDevice, c->st), "H2D cam1");
         }
-        ck(cudaStreamWaitEvent(c->st, c->ev_rot, 0), "wait");
-        ck(cudaGraphLaunch(c->graph_rest[p], c->st), "graph (rest)");
-        ck(cudaEventRecord(c->ev_t1, c->st), "event");
         if (rc != AVB_OK) {
             cudaStreamSynchronize(c->st_side);
             cudaStreamSynchronize(c->st);
             return rc;
         }
+        c->submitted = 1;
+        return AVB_OK;
+    }
+    for (int s = 0; s < g.S; ++s) {
+        const uint8_t* src0 = img0[s];
+        const uint8_t* src1 = img1[s];
+        if (!src0 || !src1) {
+            cudaStreamSynchronize(c->st);
+            return fail(c, AVB_E_INVALID, "null image pointer (stream %d)", s);
+        }
+        const size_t off0 = ((size_t)s * 2) * ib, off1 = off0 + ib;
+        const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
+        if (!pin1) c->copier.post(c->h_in + off1, src1, g.W, g.H, stride);     // the helper stages cam1 meanwhile
+        cudaError_t e;
+        if (pin0) {
+            e = cudaMemcpyAsync(c->d.in[p] + off0, src0, ib, cudaMemcpyHostToDevice, c->st);
+        } else {
+            CopyWorker::copy(c->h_in + off0, src0, g.W, g.H, stride);
+            e = cudaMemcpyAsync(c->d.in[p] + off0, c->h_in + off0, ib, cudaMemcpyHostToDevice, c->st);
+        }
+        if (!pin1) c->copier.wait();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->d.in[p] + off1, pin1 ? src1 : c->h_in + off1, ib, cudaMemcpyHostToDevice, c->st);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(c->st);
+            return fail(c, AVB_E_CUDA, "H2D (stream %d): %s", s, cudaGetErrorString(e));
+        }
+    }
+    c->submitted = 2;
+    return AVB_OK;
+}
+
+// The rest of a submitted frame: the 216-byte-per-stream rotation section travels on a stream of its own (a copy this
+// small is all latency; in line behind the images it would add ~2.5 us to the chain), then the kernels, then the wait.
+static int finish_submitted(avb_ctx* c, const double* R_p_c0, const double* R_p_c1) {
+    const Geom& g = c->g;
+    if (!c->submitted) return fail(c, AVB_E_STATE, "no images submitted");
+    const int mode = c->submitted;
+    c->submitted = 0;
+    const int p = c->parity ^ 1;
+    const size_t ro = in_images_bytes(g);
+    avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
+    cudaError_t e = cudaStreamWaitEvent(c->st_rot, c->ev_t0, 0);               // not before the previous frame is done with d.in[p]
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_rot);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_rot, c->st_rot);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->st, c->ev_rot, 0);
+    if (e == cudaSuccess && mode == 1) {
+        e = cudaGraphLaunch(c->graph_rest[p], c->st);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_t1, c->st);
+    }
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(c->st_rot);
+        cudaStreamSynchronize(c->st_side);
+        cudaStreamSynchronize(c->st);
+        return fail(c, AVB_E_CUDA, "frame submission: %s", cudaGetErrorString(e));
+    }
+    if (mode == 1) {
         c->parity = p;
         c->have_frame = true;
         CK(cudaStreamSynchronize(c->st));
         return AVB_OK;
     }
-    bool rot_sent = false;
-    auto send_rotations = [&]() -> int {
-        CK(cudaStreamWaitEvent(c->st_side, c->ev_t0, 0));      // not before the previous frame is done with d.in[p]
-        CK(cudaMemcpyAsync(c->d.in[p] + ro, c->h_in + ro, in_block_bytes(g) - ro, cudaMemcpyHostToDevice, c->st_side));
-        CK(cudaEventRecord(c->ev_join, c->st_side));
-        rot_sent = true;
-        return AVB_OK;
-    };
-    for (int s = 0; s < g.S; ++s) {
-        const uint8_t* src0 = img0[s];
-        const uint8_t* src1 = img1[s];
-        if (!src0 || !src1) return fail(c, AVB_E_INVALID, "null image pointer (stream %d)", s);
-        const size_t off0 = ((size_t)s * 2) * ib, off1 = off0 + ib;
-        const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
-        if (!pin1) c->copier.post(c->h_in + off1, src1, g.W, g.H, stride);     // the helper stages cam1 meanwhile
-        if (pin0) {
-            CK(cudaMemcpyAsync(c->d.in[p] + off0, src0, ib, cudaMemcpyHostToDevice, c->st));
-        } else {
-            CopyWorker::copy(c->h_in + off0, src0, g.W, g.H, stride);
-            CK(cudaMemcpyAsync(c->d.in[p] + off0, c->h_in + off0, ib, cudaMemcpyHostToDevice, c->st));
-        }
-        if (!rot_sent) {
-            const int r = send_rotations();
-            if (r != AVB_OK) {
-                if (!pin1) c->copier.wait();
-                return r;
-            }
-        }
-        if (pin1) {
-            CK(cudaMemcpyAsync(c->d.in[p] + off1, src1, ib, cudaMemcpyHostToDevice, c->st));
-        } else {
-            c->copier.wait();
-            CK(cudaMemcpyAsync(c->d.in[p] + off1, c->h_in + off1, ib, cudaMemcpyHostToDevice, c->st));
-        }
-    }
-    CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
     return run_frame(c, 2, true);
+}
+
+extern "C" int avb_submit_images(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    return submit_images(c, img0, img1, stride);
+}
+
+extern "C" int avb_process_submitted(avb_ctx* c, const double* R_p_c0, const double* R_p_c1) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    return finish_submitted(c, R_p_c0, R_p_c1);
+}
+
+extern "C" int avb_process_frame(avb_ctx* c, const uint8_t* const* img0, const uint8_t* const* img1, int stride,
+                                 const double* R_p_c0, const double* R_p_c1) {
+    if (!c) return AVB_E_INVALID;
+    CK(cudaSetDevice(c->cfg.device));
+    if (!(img0 && img1)) {              // the caller filled the pinned staging block in place
+        if (c->submitted) return fail(c, AVB_E_STATE, "images already submitted: call avb_process_submitted first");
+        avb_fill_rotations(c, c->h_in, R_p_c0, R_p_c1);
+        return run_frame(c, 0, true);
+    }
+    const int rc = submit_images(c, img0, img1, stride);
+    return rc != AVB_OK ? rc : finish_submitted(c, R_p_c0, R_p_c1);
 }
 
 extern "C" int avb_enqueue_frame_device(avb_ctx* c, const uint8_t* d_block) {

@@ -7,6 +7,8 @@
  * imu_processor.py:28-67) and does the per-frame work natively:
  *
  *   process_frame(ctx, img0, img1, R|None (3x3 or 2x3x3), FeatureMeasurement) -> (features, header tuple)
+ *   submit_images(ctx, img0, img1) + finish_frame(ctx, R|None, FeatureMeasurement): the same in two halves, so that the
+ *       caller integrates the gyro window between them, while the images are on the bus
  *       copies the two host images into libavb's pinned staging block (GIL released), runs avb_process_frame
  *       (H2D + CUDA-graph frame + D2H), and materialises the FeatureMeasurement list straight from the pinned
  *       result block
@@ -171,75 +173,30 @@ static int copy_image(uint8_t* dst, Py_buffer* b, int W, int H) {
     return 0;
 }
 
-/* process_frame(ctx:int, stream_count:int(=1), img0, img1, R|None, fm_type) */
-static PyObject* py_process_frame(PyObject* self, PyObject* args) {
-    unsigned long long handle;
-    PyObject *img0, *img1, *Robj, *tpobj;
-    if (!PyArg_ParseTuple(args, "KOOOO", &handle, &img0, &img1, &Robj, &tpobj)) return NULL;
-    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
-    if (!ctx || !PyType_Check(tpobj)) {
-        PyErr_SetString(PyExc_TypeError, "process_frame(ctx, img0, img1, R|None, FeatureMeasurement)");
-        return NULL;
-    }
-    int W = 0, H = 0, S = 0;
-    avb_get_geometry(ctx, &W, &H, &S);
-    if (S != 1) {
-        PyErr_SetString(PyExc_RuntimeError, "process_frame drives single-stream contexts");
-        return NULL;
-    }
-    Py_buffer b0, b1, bR;
-    int haveR = 0;
-    if (PyObject_GetBuffer(img0, &b0, PyBUF_STRIDES) < 0) return NULL;
-    if (PyObject_GetBuffer(img1, &b1, PyBUF_STRIDES) < 0) {
-        PyBuffer_Release(&b0);
-        return NULL;
-    }
-    double R[18];                       /* cam0_R_p_c [, cam1_R_p_c] */
-    int haveR1 = 0;
-    if (Robj != Py_None) {
-        if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) {
-            PyBuffer_Release(&b0);
-            PyBuffer_Release(&b1);
-            return NULL;
-        }
-        if ((bR.len != 72 && bR.len != 144) || bR.itemsize != 8) {
-            PyBuffer_Release(&b0);
-            PyBuffer_Release(&b1);
-            PyBuffer_Release(&bR);
-            PyErr_SetString(PyExc_ValueError, "R must be a C-contiguous float64 array: 3x3 (cam0_R_p_c) or 2x3x3 (cam0, cam1)");
-            return NULL;
-        }
-        memcpy(R, bR.buf, (size_t)bR.len);
-        haveR1 = bR.len == 144;
+/* R|None -> (R[18], haveR, haveR1); 0 on success, -1 with a Python error set */
+static int parse_R(PyObject* Robj, double* R, int* haveR, int* haveR1) {
+    *haveR = *haveR1 = 0;
+    if (Robj == Py_None) return 0;
+    Py_buffer bR;
+    if (PyObject_GetBuffer(Robj, &bR, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) return -1;
+    if ((bR.len != 72 && bR.len != 144) || bR.itemsize != 8) {
         PyBuffer_Release(&bR);
-        haveR = 1;
+        PyErr_SetString(PyExc_ValueError, "R must be a C-contiguous float64 array: 3x3 (cam0_R_p_c) or 2x3x3 (cam0, cam1)");
+        return -1;
     }
-    int bad = 0, rc = 0;
-    bad = b0.ndim != 2 || b0.itemsize != 1 || b0.shape[0] != H || b0.shape[1] != W || b0.strides[1] != 1 ||
-          b1.ndim != 2 || b1.itemsize != 1 || b1.shape[0] != H || b1.shape[1] != W || b1.strides[1] != 1 ||
-          b0.strides[0] != b1.strides[0] || b0.strides[0] < W;
-    if (!bad) {
-        const uint8_t* p0 = (const uint8_t*)b0.buf;
-        const uint8_t* p1 = (const uint8_t*)b1.buf;
-        const int stride = (int)b0.strides[0];
-        Py_BEGIN_ALLOW_THREADS
-        rc = avb_process_frame(ctx, &p0, &p1, stride, haveR ? R : NULL, haveR1 ? R + 9 : NULL);    /* staging + pipelined H2D + frame + D2H */
-        Py_END_ALLOW_THREADS
-    }
-    PyBuffer_Release(&b0);
-    PyBuffer_Release(&b1);
-    if (bad) {
-        PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride and equal row stride", H, W);
-        return NULL;
-    }
-    if (rc != AVB_OK) {
-        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
-        return NULL;
-    }
+    memcpy(R, bR.buf, (size_t)bR.len);
+    *haveR1 = bR.len == 144;
+    *haveR = 1;
+    PyBuffer_Release(&bR);
+    return 0;
+}
+
+/* (features, header tuple) of stream 0 from the result block of the frame just processed */
+static PyObject* frame_result(avb_ctx* ctx, PyObject* tpobj) {
     const avb_frame_header* h;
     const int64_t* ids;
     const double* meas;
-    rc = avb_get_result(ctx, 0, &h, &ids, &meas);
+    const int rc = avb_get_result(ctx, 0, &h, &ids, &meas);
     if (rc != AVB_OK) {
         PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
         return NULL;
@@ -256,6 +213,107 @@ static PyObject* py_process_frame(PyObject* self, PyObject* args) {
     Py_DECREF(list);
     Py_DECREF(hd);
     return out;
+}
+
+/* The two images of a single-stream frame through `call(ctx, &p0, &p1, stride, ...)`; returns the libavb status or -100
+ * with a Python error set. */
+typedef int (*frame_call)(avb_ctx*, const uint8_t* const*, const uint8_t* const*, int, const double*, const double*);
+static int submit_only(avb_ctx* ctx, const uint8_t* const* p0, const uint8_t* const* p1, int stride, const double* R0, const double* R1) {
+    (void)R0;
+    (void)R1;
+    return avb_submit_images(ctx, p0, p1, stride);
+}
+static int with_images(avb_ctx* ctx, PyObject* img0, PyObject* img1, frame_call call, const double* R0, const double* R1) {
+    int W = 0, H = 0, S = 0;
+    avb_get_geometry(ctx, &W, &H, &S);
+    if (S != 1) {
+        PyErr_SetString(PyExc_RuntimeError, "process_frame drives single-stream contexts");
+        return -100;
+    }
+    Py_buffer b0, b1;
+    if (PyObject_GetBuffer(img0, &b0, PyBUF_STRIDES) < 0) return -100;
+    if (PyObject_GetBuffer(img1, &b1, PyBUF_STRIDES) < 0) {
+        PyBuffer_Release(&b0);
+        return -100;
+    }
+    int rc = 0;
+    const int bad = b0.ndim != 2 || b0.itemsize != 1 || b0.shape[0] != H || b0.shape[1] != W || b0.strides[1] != 1 ||
+                    b1.ndim != 2 || b1.itemsize != 1 || b1.shape[0] != H || b1.shape[1] != W || b1.strides[1] != 1 ||
+                    b0.strides[0] != b1.strides[0] || b0.strides[0] < W;
+    if (!bad) {
+        const uint8_t* p0 = (const uint8_t*)b0.buf;
+        const uint8_t* p1 = (const uint8_t*)b1.buf;
+        const int stride = (int)b0.strides[0];
+        Py_BEGIN_ALLOW_THREADS
+        rc = call(ctx, &p0, &p1, stride, R0, R1);      /* staging + pipelined H2D [+ frame + D2H] */
+        Py_END_ALLOW_THREADS
+    }
+    PyBuffer_Release(&b0);
+    PyBuffer_Release(&b1);
+    if (bad) {
+        PyErr_Format(PyExc_RuntimeError, "images must be (%d, %d) uint8 arrays with unit column stride and equal row stride", H, W);
+        return -100;
+    }
+    if (rc != AVB_OK) {
+        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+        return -100;
+    }
+    return AVB_OK;
+}
+
+/* process_frame(ctx:int, img0, img1, R|None, fm_type) */
+static PyObject* py_process_frame(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    PyObject *img0, *img1, *Robj, *tpobj;
+    if (!PyArg_ParseTuple(args, "KOOOO", &handle, &img0, &img1, &Robj, &tpobj)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx || !PyType_Check(tpobj)) {
+        PyErr_SetString(PyExc_TypeError, "process_frame(ctx, img0, img1, R|None, FeatureMeasurement)");
+        return NULL;
+    }
+    double R[18];                       /* cam0_R_p_c [, cam1_R_p_c] */
+    int haveR, haveR1;
+    if (parse_R(Robj, R, &haveR, &haveR1) < 0) return NULL;
+    if (with_images(ctx, img0, img1, avb_process_frame, haveR ? R : NULL, haveR1 ? R + 9 : NULL) != AVB_OK) return NULL;
+    return frame_result(ctx, tpobj);
+}
+
+/* submit_images(ctx:int, img0, img1): the first half of process_frame (avb_submit_images): the copies are on their way
+ * and, in the steady state of a single stream, FAST runs behind cam0's; the arrays must stay alive until finish_frame. */
+static PyObject* py_submit_images(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    PyObject *img0, *img1;
+    if (!PyArg_ParseTuple(args, "KOO", &handle, &img0, &img1)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx) {
+        PyErr_SetString(PyExc_TypeError, "submit_images(ctx, img0, img1)");
+        return NULL;
+    }
+    if (with_images(ctx, img0, img1, submit_only, NULL, NULL) != AVB_OK) return NULL;
+    Py_RETURN_NONE;
+}
+
+/* finish_frame(ctx:int, R|None, fm_type) -> (features, header tuple): the second half (avb_process_submitted) */
+static PyObject* py_finish_frame(PyObject* self, PyObject* args) {
+    unsigned long long handle;
+    PyObject *Robj, *tpobj;
+    if (!PyArg_ParseTuple(args, "KOO", &handle, &Robj, &tpobj)) return NULL;
+    avb_ctx* ctx = (avb_ctx*)(uintptr_t)handle;
+    if (!ctx || !PyType_Check(tpobj)) {
+        PyErr_SetString(PyExc_TypeError, "finish_frame(ctx, R|None, FeatureMeasurement)");
+        return NULL;
+    }
+    double R[18];
+    int haveR, haveR1, rc;
+    if (parse_R(Robj, R, &haveR, &haveR1) < 0) return NULL;
+    Py_BEGIN_ALLOW_THREADS
+    rc = avb_process_submitted(ctx, haveR ? R : NULL, haveR1 ? R + 9 : NULL);
+    Py_END_ALLOW_THREADS
+    if (rc != AVB_OK) {
+        PyErr_Format(PyExc_RuntimeError, "libavb error %d: %s", rc, avb_last_error(ctx));
+        return NULL;
+    }
+    return frame_result(ctx, tpobj);
 }
 
 /* process_frames(ctx:int, imgs0:sequence, imgs1:sequence, R|None (S x 9 doubles, C-contiguous), fm_type)
@@ -597,6 +655,8 @@ static PyObject* py_png_unfilter(PyObject* self, PyObject* args) {
 
 static PyMethodDef methods[] = {
     {"process_frame", py_process_frame, METH_VARARGS, "One stereo frame: host images in, (FeatureMeasurement list, header) out."},
+    {"submit_images", py_submit_images, METH_VARARGS, "First half of process_frame: image intake (copies, cam0-only kernels)."},
+    {"finish_frame", py_finish_frame, METH_VARARGS, "Second half of process_frame: rotations in, (FeatureMeasurement list, header) out."},
     {"process_frames", py_process_frames, METH_VARARGS, "One stereo frame for every stream of a multi-stream context."},
     {"features_from_result", py_features_from_result, METH_VARARGS, "FeatureMeasurement list of stream s from the last frame."},
     {"features_from_arrays", py_features_from_arrays, METH_VARARGS, "FeatureMeasurement list from ids / measurement arrays."},

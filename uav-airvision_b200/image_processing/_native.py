@@ -14,7 +14,7 @@ EXPORTS = (
     'avb_abi_version', 'avb_last_error', 'avb_create', 'avb_destroy', 'avb_capacity', 'avb_num_cells',
     'avb_reset', 'avb_input_staging', 'avb_input_block_bytes', 'avb_input_rotation_offset',
     'avb_input_rotation_stride',
-    'avb_fill_rotations', 'avb_process_frame', 'avb_process_frame_device', 'avb_enqueue_frame_device',
+    'avb_fill_rotations', 'avb_process_frame', 'avb_submit_images', 'avb_process_submitted', 'avb_process_frame_device', 'avb_enqueue_frame_device',
     'avb_sync', 'avb_get_result', 'avb_get_result_prev', 'avb_get_features', 'avb_upload_stereo', 'avb_advance',
     'avb_build_pyramids', 'avb_download_level', 'avb_fast_detect', 'avb_klt_track', 'avb_stereo_match',
     'avb_undistort_points', 'avb_distort_points', 'avb_two_point_ransac', 'avb_last_frame_ms', 'avb_kernels_per_frame',
@@ -86,6 +86,8 @@ def load():
     lib.avb_input_rotation_stride.restype = C.c_size_t
     lib.avb_fill_rotations.argtypes = [vp, u8p, f64p, f64p]
     lib.avb_process_frame.argtypes = [vp, vp, vp, ip, f64p, f64p]
+    lib.avb_submit_images.argtypes = [vp, vp, vp, ip]
+    lib.avb_process_submitted.argtypes = [vp, f64p, f64p]
     lib.avb_process_frame_device.argtypes = [vp, vp]
     lib.avb_enqueue_frame_device.argtypes = [vp, vp]
     lib.avb_get_result.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -115,7 +117,7 @@ def load():
     lib.avb_store_image.restype = C.c_void_p
     lib.avb_process_frame_gather.argtypes = [vp, vp, f64p, f64p]
     lib.avb_enqueue_frame_gather.argtypes = [vp, vp, f64p, f64p]
-    if lib.avb_abi_version() != 4:
+    if lib.avb_abi_version() != 5:
         raise OSError('libavb.so ABI version mismatch: rebuild')
     _lib = lib
     return lib
@@ -271,6 +273,29 @@ class Context:
             self.staging[s, 0] = imgs0[s]
             self.staging[s, 1] = imgs1[s]
         self.process_staged(R_p_c0, R_p_c1)
+
+    def submit_images(self, imgs0, imgs1):
+        """First half of a frame straight from the callers' arrays (avb_submit_images): imgs0[s], imgs1[s] are (H, W) uint8
+        arrays with unit column stride and one common row stride; they must stay alive until process_submitted()."""
+        a0 = [np.asarray(a) for a in imgs0]
+        a1 = [np.asarray(a) for a in imgs1]
+        stride = a0[0].strides[0]
+        for a in a0 + a1:
+            if a.dtype != np.uint8 or a.shape != (self.height, self.width) or a.strides != (stride, 1):
+                raise ValueError('images must be (H, W) uint8 arrays with unit column stride and equal row stride')
+        p0 = (C.c_void_p * self.S)(*[a.ctypes.data for a in a0])
+        p1 = (C.c_void_p * self.S)(*[a.ctypes.data for a in a1])
+        self._submitted = (a0, a1)                      # keeps the arrays alive
+        self._ck(self._lib.avb_submit_images(self._h, p0, p1, int(stride)))
+
+    def process_submitted(self, R_p_c0=None, R_p_c1=None):
+        """Second half (avb_process_submitted): rotations in, results in host memory when it returns."""
+        R = None if R_p_c0 is None else np.ascontiguousarray(R_p_c0, dtype=np.float64).reshape(-1)
+        R1 = None if (R is None or R_p_c1 is None) else np.ascontiguousarray(R_p_c1, dtype=np.float64).reshape(-1)
+        try:
+            self._ck(self._lib.avb_process_submitted(self._h, _ptr(R), _ptr(R1)))
+        finally:
+            self._submitted = None
 
     def process_gather(self, image_addrs, R_p_c0=None, R_p_c1=None, wait=True):
         """One frame from device-resident images: image_addrs = uint64[S, 2] device addresses (FrameStore.addr rows).

@@ -125,13 +125,21 @@ class ImageProcessingPipeline:
         imu = self.imu_processor
         imu.cam0_prev_img_msg = self.prev_cam0_msg
         imu.cam0_curr_img_msg = cam0_msg
-        R = None
-        if not self.first_frame:
-            R, R1 = imu.integrate_imu_data()
-            if ctx.ransac:              # the RANSAC kernel compensates each camera with its own gyro rotation
-                R = np.ascontiguousarray(np.stack([R, R1]), dtype=np.float64)
-        # host images -> pinned staging -> H2D -> CUDA-graph frame -> D2H -> FeatureMeasurement list, all in C
-        feats, hdr = _avbhost.process_frame(ctx._h.value, cam0_msg.image, cam1_msg.image, R, FeatureMeasurement)
+        # host images -> pinned staging -> H2D -> CUDA-graph frame -> D2H -> FeatureMeasurement list, all in C.  The
+        # image copies (and FAST behind cam0's) go out first; the gyro window is integrated while they are on the bus
+        # (the reference integrates at the top of stereo_callback, pipeline.py:52-55: same inputs, same result).
+        h = ctx._h.value
+        if self.first_frame:
+            feats, hdr = _avbhost.process_frame(h, cam0_msg.image, cam1_msg.image, None, FeatureMeasurement)
+        else:
+            _avbhost.submit_images(h, cam0_msg.image, cam1_msg.image)
+            R = None
+            try:
+                R, R1 = imu.integrate_imu_data()
+                if ctx.ransac:          # the RANSAC kernel compensates each camera with its own gyro rotation
+                    R = np.ascontiguousarray(np.stack([R, R1]), dtype=np.float64)
+            finally:                    # a submitted frame is always finished (identity rotation if the window failed)
+                feats, hdr = _avbhost.finish_frame(h, R, FeatureMeasurement)
         self.next_feature_id = hdr[1]
         if not self.first_frame:
             nf = self.num_features
