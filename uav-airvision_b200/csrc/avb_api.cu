@@ -792,15 +792,23 @@ static int submit_images(avb_ctx* c, const uint8_t* const* img0, const uint8_t* 
         const uint8_t *src0 = img0[0], *src1 = img1[0];
         if (!src0 || !src1) return fail(c, AVB_E_INVALID, "null image pointer (stream 0)");
         const bool pin0 = stride == g.W && is_page_locked(c, src0, ib), pin1 = stride == g.W && is_page_locked(c, src1, ib);
-        if (!pin1) c->copier.post(c->h_in + ib, src1, g.W, g.H, stride);       // the helper stages cam1 meanwhile
         int rc = AVB_OK;
         auto ck = [&](cudaError_t e, const char* what) {
             if (e != cudaSuccess && rc == AVB_OK) rc = fail(c, AVB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
         };
+        // Pageable (or strided) images are staged into the pinned block by two cores at once, each image split in a top
+        // and a bottom half: cam0 is what the GPU waits for first (FAST runs behind its copy), so both cores work on it
+        // before either touches cam1 (one core per image put cam0 on the bus 10 us later).
+        const int h_top = g.H / 2, h_bot = g.H - h_top;
+        auto stage = [&](uint8_t* dst, const uint8_t* src) {
+            c->copier.post(dst + (size_t)h_top * g.W, src + (size_t)h_top * stride, g.W, h_bot, stride);
+            CopyWorker::copy(dst, src, g.W, h_top, stride);
+            c->copier.wait();
+        };
         if (pin0) {
             ck(cudaMemcpyAsync(c->d.in[p], src0, ib, cudaMemcpyHostToDevice, c->st), "H2D cam0");
         } else {
-            CopyWorker::copy(c->h_in, src0, g.W, g.H, stride);
+            stage(c->h_in, src0);
             ck(cudaMemcpyAsync(c->d.in[p], c->h_in, ib, cudaMemcpyHostToDevice, c->st), "H2D cam0");
         }
         ck(cudaEventRecord(c->ev_cam0, c->st), "event");
@@ -811,7 +819,7 @@ static int submit_images(avb_ctx* c, const uint8_t* const* img0, const uint8_t* 
         if (pin1) {
             ck(cudaMemcpyAsync(c->d.in[p] + ib, src1, ib, cudaMemcpyHostToDevice, c->st), "H2D cam1");
         } else {
-            c->copier.wait();
+            stage(c->h_in + ib, src1);
             ck(cudaMemcpyAsync(c->d.in[p] + ib, c->h_in + ib, ib, cudaMemcpyHostToDevice, c->st), "H2D cam1");
         }
         if (rc != AVB_OK) {
